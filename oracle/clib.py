@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE -- ctypes loader for oracle/_build/libfrx_oracle.so (the plain-C restatement
+in oracle/frx_oracle.c).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs may import this."""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, '_build', 'libfrx_oracle.so')
+RULE_CODE = {'caputo': 0, 'rectangle': 1, 'trapezoidal': 2, 'simpson': 3}
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, 'frx_oracle.c')
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(['make', '-C', _HERE, '-B', '-s'])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        dp, lp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long), ctypes.POINTER(ctypes.c_int)
+        L.orc_tgamma.restype = ctypes.c_double
+        L.orc_tgamma.argtypes = [ctypes.c_double]
+        L.orc_left_layout.argtypes = [ctypes.c_int, ctypes.c_double, ip, ip]
+        L.orc_left_weights.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ip, ip, dp]
+        L.orc_tables.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long, dp, dp, dp, dp, dp]
+        L.orc_history_rows_naive.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, dp, ctypes.c_long,
+                                             lp, ctypes.c_long, dp, ctypes.c_int]
+        L.orc_history_full.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long, dp,
+                                       ctypes.c_long, ctypes.c_long, ctypes.c_long, dp, ctypes.c_long, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _raise(rc):
+    if rc == -3:
+        raise ZeroDivisionError('float division by zero')
+    if rc == -1:
+        raise KeyError('unknown rule')
+    if rc:
+        raise ValueError('settings outside the domain of the rule (rc=%d)' % rc)
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def tgamma(x):
+    return lib().orc_tgamma(float(x))
+
+
+def left_arrays(rule, settings):
+    """(first_offset, np.float64[count]) of the reference's create_left_stencil(rule, settings)."""
+    alpha, lf, res = settings
+    code = RULE_CODE[rule]
+    if res == 0:
+        raise ZeroDivisionError('float division by zero')
+    first, count = ctypes.c_int(), ctypes.c_int()
+    w = np.empty(int(res) + 2, dtype=np.float64)
+    _raise(lib().orc_left_weights(code, float(alpha), float(lf), float(res), ctypes.byref(first),
+                                  ctypes.byref(count), _dp(w)))
+    return first.value, w[:count.value].copy()
+
+
+def right_arrays(rule, settings):
+    first, w = left_arrays(rule, settings)           # equation.py:32-39
+    return -(first + len(w) - 1), (w * -1.)[::-1].copy()
+
+
+def riesz_caputo_arrays(rule, settings):
+    """equation.py:13-25 with Python-float scalar arithmetic (identical to oracle/ref_port.py)."""
+    alpha = settings[0]
+    first, w = left_arrays(rule, settings)
+    n = math.floor(alpha) + 1.
+    K = 1. / 2. * math.gamma(2. - alpha) / math.gamma(2.)
+    sgn = (-1.) ** n
+    left = {first + i: float(x) for i, x in enumerate(w)}
+    lo = min(first, -(first + len(w) - 1))
+    out = []
+    for o in range(lo, -lo + 1):
+        a = left.get(o)
+        b = sgn * (left[-o] * -1.) if -o in left else None
+        out.append(K * (a if b is None else (b if a is None else a + b)))
+    return lo, np.array(out)
+
+
+def tables(rule, alpha, h, N):
+    cA, cB = np.zeros(N), np.zeros(N)
+    w0, mult = np.zeros(N + 1), np.zeros(N + 1)
+    cm1 = ctypes.c_double()
+    _raise(lib().orc_tables(RULE_CODE[rule], float(alpha), float(h), N, _dp(cA), _dp(cB), _dp(w0), _dp(mult),
+                            ctypes.byref(cm1)))
+    return cA, cB, w0, mult, cm1.value
+
+
+def history_rows_naive(rule, alpha, h, g, rows, n_threads=0):
+    """The reference's own algorithm: every row rebuilds its stencil (O(i) pow) and sums."""
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    y = np.empty(len(rows))
+    lib().orc_history_rows_naive(RULE_CODE[rule], float(alpha), float(h), _dp(g), len(g),
+                                 rows.ctypes.data_as(ctypes.POINTER(ctypes.c_long)), len(rows), _dp(y), n_threads)
+    return y
+
+
+def history_full(rule, alpha, h, N, g, n_threads=0):
+    """Same values for rows 0..N (row 0 = 0), table-accelerated; g is [n_g] or [n_fields, n_g]."""
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    g2 = g.reshape(-1, g.shape[-1])
+    y = np.empty((g2.shape[0], N + 1))
+    _raise(lib().orc_history_full(RULE_CODE[rule], float(alpha), float(h), N, _dp(g2), g2.shape[1], g2.shape[0],
+                                  g2.shape[1], _dp(y), N + 1, n_threads))
+    return y.reshape(g.shape[:-1] + (N + 1,))
