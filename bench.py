@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- the fractional-operator hot path on B200, one JSON line on rank 0.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], "cfg 2"): growing-history 'caputo' fractional derivative of one
+smooth synthetic field on N_NODES = 1e5 nodes, FP64.  One step = weight-table generation (K1) + field
+padding + history sum (K2 main + fix-up) for `--alphas-per-gpu` values of alpha per GPU (default 1).
+With N > 1 GPUs the alphas form a sweep dealt in contiguous blocks to the ranks (cfg 5 pattern, weak
+scaling) and every step ends with an NCCL all_gather of the per-rank results.
+Metric: node-evals/s (one node-eval = one output y_i, i.e. one full history row).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_NODES = 100000
+RULE = 'caputo'
+METRIC = 'fractional_history_node_evals_per_sec'
+UNIT = 'node-evals/s'
+FLUSH_BYTES = 256 << 20      # > 126 MB L2
+
+
+def smooth_field_np(n, h):
+    import numpy as np
+    x = np.arange(n, dtype=np.float64) * h
+    return 3.0 * np.cos(3.0 * x) + 2.0 * x      # g = f' for f = sin 3x + x^2 (SURVEY.md 8(d) cfg 2)
+
+
+def workload_alphas(n_total):
+    import numpy as np
+    return np.array([0.5]) if n_total == 1 else np.linspace(0.1, 0.9, n_total)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, power, reasons = [], None, [], set()
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9 or not (t_begin - 0.05 <= t <= t_end + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm), 'power_w_max': max(power) if power else None}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs: the oracle (plain-C restatement of the reference's algorithm: every row rebuilds its stencil
+# with O(i) pow calls, then sums), all host threads, on a bounded row sample, extrapolated by sum(i+1)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_leg(budget_s):
+    import numpy as np
+    from oracle import clib
+    h = 1.0 / N_NODES
+    g = smooth_field_np(N_NODES + 2, h)
+    cores = clib.num_threads()
+    # calibrate on a thin sample, then size the stride for the time budget
+    rows = np.arange(4096, N_NODES + 1, 4096, dtype=np.int64)
+    t0 = time.perf_counter()
+    clib.history_rows_naive(RULE, 0.5, h, g, rows)
+    t_cal = time.perf_counter() - t0
+    w_cal = float(np.sum(rows + 1.0))
+    total_w = N_NODES * (N_NODES + 3) / 2.0
+    per_weight = t_cal / w_cal
+    stride = int(max(1, math.ceil(total_w * per_weight / budget_s)))
+    rows = np.arange(stride, N_NODES + 1, stride, dtype=np.int64)
+    if rows[-1] != N_NODES:
+        rows = np.append(rows, N_NODES)
+    t0 = time.perf_counter()
+    y = clib.history_rows_naive(RULE, 0.5, h, g, rows)
+    dt = time.perf_counter() - t0
+    t_full = dt * total_w / float(np.sum(rows + 1.0))
+    assert np.all(np.isfinite(y))
+    return {'value': N_NODES / t_full, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': 'oracle/frx_oracle.c orc_history_rows_naive (reference algorithm: stencil of Settings(alpha,i*h,i) '
+                      'rebuilt per row), OpenMP %d threads, rows i = %d*k (%d rows, %.1f s), full N=1e5 job extrapolated by '
+                      'sum(i+1)' % (cores, stride, len(rows), dt),
+            'seconds_sample': dt, 'seconds_full_extrapolated': t_full}
+
+
+def python_reference_leg():
+    """The same path in pure Python (oracle/ref_port.py, bit-identical to the unmodified reference):
+    what a user of the reference actually waits for.  Three rows, one core, extrapolated."""
+    from oracle import ref_port
+    h = 1.0 / N_NODES
+    g = list(smooth_field_np(N_NODES + 2, h))
+    rows = (20000, 40000)
+    t0 = time.perf_counter()
+    ref_port.history(RULE, 0.5, h, g, rows)
+    dt = time.perf_counter() - t0
+    t_full = dt * (N_NODES * (N_NODES + 3) / 2.0) / sum(i + 1.0 for i in rows)
+    return {'value': N_NODES / t_full, 'unit': UNIT, 'cores': 1, 'seconds_full_extrapolated': t_full}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    steps, warmup = args.steps, args.warmup
+    budget = max(0.5, min(4.0, 150.0 / (steps + warmup)))
+    vals = []
+    last = None
+    for k in range(warmup + steps):
+        last = cpu_reference_leg(budget)
+        if k >= warmup:
+            vals.append(last['seconds_full_extrapolated'])
+    t_full = sum(vals) / len(vals)
+    value = N_NODES / t_full
+    last['value'] = value
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': t_full * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(1, 1),
+        'cpu_baseline': last,
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': 'the reference is pure Python with an absent dependency (fdm); this arm times the C port of its '
+                'algorithm (bit-identical results, tests/test_oracle_golden.py) on all host threads; each step is a '
+                'bounded row sample extrapolated to the full N=1e5 job',
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(world, alphas_per_gpu):
+    return {
+        'workload': 'cfg2: 1D fractional derivative history sum, N=1e5 nodes, single smooth field '
+                    "g=3cos3x+2x, rule 'caputo', FP64; %d alpha per GPU (%s); step = K1 weight tables + K2 history sum%s"
+                    % (alphas_per_gpu, 'alpha=0.5' if world * alphas_per_gpu == 1 else
+                       'alpha sweep linspace(0.1,0.9,%d) in contiguous blocks per rank' % (world * alphas_per_gpu),
+                       '' if world == 1 else ' + NCCL all_gather of results'),
+        'n_nodes': N_NODES, 'n_fields': 1, 'alphas_per_gpu': alphas_per_gpu, 'rule': RULE,
+        'l2': 'flushed between timed steps by writing a %d MiB buffer' % (FLUSH_BYTES >> 20),
+        'parallelism': 'independent alpha per GPU' if world > 1 else 'single GPU',
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fractulus_b200 import _lib, batched, sweep
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- fractulus_b200 has no CPU path')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    A = args.alphas_per_gpu
+    steps, warmup = args.steps, max(args.warmup, 3)
+    h = 1.0 / N_NODES
+    alphas = workload_alphas(world * A)
+    b, e = sweep.partition(len(alphas), world, rank)
+    my_alphas = torch.as_tensor(alphas[b:e], device=dev)
+    g_host = torch.from_numpy(smooth_field_np(N_NODES + 2, h)).pin_memory()
+    g = g_host.to(dev)
+    y = torch.empty((A, 1, N_NODES + 1), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * A, N_NODES + 1), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    ctx = _lib.context(local_rank)
+
+    def step():
+        batched.history(RULE, my_alphas, h, g, N=N_NODES, out=y, validate=False)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y.view(A, N_NODES + 1))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_load0 = time.time()
+    # warm-up: W steps, and at least ~1 s of load so the sampled clocks are clocks under load
+    t0 = time.perf_counter()
+    n = 0
+    while n < warmup or time.perf_counter() - t0 < 1.0:
+        step()
+        n += 1
+        if n % 16 == 0:
+            torch.cuda.synchronize()
+    barrier()
+
+    # ---- timed region: exactly K steps, device time per step, L2 flushed between steps -------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    launches0 = ctx.launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count() - launches0
+    ms = [a.elapsed_time(b_) for a, b_ in ev]
+    ms_per_step = sum(ms) / steps
+    if world > 1:
+        t = torch.tensor([ms_per_step], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = t.item()
+    value = world * A * N_NODES / (ms_per_step * 1e-3)
+
+    # ---- per-kernel pass: same K steps with CUDA events around every kernel (roofline numbers) -----
+    ctx.set_timing(True)
+    for k in range(steps):
+        flush.zero_()
+        batched.history(RULE, my_alphas, h, g, N=N_NODES, out=y, validate=False)
+    ktimes = ctx.kernel_times()
+    ctx.set_timing(False)
+    t_load1 = time.time()
+    clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
+
+    # ---- e2e: host buffers in, host buffers out, through the public host-buffer API ---------------
+    g_np = g_host.numpy()
+    if world == 1:
+        def e2e_step():
+            return batched.history_host(RULE, alphas[b:e], h, g_np, N=N_NODES, device=local_rank)
+        h2d = 8 * (N_NODES + 2) + 8 * A
+        d2h = 8 * (N_NODES + 1) * A
+    else:
+        def e2e_step():
+            return sweep.history_sweep(RULE, alphas, h, g_np, N=N_NODES)
+        h2d = 8 * (N_NODES + 2)
+        d2h = 8 * (N_NODES + 1) * A * world
+    for _ in range(3):
+        y_e2e = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y_e2e = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e_value = world * A * N_NODES / e2e_s
+    # the host-buffer path and the device path give the same bits
+    y_dev = y.cpu().numpy().reshape(A, N_NODES + 1)
+    same = bool(np.array_equal(np.asarray(y_e2e).reshape(-1, N_NODES + 1)[b:e], y_dev, equal_nan=True))
+
+    if rank == 0:
+        peak_dfma, peak_dmma = ctx.fp64_peak()
+        main_ms, main_calls = ktimes['history_main']
+        main_avg_ms = main_ms / max(main_calls, 1)
+        algo_flop = A * (N_NODES * (N_NODES + 1) / 2.0) * 2.0        # N(N+1)/2 FMA per (alpha, field)
+        achieved = algo_flop / (main_avg_ms * 1e-3) / 1e12
+        per_step_kernel_ms = {k: v[0] / steps for k, v in ktimes.items() if v[1]}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        algo_bytes = A * 8.0 * (N_NODES + 1) + 8.0 * (N_NODES + 2)
+        roofline = {
+            'kernel': 'frx_k2_history_main', 'bound': 'fp64', 'achieved': achieved, 'peak': peak_dfma,
+            'unit': 'TFLOP/s', 'frac': achieved / peak_dfma if peak_dfma else None,
+            'traffic': K2_DRAM_TRAFFIC_BYTES,
+            'peak_source': 'measured in this run: register-only DFMA probe (frx_measure_fp64_peak); '
+                           'MEASURED_PEAKS.json has no FP64 figure (bf16/HBM only); DMMA probe %.2f TFLOP/s' % peak_dmma,
+            'algorithmic_flop_per_launch': algo_flop, 'algorithmic_bytes_per_launch': algo_bytes,
+            'kernel_ms': main_avg_ms, 'kernel_share_of_step': main_avg_ms / sum(per_step_kernel_ms.values()),
+            'per_step_kernel_ms': per_step_kernel_ms,
+            'hbm_view': {'achieved_gbs': algo_bytes / (main_avg_ms * 1e-3) / 1e9, 'peak_gbs': peaks.get('hbm_gbs'),
+                         'note': 'intensity ~6e3 flop/B: not HBM bound'},
+            'timing': 'per-kernel CUDA events on the launching stream, separate pass of the same K steps',
+        }
+        cpu = cpu_reference_leg(8.0)
+        try:
+            cpu['python_port'] = python_reference_leg()
+        except Exception as ex:      # never let the informational leg break the line
+            cpu['python_port'] = {'error': repr(ex)}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(world, A),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': e2e_s * 1e3, 'api': 'frx_history_host (C ABI, host buffers)' if world == 1 else
+                    'fractulus_b200.sweep.history_sweep (host field in, gathered host result out)',
+                    'bitwise_equal_to_device_path': same},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+            'wall_s_timed_region': wall, 'ms_per_step_min': min(ms), 'ms_per_step_max': max(ms),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of frx_k2_history_main per launch from the committed
+# `ncu --set full` capture (profiles/); None until a capture exists.
+K2_DRAM_TRAFFIC_BYTES = None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=('b200', 'reference'))
+    ap.add_argument('--alphas-per-gpu', type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

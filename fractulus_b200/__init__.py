@@ -1,0 +1,5 @@
+"""fractulus_b200 -- B200 (sm_100a) implementation of the fractional-operator hot path of
+szajek/fractulus.  ``from fractulus_b200 import *`` gives the reference's four public names
+(reference fractulus/__init__.py:1); ``fractulus_b200.batched`` is the tensor-level API."""
+from .equation import *          # noqa: F401,F403  (Settings, create_*_stencil)
+from . import equation           # noqa: F401

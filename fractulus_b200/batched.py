@@ -1,0 +1,161 @@
+"""Tensor-level API over the C ABI (include/frx.h): the batched forms of the reference's path that the
+GPU actually runs.  PyTorch tensors are only the buffer carrier (device memory + streams); every
+number is produced by the hand-written kernels in fractulus_b200/csrc.
+
+    stencil_weights(approximation, side, alpha, lf, resolution)  -> row_ptr, offsets, weights   (K5)
+    weights_table(approximation, alpha, h, N)                    -> WeightTables                 (K1)
+    history(approximation, alpha, h, g)                          -> y[n_alpha, n_fields, N+1]    (K1+K2)
+    history_host(approximation, alpha, h, g)                     -> NumPy in / NumPy out, copies inside
+"""
+import collections
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+WeightTables = collections.namedtuple('WeightTables', ('cA', 'cB', 'w0', 'mult', 'cm1', 'N'))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _ctx_for(device):
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError('fractulus_b200 computes on CUDA devices only (got %s); there is no CPU path' % device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ctx = _lib.context(idx)
+    ctx.set_stream(torch.cuda.current_stream(idx).cuda_stream)
+    return ctx, idx
+
+
+def _as_f64(x, device):
+    return torch.as_tensor(x, dtype=torch.float64, device=device).contiguous()
+
+
+def _check_alpha_host(rule_name, alpha):
+    """Domain of the rules, enforced on the host like the reference would fail (equation.py:68 ...)."""
+    a = np.atleast_1d(np.asarray(alpha, dtype=np.float64))
+    if not np.all(np.isfinite(a)) or np.any(a < 0):
+        raise ValueError('alpha must be finite and >= 0')
+    if rule_name == 'rectangle' and np.any(a > 1.0):
+        raise ZeroDivisionError("'rectangle' with alpha > 1: 0.0 cannot be raised to a negative power")
+    if rule_name in ('trapezoidal', 'simpson') and np.any(a > 1.0):
+        raise ValueError("%r is only defined for alpha <= 1" % rule_name)
+    return a
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('no CUDA device: fractulus_b200 has no CPU path')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def stencil_weights(approximation, side, alpha, lf, resolution, device=None):
+    """K5 for a batch of Settings triples (1-D array-likes of equal length, host or device).
+    Returns (row_ptr[int64, host numpy], offsets[int32 cuda], weights[float64 cuda])."""
+    rule = _lib.RULES[approximation]
+    sd = _lib.SIDES[side]
+    device = torch.device(device) if device is not None else default_device()
+    a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha)
+    r_h = np.atleast_1d(np.asarray(resolution.cpu().numpy() if torch.is_tensor(resolution) else resolution,
+                                   dtype=np.float64))
+    n = len(a_h)
+    L = _lib.lib()
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    first, count = ctypes.c_int32(), ctypes.c_int32()
+    for s in range(n):
+        _lib.check(L.frx_stencil_layout(rule, sd, float(a_h[s]), float(r_h[s]), ctypes.byref(first), ctypes.byref(count)))
+        row_ptr[s + 1] = row_ptr[s] + count.value
+    ctx, idx = _ctx_for(device)
+    d_alpha, d_lf, d_res = _as_f64(a_h, device), _as_f64(np.atleast_1d(lf.cpu().numpy() if torch.is_tensor(lf) else lf), device), _as_f64(r_h, device)
+    offsets = torch.empty(int(row_ptr[-1]), dtype=torch.int32, device=device)
+    weights = torch.empty(int(row_ptr[-1]), dtype=torch.float64, device=device)
+    _lib.check(L.frx_stencil_weights(ctx.handle, rule, sd, n, _ptr(d_alpha), _ptr(d_lf), _ptr(d_res),
+                                     row_ptr.ctypes.data_as(_lib.c_int64_p), _ptr(offsets), _ptr(weights)))
+    return row_ptr, offsets, weights
+
+
+def weights_table(approximation, alpha, h, N, device=None):
+    """K1: Toeplitz tables of the growing-history operator for every alpha (see include/frx.h)."""
+    rule = _lib.RULES[approximation]
+    device = torch.device(device) if device is not None else default_device()
+    a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha)
+    n_alpha = len(a_h)
+    L = _lib.lib()
+    ldc = L.frx_table_ldc(int(N))
+    ldw = N + 1
+    ctx, idx = _ctx_for(device)
+    d_alpha = _as_f64(a_h, device)
+    cA = torch.empty((n_alpha, ldc), dtype=torch.float64, device=device)
+    cB = torch.empty((n_alpha, ldc), dtype=torch.float64, device=device) if approximation == 'simpson' else None
+    w0 = torch.empty((n_alpha, ldw), dtype=torch.float64, device=device)
+    mult = torch.empty((n_alpha, ldw), dtype=torch.float64, device=device)
+    cm1 = torch.empty((n_alpha,), dtype=torch.float64, device=device)
+    _lib.check(L.frx_weights_table(ctx.handle, rule, n_alpha, _ptr(d_alpha), float(h), int(N), _ptr(cA), _ptr(cB), ldc,
+                                   _ptr(w0), _ptr(mult), ldw, _ptr(cm1)))
+    return WeightTables(cA, cB, w0, mult, cm1, N)
+
+
+def history(approximation, alpha, h, g, N=None, out=None, validate=True):
+    """K1 + K2: y[a, f, i] = (D^alpha_a g_f)(x_i), i = 0..N, of the growing-history operator whose row i
+    is the reference stencil of Settings(alpha, i*h, i) (reference test/integration/test_equation.py:51-66).
+
+    alpha: scalar / 1-D (host or cuda); g: cuda float64 [n_g] or [n_fields, n_g]; N defaults to
+    n_g - 1 (n_g - 2 for 'simpson', whose odd rows read one node to the right)."""
+    rule = _lib.RULES[approximation]
+    if not torch.is_tensor(g) or not g.is_cuda:
+        raise TypeError('g must be a CUDA tensor (use history_host for NumPy buffers)')
+    device = g.device
+    g2 = g.to(torch.float64)
+    squeeze_f = g2.dim() == 1
+    g2 = g2.reshape(-1, g2.shape[-1]).contiguous()
+    n_fields, n_g = g2.shape
+    if N is None:
+        N = n_g - 1 - (1 if approximation == 'simpson' else 0)
+    if torch.is_tensor(alpha) and alpha.is_cuda and not validate:
+        d_alpha = alpha.to(torch.float64).reshape(-1).contiguous()
+        squeeze_a = alpha.dim() == 0
+    else:
+        a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha)
+        squeeze_a = np.ndim(alpha) == 0
+        d_alpha = _as_f64(a_h, device)
+    n_alpha = d_alpha.numel()
+    ctx, idx = _ctx_for(device)
+    if out is None:
+        out = torch.empty((n_alpha, n_fields, N + 1), dtype=torch.float64, device=device)
+    else:
+        assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == n_alpha * n_fields * (N + 1)
+    _lib.check(_lib.lib().frx_history(ctx.handle, rule, n_alpha, _ptr(d_alpha), float(h), int(N), n_fields, _ptr(g2),
+                                      n_g, n_g, _ptr(out), N + 1))
+    y = out.view(n_alpha, n_fields, N + 1)
+    if squeeze_f:
+        y = y[:, 0]
+    if squeeze_a:
+        y = y[0]
+    return y
+
+
+def history_host(approximation, alpha, h, g, N=None, device=None):
+    """Same operator through the host-buffer entry point frx_history_host: NumPy in, NumPy out, the
+    host<->device copies happen inside the call."""
+    rule = _lib.RULES[approximation]
+    a_h = np.ascontiguousarray(np.atleast_1d(np.asarray(alpha, dtype=np.float64)))
+    g_h = np.ascontiguousarray(g, dtype=np.float64)
+    g2 = g_h.reshape(-1, g_h.shape[-1])
+    n_fields, n_g = g2.shape
+    if N is None:
+        N = n_g - 1 - (1 if approximation == 'simpson' else 0)
+    ctx = _lib.context(device)
+    y = np.empty((len(a_h), n_fields, N + 1), dtype=np.float64)
+    _lib.check(_lib.lib().frx_history_host(ctx.handle, rule, len(a_h), a_h.ctypes.data_as(_lib.c_double_p), float(h),
+                                           int(N), n_fields, g2.ctypes.data_as(_lib.c_double_p), n_g, n_g,
+                                           y.ctypes.data_as(_lib.c_double_p), N + 1))
+    if g_h.ndim == 1:
+        y = y[:, 0]
+    if np.ndim(alpha) == 0:
+        y = y[0]
+    return y

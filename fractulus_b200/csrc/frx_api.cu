@@ -1,0 +1,245 @@
+// frx_api.cu -- context management, error reporting and the host-side integer/domain logic of the C ABI
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "frx_internal.h"
+#include "frx_rules.cuh"
+
+static thread_local char g_err[512] = "";
+
+void frx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int frx_version(void) { return FRX_VERSION; }
+extern "C" const char* frx_last_error_string(void) { return g_err; }
+
+extern "C" int frx_device_count(int* n) {
+    FRX_REQUIRE(n != nullptr, FRX_ERR_INVALID_ARG, "n_devices is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    *n = c;
+    return FRX_OK;
+}
+
+extern "C" int frx_ctx_create(int device, frx_ctx** out) {
+    FRX_REQUIRE(out != nullptr, FRX_ERR_INVALID_ARG, "out is NULL");
+    int n = 0;
+    frx_device_count(&n);
+    if (n <= 0) {
+        frx_set_error("no CUDA device visible: libfrx_b200 has no CPU path");
+        return FRX_ERR_NO_DEVICE;
+    }
+    FRX_REQUIRE(device >= 0 && device < n, FRX_ERR_INVALID_ARG, "device index out of range");
+    FRX_CUDA(cudaSetDevice(device));
+    frx_ctx* c = (frx_ctx*)calloc(1, sizeof(frx_ctx));
+    FRX_REQUIRE(c != nullptr, FRX_ERR_ALLOC, "host allocation failed");
+    c->device = device;
+    FRX_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    c->stream = 0;
+    *out = c;
+    return FRX_OK;
+}
+
+extern "C" int frx_ctx_destroy(frx_ctx* ctx) {
+    if (!ctx) return FRX_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < FRX_EV_POOL; ++i) {
+        if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
+        if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
+    }
+    free(ctx);
+    return FRX_OK;
+}
+
+extern "C" int frx_ctx_set_stream(frx_ctx* ctx, void* s) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    ctx->stream = (cudaStream_t)s;
+    return FRX_OK;
+}
+
+extern "C" int frx_ctx_synchronize(frx_ctx* ctx) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+extern "C" int frx_ctx_launch_count(frx_ctx* ctx, int64_t* n) {
+    FRX_REQUIRE(ctx != nullptr && n != nullptr, FRX_ERR_INVALID_ARG, "NULL argument");
+    *n = ctx->launches;
+    return FRX_OK;
+}
+
+int frx_timing_begin(frx_ctx* ctx, int kid) {
+    if (!ctx->timing) return FRX_OK;
+    if (ctx->ev_n == FRX_EV_POOL) {
+        int rc = frx_timing_flush(ctx);
+        if (rc) return rc;
+    }
+    int i = ctx->ev_n;
+    if (!ctx->ev0[i]) {
+        FRX_CUDA(cudaEventCreate(&ctx->ev0[i]));
+        FRX_CUDA(cudaEventCreate(&ctx->ev1[i]));
+    }
+    ctx->ev_kid[i] = kid;
+    FRX_CUDA(cudaEventRecord(ctx->ev0[i], ctx->stream));
+    return FRX_OK;
+}
+
+int frx_timing_end(frx_ctx* ctx) {
+    if (!ctx->timing) return FRX_OK;
+    FRX_CUDA(cudaEventRecord(ctx->ev1[ctx->ev_n], ctx->stream));
+    ctx->ev_n += 1;
+    return FRX_OK;
+}
+
+int frx_timing_flush(frx_ctx* ctx) {
+    for (int i = 0; i < ctx->ev_n; ++i) {
+        float ms = 0.f;
+        FRX_CUDA(cudaEventSynchronize(ctx->ev1[i]));
+        FRX_CUDA(cudaEventElapsedTime(&ms, ctx->ev0[i], ctx->ev1[i]));
+        ctx->k_ms[ctx->ev_kid[i]] += ms;
+        ctx->k_calls[ctx->ev_kid[i]] += 1;
+    }
+    ctx->ev_n = 0;
+    return FRX_OK;
+}
+
+extern "C" int frx_ctx_set_timing(frx_ctx* ctx, int on) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    int rc = frx_timing_flush(ctx);
+    if (rc) return rc;
+    ctx->timing = on ? 1 : 0;
+    if (on) {
+        for (int k = 0; k < FRX_K_COUNT; ++k) {
+            ctx->k_ms[k] = 0.0;
+            ctx->k_calls[k] = 0;
+        }
+    }
+    return FRX_OK;
+}
+
+extern "C" int frx_ctx_kernel_times(frx_ctx* ctx, double* ms, int64_t* calls) {
+    FRX_REQUIRE(ctx && ms && calls, FRX_ERR_INVALID_ARG, "NULL argument");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    int rc = frx_timing_flush(ctx);
+    if (rc) return rc;
+    for (int k = 0; k < FRX_K_COUNT; ++k) {
+        ms[k] = ctx->k_ms[k];
+        calls[k] = ctx->k_calls[k];
+    }
+    return FRX_OK;
+}
+
+int frx_ws_reserve(frx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return FRX_OK;
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->ws) {
+        FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+        FRX_CUDA(cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_bytes = 0;
+    }
+    size_t want = frx_align_up(bytes + bytes / 8, (size_t)1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        frx_set_error("device workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        return FRX_ERR_ALLOC;
+    }
+    ctx->ws_bytes = want;
+    return FRX_OK;
+}
+
+int frx_pinned_reserve(frx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return FRX_OK;
+    if (ctx->pinned) {
+        FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+        FRX_CUDA(cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+    }
+    size_t want = frx_align_up(bytes, (size_t)1 << 16);
+    FRX_CUDA(cudaMallocHost(&ctx->pinned, want));
+    ctx->pinned_bytes = want;
+    return FRX_OK;
+}
+
+// ---- domain checks mirroring what the reference does with such settings -------------------------
+int frx_check_rule_alpha(int rule, double alpha) {
+    if (rule < FRX_RULE_CAPUTO || rule > FRX_RULE_SIMPSON) {
+        frx_set_error("unknown approximation key (reference: KeyError at equation.py:29)");
+        return FRX_ERR_UNKNOWN_RULE;
+    }
+    if (!(alpha >= 0.0) || !isfinite(alpha)) {
+        frx_set_error("alpha must be finite and >= 0");
+        return FRX_ERR_DOMAIN;
+    }
+    if (rule == FRX_RULE_RECTANGLE && alpha > 1.0) {
+        frx_set_error("'rectangle' with alpha > 1: 0.0 ** negative (reference: ZeroDivisionError, equation.py:68)");
+        return FRX_ERR_ZERO_DIVISION;
+    }
+    if ((rule == FRX_RULE_TRAPEZOIDAL || rule == FRX_RULE_SIMPSON) && alpha > 1.0) {
+        frx_set_error("rule is only defined for alpha <= 1 (reference yields negative bases / complex weights)");
+        return FRX_ERR_DOMAIN;
+    }
+    return FRX_OK;
+}
+
+int frx_check_settings(int rule, double alpha, double resolution) {
+    int rc = frx_check_rule_alpha(rule, alpha);
+    if (rc) return rc;
+    if (resolution == 0.0) {
+        frx_set_error("resolution 0 (reference: ZeroDivisionError, equation.py:56,64,99,105)");
+        return FRX_ERR_ZERO_DIVISION;
+    }
+    if (!(resolution > 0.0) || resolution != floor(resolution) || resolution > 2.0e9) {
+        frx_set_error("resolution must be a positive integer value");
+        return FRX_ERR_DOMAIN;
+    }
+    if (rule == FRX_RULE_RECTANGLE && resolution < 2.0) {
+        frx_set_error("'rectangle' with resolution 1 asks for a uniform stencil with zero intervals");
+        return FRX_ERR_ZERO_DIVISION;
+    }
+    if (rule == FRX_RULE_SIMPSON && resolution < 2.0) {
+        frx_set_error("'simpson' with resolution 1: (m-2)**(3-alpha) has a negative base (complex in the reference)");
+        return FRX_ERR_DOMAIN;
+    }
+    return FRX_OK;
+}
+
+extern "C" int frx_stencil_layout(int rule, int side, double alpha, double resolution, int32_t* first_offset,
+                                  int32_t* count) {
+    FRX_REQUIRE(first_offset && count, FRX_ERR_INVALID_ARG, "NULL output pointer");
+    FRX_REQUIRE(side >= FRX_SIDE_LEFT && side <= FRX_SIDE_RIESZ_CAPUTO, FRX_ERR_INVALID_ARG, "bad side");
+    int rc = frx_check_settings(rule, alpha, resolution);
+    if (rc) return rc;
+    long long f, c;
+    frx_left_layout(rule, (long long)resolution, &f, &c);
+    long long last = f + c - 1;
+    if (side == FRX_SIDE_RIGHT) {              // o -> -o                                     equation.py:38-39
+        f = -last;
+    } else if (side == FRX_SIDE_RIESZ_CAPUTO) {  // union of left and mirrored left           equation.py:20-25
+        long long lo = f < -last ? f : -last;
+        f = lo;
+        c = -2 * lo + 1;
+    }
+    *first_offset = (int32_t)f;
+    *count = (int32_t)c;
+    return FRX_OK;
+}
+
+extern "C" int64_t frx_table_ldc(int64_t N);  // defined in frx_history.cu (depends on the tile sizes)

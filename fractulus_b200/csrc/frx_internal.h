@@ -1,0 +1,71 @@
+// frx_internal.h -- context object and error plumbing shared by the translation units of libfrx_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/frx.h"
+
+#define FRX_EV_POOL 64
+struct frx_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    int64_t launches;      // kernels launched through this context
+    // grow-only device workspace (weight tables, padded fields, stream-K partials)
+    void* ws;
+    size_t ws_bytes;
+    // small pinned host staging for the *_host entry points
+    void* pinned;
+    size_t pinned_bytes;
+    // optional per-kernel CUDA-event timing (frx_ctx_set_timing): bench.py's roofline numbers
+    int timing;
+    int ev_n;
+    cudaEvent_t ev0[FRX_EV_POOL], ev1[FRX_EV_POOL];
+    int ev_kid[FRX_EV_POOL];
+    double k_ms[FRX_K_COUNT];
+    int64_t k_calls[FRX_K_COUNT];
+};
+
+// a kernel launch bracketed by events when timing is on; counts the launch either way
+int frx_timing_begin(frx_ctx* ctx, int kid);
+int frx_timing_end(frx_ctx* ctx);
+int frx_timing_flush(frx_ctx* ctx);
+#define FRX_LAUNCH(ctx, kid, ...)                 \
+    do {                                          \
+        int rc_ = frx_timing_begin((ctx), (kid)); \
+        if (rc_) return rc_;                      \
+        __VA_ARGS__;                              \
+        (ctx)->launches += 1;                     \
+        FRX_CUDA(cudaGetLastError());             \
+        rc_ = frx_timing_end((ctx));              \
+        if (rc_) return rc_;                      \
+    } while (0)
+
+void frx_set_error(const char* fmt, ...);
+
+#define FRX_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            frx_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return FRX_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define FRX_REQUIRE(cond, code, msg)         \
+    do {                                     \
+        if (!(cond)) {                       \
+            frx_set_error("%s", msg);        \
+            return code;                     \
+        }                                    \
+    } while (0)
+
+// ensure ctx->ws holds at least `bytes`; contents are NOT preserved on growth
+int frx_ws_reserve(frx_ctx* ctx, size_t bytes);
+int frx_pinned_reserve(frx_ctx* ctx, size_t bytes);
+// host-side domain check of one Settings triple against the reference's behaviour
+int frx_check_settings(int rule, double alpha, double resolution);
+int frx_check_rule_alpha(int rule, double alpha);
+
+static inline size_t frx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -1,0 +1,172 @@
+// frx_weights.cu -- K5 (stencil weights for batches of Settings) and K1 (Toeplitz weight tables of the
+// growing-history operator).  FP64 ALU work: O(count) correctly rounded pow() per stencil / table.
+#include "frx_internal.h"
+#include "frx_rules.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// K5: one CTA per Settings(alpha, lf, resolution); thread k produces the node at offset first + k.
+// Replaces create_left_stencil / create_right_stencil / create_riesz_caputo_stencil
+// (reference fractulus/equation.py:13-39) including the scalar algebra the reference delegates to
+// fdm: mirror + multiply(-1.) (:38-39) and K * (left + (-1.)**n * right) flattened at 0 (:20-25).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) frx_k5_stencil_weights(int rule, int side, const double* __restrict__ alpha,
+                                                              const double* __restrict__ lf,
+                                                              const double* __restrict__ resolution,
+                                                              const int64_t* __restrict__ row_ptr,
+                                                              int32_t* __restrict__ offsets, double* __restrict__ weights) {
+    __shared__ frx_par P;
+    __shared__ double s_mult, s_K, s_sgn;
+    const int64_t s = blockIdx.x;
+    const double a = alpha[s], L = lf[s], res = resolution[s];
+    const long long p = (long long)res;
+    if (threadIdx.x == 0) {
+        P = frx_par_init(rule, a);
+        s_mult = frx_multiplier(P, L, res);
+        // Number(1. / 2. * math.gamma(2. - alpha) / math.gamma(2.))                     equation.py:23
+        s_K = FRX_DIV(FRX_MUL(0.5, frx_gamma_py(FRX_SUB(2.0, a))), 1.0);
+        s_sgn = (((long long)P.n) & 1) ? -1.0 : 1.0;  // (-1.) ** n                      equation.py:24
+    }
+    __syncthreads();
+    long long lfirst, lcount;
+    frx_left_layout(rule, p, &lfirst, &lcount);
+    const long long llast = lfirst + lcount - 1;
+    long long first = lfirst, count = lcount;
+    if (side == FRX_SIDE_RIGHT) {
+        first = -llast;
+    } else if (side == FRX_SIDE_RIESZ_CAPUTO) {
+        first = lfirst < -llast ? lfirst : -llast;
+        count = -2 * first + 1;
+    }
+    const int64_t base = row_ptr[s];
+    const double mult = s_mult;
+    for (long long k = threadIdx.x; k < count; k += blockDim.x) {
+        const long long o = first + k;
+        double w;
+        if (side == FRX_SIDE_LEFT) {
+            w = FRX_MUL(mult, frx_raw_at_offset(P, p, o));                 // multiplier * weight(node)   :78-79
+        } else if (side == FRX_SIDE_RIGHT) {
+            w = FRX_MUL(FRX_MUL(mult, frx_raw_at_offset(P, p, -o)), -1.0);  // symmetry + multiply(-1.)    :38-39
+        } else {
+            const bool in_left = (o >= lfirst && o <= llast), in_mirror = (-o >= lfirst && -o <= llast);
+            double acc = 0.0;
+            if (in_left) acc = FRX_MUL(mult, frx_raw_at_offset(P, p, o));
+            if (in_mirror) {
+                double r = FRX_MUL(s_sgn, FRX_MUL(FRX_MUL(mult, frx_raw_at_offset(P, p, -o)), -1.0));
+                acc = in_left ? FRX_ADD(acc, r) : r;
+            }
+            w = FRX_MUL(s_K, acc);
+        }
+        weights[base + k] = w;
+        if (offsets) offsets[base + k] = (int32_t)o;
+    }
+}
+
+extern "C" int frx_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_settings, const double* d_alpha,
+                                   const double* d_lf, const double* d_resolution, const int64_t* h_row_ptr,
+                                   int32_t* d_offsets, double* d_weights) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
+    FRX_REQUIRE(side >= FRX_SIDE_LEFT && side <= FRX_SIDE_RIESZ_CAPUTO, FRX_ERR_INVALID_ARG, "bad side");
+    FRX_REQUIRE(n_settings >= 0 && n_settings < ((int64_t)1 << 31), FRX_ERR_INVALID_ARG, "bad n_settings");
+    if (n_settings == 0) return FRX_OK;
+    FRX_REQUIRE(d_alpha && d_lf && d_resolution && h_row_ptr && d_weights, FRX_ERR_INVALID_ARG, "NULL buffer");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    // row_ptr travels through the workspace (it is host data describing the caller's layout)
+    size_t bytes = sizeof(int64_t) * (size_t)(n_settings + 1);
+    int rc = frx_ws_reserve(ctx, bytes);
+    if (rc) return rc;
+    FRX_CUDA(cudaMemcpyAsync(ctx->ws, h_row_ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FRX_LAUNCH(ctx, FRX_K_STENCIL,
+               frx_k5_stencil_weights<<<(unsigned)n_settings, 128, 0, ctx->stream>>>(
+                   rule, side, d_alpha, d_lf, d_resolution, (const int64_t*)ctx->ws, d_offsets, d_weights));
+    return FRX_OK;
+}
+
+extern "C" int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double alpha, double lf, double resolution,
+                                        int32_t capacity, int32_t* h_offsets, double* h_weights, int32_t* count) {
+    FRX_REQUIRE(ctx != nullptr && h_weights != nullptr && count != nullptr, FRX_ERR_INVALID_ARG, "NULL argument");
+    int32_t first, cnt;
+    int rc = frx_stencil_layout(rule, side, alpha, resolution, &first, &cnt);
+    if (rc) return rc;
+    *count = cnt;
+    FRX_REQUIRE(capacity >= cnt, FRX_ERR_INVALID_ARG, "capacity smaller than the stencil length");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    // workspace: [row_ptr (2 x i64, written by frx_stencil_weights)] [3 doubles] [weights] [offsets]
+    size_t off_par = 64, off_w = 128, off_o = off_w + frx_align_up(sizeof(double) * cnt, 64);
+    size_t total = off_o + sizeof(int32_t) * (size_t)cnt;
+    rc = frx_ws_reserve(ctx, total);
+    if (rc) return rc;
+    char* ws = (char*)ctx->ws;
+    double par[3] = {alpha, lf, resolution};
+    FRX_CUDA(cudaMemcpyAsync(ws + off_par, par, sizeof(par), cudaMemcpyHostToDevice, ctx->stream));
+    int64_t row_ptr[2] = {0, cnt};
+    const double* dpar = (const double*)(ws + off_par);
+    // (frx_stencil_weights puts row_ptr at ws + 0; the regions above do not overlap it)
+    rc = frx_stencil_weights(ctx, rule, side, 1, dpar, dpar + 1, dpar + 2, row_ptr, (int32_t*)(ws + off_o),
+                             (double*)(ws + off_w));
+    if (rc) return rc;
+    FRX_CUDA(cudaMemcpyAsync(h_weights, ws + off_w, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_offsets)
+        FRX_CUDA(cudaMemcpyAsync(h_offsets, ws + off_o, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: weight tables.  grid = (ceil(ldc / 128), n_alpha); thread <-> table index x, which serves both
+// as a distance d (cA/cB) and as a row number i (w0/mult).  Row i is Settings(alpha, fl(i*h), i).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) frx_k1_weights_table(int rule, const double* __restrict__ alpha, double h, int64_t N,
+                                                            double* __restrict__ cA, double* __restrict__ cB, int64_t ldc,
+                                                            double* __restrict__ w0, double* __restrict__ mult, int64_t ldw,
+                                                            double* __restrict__ cm1) {
+    __shared__ frx_par P;
+    const int64_t a = blockIdx.y;
+    if (threadIdx.x == 0) P = frx_par_init(rule, alpha[a]);
+    __syncthreads();
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= ldc) return;
+    const double xd = (double)x;
+    double ca = 0.0, cb = 0.0;
+    if (x < N) {
+        ca = frx_raw_toeplitz(P, xd, true);
+        if (rule == FRX_R_SIMPSON) cb = frx_raw_toeplitz(P, xd, false);
+    }
+    cA[a * ldc + x] = ca;
+    if (cB) cB[a * ldc + x] = cb;
+    if (x <= N) {
+        double w = 0.0, m = 0.0;
+        if (x >= 1) {
+            const double lf = FRX_MUL(xd, h);               // lf = i * h at the call site
+            m = frx_multiplier(P, lf, xd);
+            if (rule != FRX_R_RECTANGLE && !(rule == FRX_R_SIMPSON && x < 2)) w = frx_raw_first(P, xd);
+        }
+        w0[a * ldw + x] = w;
+        mult[a * ldw + x] = m;
+    }
+    if (x == 0 && cm1) cm1[a] = rule == FRX_R_SIMPSON ? frx_raw_right_of_point(P) : 0.0;
+}
+
+int frx_launch_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                             double* d_cA, double* d_cB, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
+                             double* d_cm1) {
+    dim3 grid((unsigned)((ldc + 127) / 128), (unsigned)n_alpha);
+    FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
+               frx_k1_weights_table<<<grid, 128, 0, ctx->stream>>>(rule, d_alpha, h, N, d_cA, d_cB, ldc, d_w0, d_mult,
+                                                                   ldw, d_cm1));
+    return FRX_OK;
+}
+
+extern "C" int frx_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                                 double* d_cA, double* d_cB, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
+                                 double* d_cm1) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
+    FRX_REQUIRE(n_alpha >= 0 && n_alpha <= 65535 && N >= 1, FRX_ERR_INVALID_ARG, "bad n_alpha (<= 65535) or N");
+    FRX_REQUIRE(ldc >= frx_table_ldc(N) && ldw >= N + 1, FRX_ERR_INVALID_ARG, "leading dimension too small");
+    FRX_REQUIRE(d_alpha && d_cA && d_w0 && d_mult, FRX_ERR_INVALID_ARG, "NULL buffer");
+    FRX_REQUIRE(rule != FRX_RULE_SIMPSON || (d_cB && d_cm1), FRX_ERR_INVALID_ARG, "'simpson' needs d_cB and d_cm1");
+    if (n_alpha == 0) return FRX_OK;
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    return frx_launch_weights_table(ctx, rule, n_alpha, d_alpha, h, N, d_cA, d_cB, ldc, d_w0, d_mult, ldw, d_cm1);
+}

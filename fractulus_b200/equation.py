@@ -1,0 +1,105 @@
+"""Drop-in for reference ``fractulus/equation.py``: the same four public names with the same
+signatures, keys and exceptions, the weights computed by hand-written sm_100a CUDA kernels
+(fractulus_b200/csrc/frx_weights.cu, kernel K5) behind the C ABI of include/frx.h.
+
+    Settings(alpha, lf, resolution)                      reference equation.py:10
+    create_left_stencil(approximation, settings)         reference equation.py:28-29
+    create_right_stencil(approximation, settings)        reference equation.py:32-35
+    create_riesz_caputo_stencil(approximation, settings) reference equation.py:13-17
+    approximation in 'caputo' | 'rectangle' | 'trapezoidal' | 'simpson'   reference equation.py:179-184
+
+The returned object is an ``fdm.equation.Stencil`` when the reference's ``fdm`` dependency is
+importable, otherwise the equivalent carrier of fractulus_b200/fdm_carrier.py.  There is no CPU path:
+without the CUDA library or without a GPU these functions raise.
+"""
+import collections
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+from . import _lib
+
+__all__ = 'Settings', 'create_left_stencil', 'create_right_stencil', 'create_riesz_caputo_stencil'
+
+# namedtuple type name 'CaputoSettings' as in the reference (equation.py:10)
+Settings = collections.namedtuple('CaputoSettings', ('alpha', 'lf', 'resolution'))
+
+
+def _carrier():
+    """(Stencil, Point) classes: real fdm unless absent / disabled / a test shim."""
+    mode = os.environ.get('FRACTULUS_B200_FDM', 'auto')
+    if mode != 'builtin':
+        try:
+            import fdm
+            if not getattr(fdm, '__fdm_shim__', False):
+                from fdm.equation import Stencil
+                from fdm.geometry import Point
+                return Stencil, Point, False
+        except ImportError:
+            if mode == 'external':
+                raise
+    from . import fdm_carrier
+    return fdm_carrier.Stencil, fdm_carrier.Point, True
+
+
+def _node_coordinates(approximation, side, lf, resolution, first, count):
+    """Node coordinates the way the reference places them: start + j * (end - start) / n_intervals
+    (equation.py:59,70-71,98,174-176 through Stencil.uniform, equation.py:81), mirrored by
+    symmetry(Point(0.)) for the right stencil (equation.py:38-39); Riesz-Caputo nodes are the union."""
+    p = int(resolution)
+    if approximation == 'rectangle':
+        start = -lf + lf / float(resolution)
+        intervals, end = p - 1, 0.
+    elif approximation == 'simpson' and p % 2 == 1:
+        start, end, intervals = -lf, lf / float(resolution), p + 1
+    else:
+        start, end, intervals = -lf, 0., p
+    delta = (end - start) / intervals
+    left_first = -(p - 1) if approximation == 'rectangle' else -p
+    left = {left_first + j: start + delta * j for j in range(intervals + 1)}
+    xs = []
+    for o in range(first, first + count):
+        if side == 'left':
+            xs.append(left[o])
+        elif side == 'right':
+            xs.append(0. * 2. - left[-o])
+        else:
+            xs.append(left[o] - 0. if o in left else (0. * 2. - left[-o]) - 0.)
+    return xs
+
+
+def _stencil(approximation, side, settings):
+    rule = _lib.RULES[approximation]          # KeyError for an unknown key, like _factory[approximation]
+    alpha, lf, resolution = settings          # same unpacking (and exceptions) as the reference
+    L = _lib.lib()
+    first, count = ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(L.frx_stencil_layout(rule, _lib.SIDES[side], float(alpha), float(resolution),
+                                    ctypes.byref(first), ctypes.byref(count)))
+    n = count.value
+    weights = np.empty(n, dtype=np.float64)
+    offsets = np.empty(n, dtype=np.int32)
+    got = ctypes.c_int32()
+    ctx = _lib.context()
+    _lib.check(L.frx_stencil_weights_host(ctx.handle, rule, _lib.SIDES[side], float(alpha), float(lf),
+                                          float(resolution), n, offsets.ctypes.data_as(_lib.c_int32_p),
+                                          weights.ctypes.data_as(_lib.c_double_p), ctypes.byref(got)))
+    assert got.value == n and offsets[0] == first.value
+    xs = _node_coordinates(approximation, side, lf, resolution, first.value, n)
+    Stencil, Point, builtin = _carrier()
+    if builtin:
+        return Stencil.from_layout(xs, weights, first.value, lf / float(resolution))
+    return Stencil({Point(x): float(w) for x, w in zip(xs, weights)})
+
+
+def create_left_stencil(approximation, settings):
+    return _stencil(approximation, 'left', settings)
+
+
+def create_right_stencil(approximation, settings):
+    return _stencil(approximation, 'right', settings)
+
+
+def create_riesz_caputo_stencil(approximation, settings):
+    return _stencil(approximation, 'riesz_caputo', settings)

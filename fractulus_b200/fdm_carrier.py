@@ -1,0 +1,174 @@
+"""Host-side carrier objects for the stencils this package returns.
+
+The reference hands its weights to the third-party package ``fdm`` (``fdm.equation.Stencil``,
+``fdm.equation.Number``, ``fdm.geometry.Point``: reference fractulus/equation.py:4-5) and its users
+compose them with ``fdm.Operator`` (reference fractulus/test/integration/test_equation.py:61-66,
+88-94).  ``fdm`` is not part of the reference checkout; when it is importable this package returns
+real ``fdm`` objects (see fractulus_b200/equation.py), otherwise these minimal equivalents, whose
+behaviour is exactly what the reference's call sites need:
+
+    Point(x, y=0, z=0)             hashable, tolerant equality, + - * by scalar
+    Stencil({Point: weight})       ._weights, .expand(point), .symmetry(point), .multiply(f), ==,
+                                   Stencil.uniform(left, right, n_intervals, provider), Stencil.central(span)
+    Number(value | callable)       .expand(point) -> {point: value}
+    Operator(stencil, element)     .expand(point): stencil applied to element
+    a + b, Number * element        lazy algebra with .to_stencil(origin)
+
+In addition a Stencil built by this package remembers its integer layout (``first_offset``, ``step``)
+and keeps its weights as a NumPy array (``weights_array``) so batched code never touches the dict.
+"""
+import numpy as np
+
+_ROUND = 9   # Points are identified after rounding: -0.6000000000000001 and -0.6 are the same node
+
+
+class Point(object):
+    __slots__ = ('x', 'y', 'z', '_key')
+
+    def __init__(self, x=0., y=0., z=0.):
+        self.x, self.y, self.z = x, y, z
+        self._key = (round(x, _ROUND) + 0., round(y, _ROUND) + 0., round(z, _ROUND) + 0.)
+
+    def __hash__(self):
+        return hash(self._key)
+
+    def __eq__(self, other):
+        return isinstance(other, Point) and self._key == other._key
+
+    def __ne__(self, other):
+        return not self == other
+
+    def __add__(self, other):
+        return Point(self.x + other.x, self.y + other.y, self.z + other.z)
+
+    def __sub__(self, other):
+        return Point(self.x - other.x, self.y - other.y, self.z - other.z)
+
+    def __mul__(self, scalar):
+        return Point(self.x * scalar, self.y * scalar, self.z * scalar)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, scalar):
+        return Point(self.x / scalar, self.y / scalar, self.z / scalar)
+
+    def __neg__(self):
+        return Point(-self.x, -self.y, -self.z)
+
+    def __iter__(self):
+        return iter((self.x, self.y, self.z))
+
+    def __repr__(self):
+        return 'Point(%r, %r, %r)' % (self.x, self.y, self.z)
+
+
+def _accumulate(into, node, weight):
+    if node in into:
+        into[node] = into[node] + weight
+    else:
+        into[node] = weight
+
+
+class Element(object):
+    def expand(self, point):
+        raise NotImplementedError
+
+    def __add__(self, other):
+        return LazyOperation('+', self, other)
+
+    def __mul__(self, other):
+        return LazyOperation('*', self, other)
+
+    def to_stencil(self, origin):
+        return Stencil({node - origin: w for node, w in self.expand(origin).items()})
+
+
+class Stencil(Element):
+    def __init__(self, weights, first_offset=None, step=None, weights_array=None):
+        self._weights = dict(weights)
+        self.first_offset = first_offset
+        self.step = step
+        self.weights_array = weights_array
+
+    @classmethod
+    def from_layout(cls, nodes_x, weights, first_offset, step):
+        """nodes_x: node coordinates; weights: float64 array (kept); integer layout remembered."""
+        w = np.asarray(weights, dtype=np.float64)
+        return cls({Point(float(x)): float(v) for x, v in zip(nodes_x, w)}, first_offset, step, w)
+
+    @classmethod
+    def uniform(cls, left, right, resolution, weights_provider):
+        span = right - left
+        delta = span / resolution
+        return cls({left + delta * i: weights_provider(i, left + delta * i) for i in range(int(resolution) + 1)})
+
+    @classmethod
+    def central(cls, span=1.):
+        return cls({Point(-span / 2.): -1. / span, Point(span / 2.): 1. / span})
+
+    def expand(self, point):
+        return {point + node: w for node, w in self._weights.items()}
+
+    def symmetry(self, point):
+        return Stencil({point * 2. - node: w for node, w in self._weights.items()})
+
+    def multiply(self, factor):
+        return Stencil({node: w * factor for node, w in self._weights.items()})
+
+    def __eq__(self, other):
+        return isinstance(other, Stencil) and self._weights == other._weights
+
+    def __ne__(self, other):
+        return not self == other
+
+    __hash__ = None
+
+    def __repr__(self):
+        return 'Stencil(%r)' % (self._weights,)
+
+
+class Number(Element):
+    def __init__(self, value):
+        self._value = value
+
+    def value_at(self, point):
+        return self._value(point) if callable(self._value) else self._value
+
+    def expand(self, point):
+        return {point: self.value_at(point)}
+
+
+class Operator(Element):
+    def __init__(self, stencil, element=None):
+        self._stencil = stencil
+        self._element = element
+
+    def expand(self, point):
+        outer = self._stencil.expand(point)
+        if self._element is None:
+            return outer
+        out = {}
+        for node, w in outer.items():
+            for inner, wi in self._element.expand(node).items():
+                _accumulate(out, inner, w * wi)
+        return out
+
+
+class LazyOperation(Element):
+    def __init__(self, op, left, right):
+        self._op, self._left, self._right = op, left, right
+
+    def expand(self, point):
+        a, b = self._left, self._right
+        if self._op == '+':
+            out = dict(a.expand(point))
+            for node, w in b.expand(point).items():
+                _accumulate(out, node, w)
+            return out
+        if isinstance(a, Number):
+            s = a.value_at(point)
+            return {node: s * w for node, w in b.expand(point).items()}
+        if isinstance(b, Number):
+            s = b.value_at(point)
+            return {node: w * s for node, w in a.expand(point).items()}
+        raise TypeError('only Number * element products are supported')

@@ -1,0 +1,67 @@
+"""Parameter sweeps across the GPUs of one box: one process per GPU (torch.distributed, NCCL over
+NVLink), independent problems dealt to ranks in contiguous blocks, no collective on the data path,
+one all_gather of the results at the end (BASELINE cfg 5).
+
+    partition(n_units, world, rank)            -> (begin, end) of this rank's contiguous block
+    history_sweep(approximation, alphas, h, g) -> y[n_alpha, N+1] for ALL alphas on every rank
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import batched
+
+
+def partition(n_units, world, rank):
+    """Contiguous block of units for `rank`: sizes differ by at most one, earlier ranks get the extra."""
+    base, extra = divmod(int(n_units), int(world))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def gather_blocks(local, n_total, group=None):
+    """all_gather of per-rank row blocks [n_local, M] of a partition() split into [n_total, M].
+    Equal blocks use one all_gather_into_tensor; ragged ones are padded to the largest block."""
+    world, rank = _world(group)
+    if world == 1:
+        return local
+    m = local.shape[1]
+    sizes = [partition(n_total, world, r) for r in range(world)]
+    nmax = max(e - b for b, e in sizes)
+    if all(e - b == nmax for b, e in sizes):
+        out = torch.empty((n_total, m), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    padded = torch.zeros((nmax, m), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    buf = torch.empty((world * nmax, m), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    return torch.cat([buf[r * nmax:r * nmax + (e - b)] for r, (b, e) in enumerate(sizes)], dim=0)
+
+
+def history_sweep(approximation, alphas, h, g, N=None, group=None, compute=None):
+    """Growing-history derivative of ONE field for many alpha, sharded over the ranks of `group`.
+
+    alphas: 1-D array-like (the same on every rank); g: NumPy array (host: copied in, result copied
+    out, like the reference's user would hold it) or CUDA tensor (result stays on the device).
+    `compute` (tests only) replaces the per-rank kernel call so the sharding/gather logic can run on
+    CPU tensors with the gloo backend."""
+    world, rank = _world(group)
+    alphas = np.ascontiguousarray(np.asarray(alphas, dtype=np.float64).reshape(-1))
+    begin, end = partition(len(alphas), world, rank)
+    host_io = not torch.is_tensor(g)
+    if compute is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+        g_dev = torch.as_tensor(np.asarray(g, dtype=np.float64)).to(dev, non_blocking=True) if host_io else g
+        local = batched.history(approximation, alphas[begin:end], h, g_dev, N=N) if end > begin else \
+            torch.empty((0, (N if N is not None else g_dev.shape[-1] - 1) + 1), dtype=torch.float64, device=dev)
+    else:
+        local = compute(alphas[begin:end], g)
+    full = gather_blocks(local, len(alphas), group)
+    return full.cpu().numpy() if host_io else full

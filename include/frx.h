@@ -1,0 +1,138 @@
+/* frx.h -- C ABI of libfrx_b200.so: the B200 (sm_100a) implementation of the fractional-operator hot
+ * path of szajek/fractulus.  Plain C, plain pointers and sizes; no torch / C++ types.
+ *
+ * The reference is pure Python and has no FFI of its own; each entry point below names the reference
+ * interface it replaces (file:line under the reference checkout).  The Python host layer
+ * (fractulus_b200/equation.py, fractulus_b200/batched.py) binds these with ctypes; INTEGRATION.md
+ * shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns FRX_OK (0) or a negative frx_status; frx_last_error_string() gives the
+ *     thread-local message of the last failure.
+ *   - "d_" pointers are device pointers on the context's device, "h_" pointers are host pointers.
+ *   - device-pointer entry points are asynchronous on the context's stream (frx_ctx_set_stream);
+ *     "_host" entry points copy in, compute, copy out and synchronise before returning.
+ *   - rule  : the reference's approximation key (fractulus/equation.py:179-184).
+ *   - side  : which of the reference's three stencil factories (equation.py:13,28,32).
+ *   - every weight is produced on the GPU; there is no CPU fallback anywhere in this library.
+ */
+#ifndef FRX_H
+#define FRX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRX_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    FRX_OK = 0,
+    FRX_ERR_CUDA = -1,          /* a CUDA runtime call failed (message has the CUDA error)          */
+    FRX_ERR_INVALID_ARG = -2,   /* null pointer, negative size, bad leading dimension ...            */
+    FRX_ERR_UNKNOWN_RULE = -3,  /* reference: KeyError from _factory[approximation], equation.py:29  */
+    FRX_ERR_ZERO_DIVISION = -4, /* reference: ZeroDivisionError (resolution 0, equation.py:56,64,99,105;
+                                   'rectangle' with alpha > 1, equation.py:68; 'rectangle' resolution 1) */
+    FRX_ERR_DOMAIN = -5,        /* settings for which the reference yields complex / undefined weights */
+    FRX_ERR_NO_DEVICE = -6,     /* no CUDA device: this library never computes on the CPU             */
+    FRX_ERR_ALLOC = -7          /* device workspace allocation failed                                 */
+} frx_status;
+
+typedef enum {                  /* keys of _factory, reference fractulus/equation.py:179-184 */
+    FRX_RULE_CAPUTO = 0,        /* _create_left_caputo_stencil,           equation.py:42-59   */
+    FRX_RULE_RECTANGLE = 1,     /* _create_left_rectangle_rule_stencil,   equation.py:62-73   */
+    FRX_RULE_TRAPEZOIDAL = 2,   /* _create_left_trapezoidal_rule_stencil, equation.py:84-100  */
+    FRX_RULE_SIMPSON = 3        /* _create_left_simpson_rule_stencil,     equation.py:103-176 */
+} frx_rule;
+
+typedef enum {
+    FRX_SIDE_LEFT = 0,          /* create_left_stencil,         equation.py:28-29 */
+    FRX_SIDE_RIGHT = 1,         /* create_right_stencil,        equation.py:32-39 */
+    FRX_SIDE_RIESZ_CAPUTO = 2   /* create_riesz_caputo_stencil, equation.py:13-25 */
+} frx_side;
+
+typedef struct frx_ctx frx_ctx; /* one per (host thread, device); not thread-safe across threads */
+
+/* ---- library / context ------------------------------------------------------------------------ */
+int frx_version(void);
+const char* frx_last_error_string(void);
+int frx_device_count(int* n_devices);
+int frx_ctx_create(int device, frx_ctx** out);
+int frx_ctx_destroy(frx_ctx* ctx);
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = legacy default */
+int frx_ctx_set_stream(frx_ctx* ctx, void* cuda_stream);
+int frx_ctx_synchronize(frx_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int frx_ctx_launch_count(frx_ctx* ctx, int64_t* n_launches);
+
+/* Per-kernel device timing with CUDA events on the context's stream (off by default; adds two event
+ * records per launch).  frx_ctx_kernel_times synchronises, then fills ms[k] / calls[k] for the kernel
+ * classes below, accumulated since timing was last switched on. */
+typedef enum {
+    FRX_K_WEIGHTS_TABLE = 0,   /* K1 */
+    FRX_K_PAD_FIELDS = 1,      /* K2 prep */
+    FRX_K_HISTORY_MAIN = 2,    /* K2 */
+    FRX_K_HISTORY_FIXUP = 3,   /* K2 split-tile fix-up */
+    FRX_K_STENCIL = 4,         /* K5 */
+    FRX_K_TOEPLITZ = 5,        /* K3 */
+    FRX_K_SOLVE = 6,           /* K4 */
+    FRX_K_OTHER = 7,
+    FRX_K_COUNT = 8
+} frx_kernel_class;
+int frx_ctx_set_timing(frx_ctx* ctx, int on);
+int frx_ctx_kernel_times(frx_ctx* ctx, double* ms /*[FRX_K_COUNT]*/, int64_t* calls /*[FRX_K_COUNT]*/);
+
+/* ---- integer layout (host-only integer logic, no GPU work) -------------------------------------
+ * The nodes of every reference stencil sit at consecutive integer multiples of lf/resolution:
+ * offsets first_offset .. first_offset+count-1 (reference equation.py:59,70-71,96-100,173-176 through
+ * _create_parametrized_stencil, equation.py:76-81; mirrored by equation.py:38-39; merged by :20-25). */
+int frx_stencil_layout(int rule, int side, double alpha, double resolution, int32_t* first_offset,
+                       int32_t* count);
+
+/* ---- K5: stencil weights for a batch of Settings(alpha, lf, resolution) ------------------------
+ * Replaces create_left_stencil / create_right_stencil / create_riesz_caputo_stencil
+ * (equation.py:13-39) for n_settings settings at once.  Stencil s occupies
+ * [row_ptr[s], row_ptr[s+1]) of d_offsets / d_weights, row_ptr[s+1]-row_ptr[s] == its layout count
+ * (host array, from frx_stencil_layout).  d_offsets may be NULL. */
+int frx_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_settings, const double* d_alpha,
+                        const double* d_lf, const double* d_resolution, const int64_t* h_row_ptr,
+                        int32_t* d_offsets, double* d_weights);
+/* one Settings triple, host buffers of `capacity` entries; *count receives the stencil length */
+int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double alpha, double lf, double resolution,
+                             int32_t capacity, int32_t* h_offsets, double* h_weights, int32_t* count);
+
+/* ---- K1: Toeplitz weight tables of the growing-history operator -------------------------------
+ * Row i of the history operator is the reference stencil of Settings(alpha, lf = i*h, resolution = i)
+ * (call pattern of reference fractulus/test/integration/test_equation.py:51-66).  Its raw weights
+ * depend on the distance d = i - j only, except node number 0 (equation.py:49,90,113-117), so for
+ * each alpha the operator is:   y_i = mult[i] * ( w0[i]*g_0 + sum_{d=0}^{i-1} c[d][j parity]*g_{i-d}
+ *                                                  + [simpson, i odd] cm1*g_{i+1} ).
+ *   d_cA[a*ldc + d], d = 0..N-1 : raw Toeplitz weights ('simpson': those multiplying even nodes j)
+ *   d_cB[a*ldc + d]             : 'simpson' only (odd nodes j); may be NULL for the other rules
+ *   d_w0[a*ldw + i], d_mult[a*ldw + i], i = 0..N : first-column raw weight and row multiplier
+ *   d_cm1[a]                    : 'simpson' right-of-point raw weight (equation.py:161-162), else 0
+ * ldc >= frx_table_ldc(N) (entries d >= N are written as 0), ldw >= N+1. */
+int64_t frx_table_ldc(int64_t N);
+int frx_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                      double* d_cA, double* d_cB, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
+                      double* d_cm1);
+
+/* ---- K2: history sum (lower-triangular Toeplitz mat-vec), few fields, many alpha ---------------
+ * y[(a*n_fields + f)*ldy + i] = D^alpha_a of field f at node i, i = 0..N, for the growing-history
+ * operator above; field f is g[f*ldg + j], j = 0..n_g-1 with n_g >= N+1 (N+2 for 'simpson').
+ * y_0 = 0; rows for which the reference cannot build a stencil ('rectangle' i=1, 'simpson' i=1) = NaN.
+ * Weight tables are generated on the fly inside the call (K1) into the context workspace. */
+int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy);
+int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_alpha, double h, int64_t N,
+                     int64_t n_fields, const double* h_g, int64_t ldg, int64_t n_g, double* h_y, int64_t ldy);
+
+/* ---- measurement aid ------------------------------------------------------------------------------
+ * Register-only probes of the FP64 DFMA pipe and of mma.sync m8n8k4 f64 (DMMA): the denominators of the
+ * FP64 rooflines bench.py reports (MEASURED_PEAKS.json carries no FP64 figure).  Best of `repeats`. */
+int frx_measure_fp64_peak(frx_ctx* ctx, int repeats, double* tflops_dfma, double* tflops_dmma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRX_H */
