@@ -54,6 +54,7 @@ extern "C" int frx_ctx_destroy(frx_ctx* ctx) {
     if (!ctx) return FRX_OK;
     cudaSetDevice(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->io) cudaFree(ctx->io);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < FRX_EV_POOL; ++i) {
         if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
@@ -161,6 +162,26 @@ int frx_ws_reserve(frx_ctx* ctx, size_t bytes) {
         return FRX_ERR_ALLOC;
     }
     ctx->ws_bytes = want;
+    return FRX_OK;
+}
+
+int frx_io_reserve(frx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->io_bytes) return FRX_OK;
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->io) {
+        FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+        FRX_CUDA(cudaFree(ctx->io));
+        ctx->io = nullptr;
+        ctx->io_bytes = 0;
+    }
+    size_t want = frx_align_up(bytes + bytes / 8, (size_t)1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->io, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        frx_set_error("device buffer allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        return FRX_ERR_ALLOC;
+    }
+    ctx->io_bytes = want;
     return FRX_OK;
 }
 

@@ -7,39 +7,84 @@
 //
 // FP64 DFMA-pipe bound (N = 1e5: 5e9 FMA over 1.6 MB of input), so the design goal is one DFMA per
 // (i, d) pair with as few other instructions as possible:
-//   * work unit  = kTI rows x kTD distances.  Units are laid out in a 1-D sequence (alpha, field, row
-//     tile, pass, distance chunk) and dealt in equal contiguous spans to a grid of
-//     sm_count * kCtasPerSm persistent CTAs (stream-K), which balances the triangle exactly.
-//   * inside a unit each thread owns kR consecutive rows (kR accumulators) and slides a register window
-//     of 2*kR field values: per kR distances it issues kR*kR DFMAs for kR/2 LDS.128 of field values and
-//     kR/2 broadcast LDS.128 of weights.
+//   * work unit  = TI rows x TD distances.  Units are laid out in a 1-D sequence (alpha, field, row
+//     tile, pass, distance chunk) and dealt in equal contiguous spans to a grid of exactly
+//     sm_count * CTAS_PER_SM persistent CTAs (stream-K), which balances the triangle; dynamic shared
+//     memory is sized so that exactly CTAS_PER_SM CTAs fit on an SM (all CTAs resident, evenly spread).
+//   * inside a unit each thread owns R consecutive rows (R accumulators) and slides a register window
+//     of 2R field values: per R distances it issues R*R DFMAs for R/2 LDS.128 of field values and
+//     R/2 broadcast LDS.128 of weights.
 //   * weights c[] and the field window are staged global -> shared with 16-byte cp.async into a double
-//     buffer; the field window is stored with 16 bytes of padding per 128-byte line so that the
-//     per-thread 64-byte chunks are bank-conflict free.
+//     buffer; each thread's 8R-byte chunk of the window is stored at a stride of 8R+16 bytes, which
+//     makes the per-thread LDS.128 bank-conflict free (consecutive lanes land on distinct 16-byte bank
+//     groups: stride/16 is odd).
 //   * the triangular edge and the first column are handled by zero padding (a padded copy of the field
-//     with g_j = 0 for j <= 0 is made by the prep kernel), so the inner loop has no predicates.
+//     with g_j = 0 for j <= 0 is made by the prepare kernel), so the inner loop has no predicates.
 //   * a row tile finished inside one CTA is scaled and written directly; a tile split between CTAs
-//     goes through per-CTA partial slots that a small fix-up kernel adds in CTA order -> bitwise
-//     deterministic results, no atomics.
+//     goes through per-CTA partial slots, and the LAST CTA to arrive (atomic ticket per tile) adds
+//     the slots in CTA order -> bitwise deterministic results, no floating-point atomics.
+//   * one prepare kernel per call generates the weight tables (K1), pads the fields and clears the
+//     tickets; one main kernel does everything else: 2 launches per call.
 #include <math.h>
+#include <stdlib.h>
 
 #include "frx_internal.h"
+#include "frx_table.cuh"
 
 namespace {
 
-constexpr int kR = 8;              // rows per thread
-constexpr int kNT = 128;           // threads per CTA
-constexpr int kTI = kR * kNT;      // rows per tile (1024)
-constexpr int kTD = 256;           // distances per unit
-constexpr int kCtasPerSm = 4;
-constexpr int kPadF = kTI + kTD;   // zero padding in front of every padded field
-constexpr int kChunkBytes = 8 * kR;
-constexpr int kWinElems = kTI + kTD;
-constexpr int kWinBytes = kWinElems * 8 + (kWinElems * 8 / 128) * 16;  // +16 B per 128 B line
-constexpr int kStageBytes = kTD * 8 + kWinBytes;
+constexpr int kNT = 128;      // threads per CTA
+constexpr int kLdcQuantum = 256;
 
-static_assert(kTI % kTD == 0, "tile rows must be a multiple of the distance chunk");
-static_assert((kTD / kR) % 2 == 0, "inner loop is unrolled by two blocks");
+template <int R_, int TD_, int CTAS_>
+struct Geo {
+    static constexpr int R = R_;                 // rows per thread
+    static constexpr int TD = TD_;               // distances per unit
+    static constexpr int CTAS_PER_SM = CTAS_;
+    static constexpr int TI = R * kNT;           // rows per tile
+    static constexpr int PADF = TI + TD;         // zero padding in front of every padded field
+    static constexpr int CHUNK_BYTES = 8 * R;
+    static constexpr int CHUNK_STRIDE = CHUNK_BYTES + 16;
+    static constexpr int WIN_ELEMS = TI + TD;
+    static constexpr int WIN_CHUNKS = WIN_ELEMS / R;
+    static constexpr int WIN_BYTES = WIN_CHUNKS * CHUNK_STRIDE;
+    static constexpr int STAGE_BYTES = (TD * 8 + WIN_BYTES + 127) / 128 * 128;
+    static constexpr int C_PAD = 0;              // c tables: natural order, no front padding
+    static constexpr int C_PERM = 0;
+    static constexpr bool TENSOR = false;
+    static_assert(TI % TD == 0, "tile rows must be a multiple of the distance chunk");
+    static_assert((TD / R) % 2 == 0, "inner loop is unrolled by two blocks");
+    static_assert(kLdcQuantum % TD == 0, "table padding quantum must cover a chunk");
+};
+
+
+// Geometry of the DMMA (FP64 tensor core) variant.  Rows are grouped in blocks of 8 (i = 8p + r) and columns
+// in blocks of 8 (j = 8m + r - s): for a fixed column block m
+//     Y'[p][r] += sum_{s=0..7} c[8(p-m) + s] * g[8m + r - s]          (exactly the terms d = i - j, no waste)
+// is a (P x 8) x (8 x 8) product, i.e. two mma.m8n8k4 per 8 block-rows p: M = p, K = s, N = r.  A warp owns
+// T interleaved 8-row-block tiles (tile t holds p = P0 + t + T*k, k = 0..7), so the A fragment of tile t at
+// column block m is the A fragment of tile t-1 at block m-1: ONE new LDS.128 per column block feeds 2T DMMAs.
+template <int T_, int TD_, int CTAS_>
+struct MGeo {
+    static constexpr int T = T_;                 // interleaved tiles per warp
+    static constexpr int R = 2 * T;              // accumulator doubles per thread
+    static constexpr int TD = TD_;               // columns per unit
+    static constexpr int MC = TD / 8;            // column blocks per unit
+    static constexpr int CTAS_PER_SM = CTAS_;
+    static constexpr int WARPS = kNT / 32;
+    static constexpr int TI = WARPS * 64 * T;    // rows per tile
+    static constexpr int PADF = TI + TD;         // zero padding in front of padded fields and c tables
+    static constexpr int NU = (TI + TD) / 8;     // 8-distance rows of the c window
+    static constexpr int ROW_STRIDE = 80;        // 64 B of data + 16 B: LDS.128 of 8 lanes x (k, k+1) conflict free for T = 4
+    static constexpr int CWIN_BYTES = NU * ROW_STRIDE;
+    static constexpr int GCH_ELEMS = TD + 8;     // 8-element halo in front (B fragments reach back 7)
+    static constexpr int STAGE_BYTES = (CWIN_BYTES + GCH_ELEMS * 8 + 127) / 128 * 128;
+    static constexpr int C_PAD = PADF;
+    static constexpr int C_PERM = 1;
+    static constexpr bool TENSOR = true;
+    static_assert(TI % TD == 0 && TD % 8 == 0 && MC % T == 0, "bad tile geometry");
+    static_assert(T == 4, "ROW_STRIDE = 80 is conflict free for T = 4 only");
+};
 
 struct HistParams {
     int rule, n_pass;
@@ -55,37 +100,43 @@ struct HistParams {
     int64_t ldg;
     double* y;
     int64_t ldy;
-    double* partial;   // [2 * grid][kTI]
+    double* partial;   // [2 * grid][TI]
+    int* tickets;      // [n_alpha * n_fields * n_tiles], zero on entry, zero again on exit
 };
 
+template <class G>
 __host__ __device__ inline int64_t tile_chunks(int64_t I, int64_t n_tiles, int64_t N) {
-    // distances needed by the rows of tile I: d <= i_last - 1
-    return I + 1 < n_tiles ? (I + 1) * (kTI / kTD) : (N + kTD - 1) / kTD;
+    // DFMA variant: chunks of distances, the rows of tile I need d <= i_last - 1;
+    // tensor variant: chunks of columns, they need j <= i_last
+    return I + 1 < n_tiles ? (I + 1) * (G::TI / G::TD) : (N + (G::TENSOR ? 1 : 0) + G::TD - 1) / G::TD;
 }
-__host__ __device__ inline int64_t tile_prefix(int64_t I, int n_pass) {  // units before tile I (all tiles < I are full)
-    return (int64_t)n_pass * (kTI / kTD) * (I * (I + 1) / 2);
+template <class G>
+__host__ __device__ inline int64_t tile_prefix(int64_t I, int n_pass) {  // units before tile I (tiles < I are full)
+    return (int64_t)n_pass * (G::TI / G::TD) * (I * (I + 1) / 2);
 }
 
 struct Cursor {
     int64_t prob, I, v, chunks, units;  // v in [0, units), units = n_pass * chunks
 };
 
+template <class G>
 __device__ inline Cursor cursor_at(const HistParams& p, int64_t u) {
     Cursor c;
     c.prob = u / p.units_per_prob;
     int64_t w = u - c.prob * p.units_per_prob;
-    const double K = (double)p.n_pass * (kTI / kTD);
+    const double K = (double)p.n_pass * (G::TI / G::TD);
     int64_t I = (int64_t)((sqrt(1.0 + 8.0 * (double)w / K) - 1.0) * 0.5);
     if (I > p.n_tiles - 1) I = p.n_tiles - 1;
-    while (I > 0 && tile_prefix(I, p.n_pass) > w) --I;
-    while (I + 1 < p.n_tiles && tile_prefix(I + 1, p.n_pass) <= w) ++I;
+    while (I > 0 && tile_prefix<G>(I, p.n_pass) > w) --I;
+    while (I + 1 < p.n_tiles && tile_prefix<G>(I + 1, p.n_pass) <= w) ++I;
     c.I = I;
-    c.v = w - tile_prefix(I, p.n_pass);
-    c.chunks = tile_chunks(I, p.n_tiles, p.N);
+    c.v = w - tile_prefix<G>(I, p.n_pass);
+    c.chunks = tile_chunks<G>(I, p.n_tiles, p.N);
     c.units = c.chunks * p.n_pass;
     return c;
 }
 
+template <class G>
 __device__ inline void cursor_advance(const HistParams& p, Cursor& c) {
     if (++c.v == c.units) {
         c.v = 0;
@@ -93,7 +144,7 @@ __device__ inline void cursor_advance(const HistParams& p, Cursor& c) {
             c.I = 0;
             ++c.prob;
         }
-        c.chunks = tile_chunks(c.I, p.n_tiles, p.N);
+        c.chunks = tile_chunks<G>(c.I, p.n_tiles, p.N);
         c.units = c.chunks * p.n_pass;
     }
 }
@@ -108,79 +159,160 @@ __device__ inline void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// stage the weights chunk and the field window of one unit into shared memory
-__device__ inline void stage_unit(const HistParams& p, const Cursor& c, char* stage) {
+// tensor variant: unit = TI rows x TD columns [j0, j0+TD).  Stage the c window (all distances i - j of the unit,
+// as NU rows of 8, in the table's permuted order) and the column chunk of the padded field (+8 halo).
+template <class G>
+__device__ inline void stage_unit_mma(const HistParams& p, const Cursor& c, char* stage) {
     const int64_t pass = c.v / c.chunks;
-    const int64_t d0 = (c.v - pass * c.chunks) * kTD;
+    const int64_t j0 = (c.v - pass * c.chunks) * G::TD;
     const int64_t a = c.prob / p.n_fields, f = c.prob - a * p.n_fields;
-    const double* ctab = (pass ? p.cB : p.cA) + a * p.ldc + d0;
-    const double* gsrc = p.gp + (f * p.n_pass + pass) * p.ldgp + kPadF + c.I * kTI - d0 - kTD;
+    // row u of the window holds distances 8e..8e+7, e = e_base + u, e_base = p0 - m0 - MC
+    const int64_t d_base = c.I * G::TI - j0 - G::TD;
+    const double* csrc = (pass ? p.cB : p.cA) + a * p.ldc + G::C_PAD + d_base;
+    const double* gsrc = p.gp + (f * p.n_pass + pass) * p.ldgp + G::PADF + j0 - 8;
     const int t = threadIdx.x;
-    for (int q = t; q < kTD / 2; q += kNT) cp_async16(stage + 16 * q, ctab + 2 * q);
-    char* win = stage + kTD * 8;
 #pragma unroll
-    for (int q = t; q < kWinElems / 2; q += kNT) {
-        const int byte = 16 * q;
-        cp_async16(win + byte + ((byte >> 7) << 4), gsrc + 2 * q);
+    for (int q = t; q < G::NU * 4; q += kNT) cp_async16(stage + (q >> 2) * G::ROW_STRIDE + (q & 3) * 16, csrc + 2 * q);
+    char* gch = stage + G::CWIN_BYTES;
+    for (int q = t; q < G::GCH_ELEMS / 2; q += kNT) cp_async16(gch + 16 * q, gsrc + 2 * q);
+}
+
+__device__ inline void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// tensor variant: acc[2t], acc[2t+1] = D fragment of tile t (rows 8(P0w + t + T k) + 2 s' + {0,1})
+template <class G>
+__device__ inline void compute_unit_mma(double (&acc)[G::R], const char* stage) {
+    constexpr int T = G::T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = lane >> 2, sp = lane & 3;
+    // A fragments: row (8T*warp + t + MC - mi + T*k) of the c window, 16 bytes at 16*s' = {c[..+s'], c[..+s'+4]}
+    const char* arow = stage + (8 * T * warp + G::MC + T * k) * G::ROW_STRIDE + 16 * sp;
+    // B fragments: g[8m + k - s' - 4kh] = gch[8 + 8mi + k - s' - 4kh]
+    const double* gch = reinterpret_cast<const double*>(stage + G::CWIN_BYTES) + (4 + k - sp);
+    double2 af[T];
+#pragma unroll
+    for (int t = 1; t < T; ++t) af[t] = *reinterpret_cast<const double2*>(arow + t * G::ROW_STRIDE);
+#pragma unroll 1
+    for (int mg = 0; mg < G::MC; mg += T) {
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const int mi = mg + j;
+            // tile t uses slot (t - mi) mod T; the new fragment (tile 0) replaces the one tile T-1 used last time
+            af[(T - j) % T] = *reinterpret_cast<const double2*>(arow - mi * G::ROW_STRIDE);
+            const double b1 = gch[8 * mi], b0 = gch[8 * mi + 4];
+#pragma unroll
+            for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].x, b0);
+#pragma unroll
+            for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].y, b1);
+        }
     }
 }
 
-__device__ inline void load_chunk(double (&dst)[kR], const char* win, int chunk) {
-    const int byte = kChunkBytes * chunk;
-    const double2* src = reinterpret_cast<const double2*>(win + byte + ((byte >> 7) << 4));
+// row of accumulator pair `t` of this thread, relative to the tile's first row (tensor variant)
+template <class G>
+__device__ inline int mma_row(int t) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    return 8 * (8 * G::T * warp + t + G::T * (lane >> 2)) + 2 * (lane & 3);
+}
+
+// stage the weights chunk and the field window of one unit into shared memory
+template <class G>
+__device__ inline void stage_unit(const HistParams& p, const Cursor& c, char* stage) {
+    if constexpr (G::TENSOR) {
+        stage_unit_mma<G>(p, c, stage);
+        return;
+    } else {
+    const int64_t pass = c.v / c.chunks;
+    const int64_t d0 = (c.v - pass * c.chunks) * G::TD;
+    const int64_t a = c.prob / p.n_fields, f = c.prob - a * p.n_fields;
+    const double* ctab = (pass ? p.cB : p.cA) + a * p.ldc + d0;
+    const double* gsrc = p.gp + (f * p.n_pass + pass) * p.ldgp + G::PADF + c.I * G::TI - d0 - G::TD;
+    const int t = threadIdx.x;
+    for (int q = t; q < G::TD / 2; q += kNT) cp_async16(stage + 16 * q, ctab + 2 * q);
+    char* win = stage + G::TD * 8;
+    constexpr int QPC = G::R / 2;  // 16-byte quads per chunk
 #pragma unroll
-    for (int q = 0; q < kR / 2; ++q) {
+    for (int q = t; q < G::WIN_ELEMS / 2; q += kNT)
+        cp_async16(win + (q / QPC) * G::CHUNK_STRIDE + (q % QPC) * 16, gsrc + 2 * q);
+    }
+}
+
+template <class G>
+__device__ inline void load_chunk(double (&dst)[G::R], const char* win, int chunk) {
+    const double2* src = reinterpret_cast<const double2*>(win + chunk * G::CHUNK_STRIDE);
+#pragma unroll
+    for (int q = 0; q < G::R / 2; ++q) {
         double2 v = src[q];
         dst[2 * q] = v.x;
         dst[2 * q + 1] = v.y;
     }
 }
 
-// acc[r] += sum_s c[s] * window(r - s), window(k) = hi[k] for k >= 0, lo[k + kR] for k < 0
-__device__ inline void fma_block(double (&acc)[kR], const double* cs, const double (&hi)[kR], const double (&lo)[kR]) {
-    double c[kR];
+// acc[r] += sum_s c[s] * window(r - s), window(k) = hi[k] for k >= 0, lo[k + R] for k < 0
+template <class G>
+__device__ inline void fma_block(double (&acc)[G::R], const double* cs, const double (&hi)[G::R],
+                                 const double (&lo)[G::R]) {
+    constexpr int R = G::R;
 #pragma unroll
-    for (int q = 0; q < kR / 2; ++q) {
-        double2 v = reinterpret_cast<const double2*>(cs)[q];
-        c[2 * q] = v.x;
-        c[2 * q + 1] = v.y;
-    }
+    for (int s2 = 0; s2 < R; s2 += 2) {
+        const double2 c2 = *reinterpret_cast<const double2*>(cs + s2);
 #pragma unroll
-    for (int s = 0; s < kR; ++s) {
+        for (int h = 0; h < 2; ++h) {
+            const int s = s2 + h;
+            const double c = h ? c2.y : c2.x;
 #pragma unroll
-        for (int r = 0; r < kR; ++r) {
-            const int k = r - s;
-            acc[r] = fma(c[s], k >= 0 ? hi[k] : lo[k + kR], acc[r]);
+            for (int r = 0; r < R; ++r) {
+                const int k = r - s;
+                acc[r] = fma(c, k >= 0 ? hi[k] : lo[k + R], acc[r]);
+            }
         }
     }
 }
 
-__device__ inline void compute_unit(double (&acc)[kR], const char* stage) {
+template <class G>
+__device__ inline void compute_unit(double (&acc)[G::R], const char* stage) {
+    if constexpr (G::TENSOR) {
+        compute_unit_mma<G>(acc, stage);
+        return;
+    } else {
+    constexpr int R = G::R;
     const double* cs = reinterpret_cast<const double*>(stage);
-    const char* win = stage + kTD * 8;
-    const int c0 = threadIdx.x + kTD / kR;
-    double hi[kR], lo[kR];
-    load_chunk(hi, win, c0);
-#pragma unroll 2
-    for (int b = 0; b < kTD / kR; b += 2) {
-        load_chunk(lo, win, c0 - b - 1);
-        fma_block(acc, cs + b * kR, hi, lo);
-        load_chunk(hi, win, c0 - b - 2 >= 0 ? c0 - b - 2 : 0);
-        fma_block(acc, cs + (b + 1) * kR, lo, hi);
+    const char* win = stage + G::TD * 8;
+    const int c0 = threadIdx.x + G::TD / R;
+    double hi[R], lo[R];
+    load_chunk<G>(hi, win, c0);
+#pragma unroll 1
+    for (int b = 0; b < G::TD / R; b += 2) {
+        load_chunk<G>(lo, win, c0 - b - 1);
+        fma_block<G>(acc, cs + b * R, hi, lo);
+        load_chunk<G>(hi, win, c0 - b - 2);  // (last iteration: chunk `threadIdx.x`, loaded but unused)
+        fma_block<G>(acc, cs + (b + 1) * R, lo, hi);
+    }
     }
 }
 
-// scale, add the first column / right-of-point terms and store the kR rows of this thread
-__device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I, const double (&acc)[kR]) {
+// position (relative to the tile's first row) of accumulator pair q = 0..R/2-1 of this thread
+template <class G>
+__device__ inline int acc_pair_row(int q) {
+    if constexpr (G::TENSOR) return mma_row<G>(q);
+    else return threadIdx.x * G::R + 2 * q;
+}
+
+// scale, add the first column / right-of-point terms and store the R rows of this thread
+template <class G>
+__device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I, const double (&acc)[G::R]) {
     const int64_t a = prob / p.n_fields, f = prob - a * p.n_fields;
     const double* gf = p.g + f * p.ldg;
     const double g0 = gf[0];
     const double cm1 = p.rule == FRX_RULE_SIMPSON ? p.cm1[a] : 0.0;
-    const int64_t ib = I * kTI + (int64_t)threadIdx.x * kR;
 #pragma unroll
-    for (int r = 0; r < kR; ++r) {
-        const int64_t i = ib + r;
-        if (i > p.N) break;
+    for (int r = 0; r < G::R; ++r) {
+        const int64_t i = I * G::TI + acc_pair_row<G>(r >> 1) + (r & 1);
+        if (i > p.N) continue;
         double v;
         if (i == 0) {
             v = 0.0;
@@ -195,141 +327,163 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
     }
 }
 
-__global__ void __launch_bounds__(kNT, kCtasPerSm) frx_k2_history_main(const HistParams p) {
-    __shared__ __align__(128) char smem[2 * kStageBytes];
-    const int64_t G = gridDim.x, k = blockIdx.x;
-    const int64_t ubeg = k * p.total_units / G, uend = (k + 1) * p.total_units / G;
+// CTA that owns unit u when `total` units are dealt to `G` CTAs as [k*total/G, (k+1)*total/G)
+__device__ inline int64_t span_owner(int64_t u, int64_t total, int64_t G) { return ((u + 1) * G - 1) / total; }
+
+template <class G>
+__global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const HistParams p) {
+    extern __shared__ __align__(128) char smem[];
+    __shared__ int s_last;
+    constexpr int R = G::R;
+    const int64_t NG = gridDim.x, k = blockIdx.x;
+    const int64_t ubeg = k * p.total_units / NG, uend = (k + 1) * p.total_units / NG;
     if (ubeg >= uend) return;
-    Cursor cur = cursor_at(p, ubeg), nxt = cur;
-    double acc[kR];
+    Cursor cur = cursor_at<G>(p, ubeg), nxt = cur;
+    double acc[R];
 #pragma unroll
-    for (int r = 0; r < kR; ++r) acc[r] = 0.0;
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
     bool from_start = (cur.v == 0);
-    stage_unit(p, cur, smem);
+    stage_unit<G>(p, cur, smem);
     cp_async_commit();
     for (int64_t u = ubeg; u < uend; ++u) {
-        char* stage = smem + ((u - ubeg) & 1) * kStageBytes;
+        char* stage = smem + ((u - ubeg) & 1) * G::STAGE_BYTES;
         if (u + 1 < uend) {
-            cursor_advance(p, nxt);
-            stage_unit(p, nxt, smem + ((u + 1 - ubeg) & 1) * kStageBytes);
+            cursor_advance<G>(p, nxt);
+            stage_unit<G>(p, nxt, smem + ((u + 1 - ubeg) & 1) * G::STAGE_BYTES);
         }
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        compute_unit(acc, stage);
+        compute_unit<G>(acc, stage);
         __syncthreads();
         const bool tile_done = (cur.v + 1 == cur.units), span_done = (u + 1 == uend);
         if (tile_done || span_done) {
             if (tile_done && from_start) {
-                finish_rows(p, cur.prob, cur.I, acc);
+                finish_rows<G>(p, cur.prob, cur.I, acc);
             } else {
-                // continuation of a tile begun by an earlier CTA -> slot 2k; tile begun here but not
-                // finished -> slot 2k+1
-                double* dst = p.partial + ((2 * k + (from_start ? 1 : 0)) * kTI + (int64_t)threadIdx.x * kR);
+                // tile shared with other CTAs.  Slot 2k: continuation of a tile begun by an earlier CTA;
+                // slot 2k+1: tile begun here but not finished here.
+                double* dst = p.partial + (2 * k + (from_start ? 1 : 0)) * G::TI;
 #pragma unroll
-                for (int r = 0; r < kR; r += 2) *reinterpret_cast<double2*>(dst + r) = make_double2(acc[r], acc[r + 1]);
+                for (int r = 0; r < R; r += 2)
+                    *reinterpret_cast<double2*>(dst + acc_pair_row<G>(r >> 1)) = make_double2(acc[r], acc[r + 1]);
+                const int64_t tile_begin = u - cur.v, tile_end = tile_begin + cur.units;
+                const int64_t k0 = span_owner(tile_begin, p.total_units, NG), k1 = span_owner(tile_end - 1, p.total_units, NG);
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int* ticket = p.tickets + (cur.prob * p.n_tiles + cur.I);
+                    const int old = atomicAdd(ticket, 1);
+                    s_last = (old == (int)(k1 - k0));
+                    if (s_last) *ticket = 0;  // leave the tickets clean for the next call
+                }
+                __syncthreads();
+                if (s_last) {  // every other participant has published its slot: add them in CTA order
+                    __threadfence();
+                    const double* src = p.partial + (2 * k0 + 1) * G::TI;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = __ldcg(src + acc_pair_row<G>(r >> 1) + (r & 1));
+                    for (int64_t kk = k0 + 1; kk <= k1; ++kk) {
+                        src = p.partial + (2 * kk) * G::TI;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r] += __ldcg(src + acc_pair_row<G>(r >> 1) + (r & 1));
+                    }
+                    finish_rows<G>(p, cur.prob, cur.I, acc);
+                }
             }
 #pragma unroll
-            for (int r = 0; r < kR; ++r) acc[r] = 0.0;
+            for (int r = 0; r < R; ++r) acc[r] = 0.0;
             from_start = true;
         }
         cur = nxt;
     }
 }
 
-// One CTA per span boundary b = 1..G-1.  If the boundary cuts a row tile and is the first boundary
-// inside that tile, this CTA adds the partial slots of every CTA that worked on the tile, in CTA
-// order, and finishes the rows.
-__global__ void __launch_bounds__(kNT) frx_k2_history_fixup(const HistParams p, int64_t G) {
-    const int64_t b = (int64_t)blockIdx.x + 1;
-    const int64_t ub = b * p.total_units / G;
-    if (ub >= p.total_units || ub == (b - 1) * p.total_units / G) return;  // empty neighbour span
-    const Cursor c = cursor_at(p, ub);
-    if (c.v == 0) return;                       // boundary coincides with a tile start
-    const int64_t tile_begin = ub - c.v, tile_end = tile_begin + c.units;
-    // first boundary inside the tile <=> the previous non-empty span starts at or before the tile start
-    int64_t prev = b - 1;
-    while (prev > 0 && prev * p.total_units / G == (prev + 1) * p.total_units / G) --prev;
-    if (prev * p.total_units / G > tile_begin) return;
-    double acc[kR];
-    const double* src = p.partial + (2 * prev + 1) * kTI + (int64_t)threadIdx.x * kR;
-#pragma unroll
-    for (int r = 0; r < kR; ++r) acc[r] = src[r];
-    for (int64_t k = b; k < G; ++k) {
-        const int64_t kb = k * p.total_units / G, ke = (k + 1) * p.total_units / G;
-        if (kb >= tile_end) break;
-        if (kb == ke) continue;
-        src = p.partial + (2 * k) * kTI + (int64_t)threadIdx.x * kR;
-#pragma unroll
-        for (int r = 0; r < kR; ++r) acc[r] += src[r];
+// prepare kernel: blocks [0, n_tab) generate the weight tables (K1); the remaining blocks build the padded
+// copies of the fields, gp[(f*n_pass + pass)*ldgp + padf + j] = g_j for 1 <= j <= N (for 'simpson' only the
+// nodes of the pass's parity: pass 0 even, pass 1 odd) and 0 elsewhere, and clear the tickets.
+__global__ void __launch_bounds__(kNT) frx_k12_prepare(int rule, const double* __restrict__ alpha, double h, int64_t N,
+                                                       double* __restrict__ cA, double* __restrict__ cB, int64_t ldc,
+                                                       double* __restrict__ w0, double* __restrict__ mult, int64_t ldw,
+                                                       double* __restrict__ cm1, int c_pad, int c_perm, int64_t n_tab,
+                                                       int64_t tab_per_alpha,
+                                                       const double* __restrict__ g, int64_t ldg, int n_pass, int64_t n_fp,
+                                                       int64_t ldgp, int padf, double* __restrict__ gp, int* __restrict__ tickets,
+                                                       int64_t n_tickets) {
+    __shared__ frx_par P;
+    const int64_t bx = blockIdx.x;
+    if (bx < n_tab) {
+        const int64_t a = bx / tab_per_alpha;
+        if (threadIdx.x == 0) P = frx_par_init(rule, alpha[a]);
+        __syncthreads();
+        // storage slot X <-> distance x = X - c_pad; the DMMA kernel wants every aligned group of 8
+        // distances stored as [0 4 1 5 2 6 3 7] so that one LDS.128 yields both k-halves of an A fragment
+        const int64_t X = (bx - a * tab_per_alpha) * kNT + threadIdx.x;
+        if (X >= ldc) return;
+        const int64_t x = X - c_pad;
+        if (x < 0) {
+            cA[a * ldc + X] = 0.0;
+            if (cB) cB[a * ldc + X] = 0.0;
+            return;
+        }
+        const frx_table_entry e = frx_table_at(P, x, N, h);
+        const int64_t slot = c_perm ? c_pad + (x & ~(int64_t)7) + ((x & 3) * 2 + ((x >> 2) & 1)) : X;
+        cA[a * ldc + slot] = e.ca;
+        if (cB) cB[a * ldc + slot] = e.cb;
+        if (x <= N) {
+            w0[a * ldw + x] = e.w0;
+            mult[a * ldw + x] = e.mult;
+        }
+        if (x == 0) cm1[a] = rule == FRX_R_SIMPSON ? frx_raw_right_of_point(P) : 0.0;
+        return;
     }
-    finish_rows(p, c.prob, c.I, acc);
-}
-
-// padded copies of the fields: gp[(f*n_pass + pass)*ldgp + kPadF + j] = g_j for 1 <= j <= N (and, for
-// 'simpson', j of the pass's parity: pass 0 even nodes, pass 1 odd nodes), 0 elsewhere
-__global__ void frx_k2_pad_fields(const double* __restrict__ g, int64_t ldg, int64_t N, int n_pass, int64_t ldgp,
-                                  double* __restrict__ gp) {
-    const int64_t fp = blockIdx.y, f = fp / n_pass, pass = fp - f * n_pass;
-    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < ldgp; x += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = x - kPadF;
+    const int64_t n_pad_blocks = gridDim.x - n_tab, pb = bx - n_tab;
+    const int64_t total = n_fp * ldgp;
+    for (int64_t e = pb * kNT + threadIdx.x; e < total; e += n_pad_blocks * kNT) {
+        const int64_t fp = e / ldgp, x = e - fp * ldgp;
+        const int64_t f = fp / n_pass, pass = fp - f * n_pass, j = x - padf;
         double v = 0.0;
         if (j >= 1 && j <= N && (n_pass == 1 || (j & 1) == pass)) v = g[f * ldg + j];
-        gp[fp * ldgp + x] = v;
+        gp[e] = v;
     }
+    for (int64_t e = pb * kNT + threadIdx.x; e < n_tickets; e += n_pad_blocks * kNT) tickets[e] = 0;
 }
 
-}  // namespace
-
-int frx_launch_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
-                             double* d_cA, double* d_cB, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
-                             double* d_cm1);
-
-extern "C" int64_t frx_table_ldc(int64_t N) { return (N + 1 + kTD - 1) / kTD * kTD; }
-
-extern "C" int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
-                           int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy) {
-    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
-    FRX_REQUIRE(N >= 1 && N < ((int64_t)1 << 30), FRX_ERR_INVALID_ARG, "N out of range");
-    FRX_REQUIRE(n_alpha >= 0 && n_alpha <= 65535 && n_fields >= 0 && n_fields <= 32767, FRX_ERR_INVALID_ARG,
-                "n_alpha (<= 65535) / n_fields (<= 32767) out of range");
-    const int64_t need_g = N + 1 + (rule == FRX_RULE_SIMPSON ? 1 : 0);
-    FRX_REQUIRE(n_g >= need_g && ldg >= n_g && ldy >= N + 1, FRX_ERR_INVALID_ARG,
-                "field too short (needs N+1 nodes, N+2 for 'simpson') or leading dimension too small");
-    if (n_alpha == 0 || n_fields == 0) return FRX_OK;
-    FRX_REQUIRE(d_alpha && d_g && d_y, FRX_ERR_INVALID_ARG, "NULL buffer");
-    FRX_CUDA(cudaSetDevice(ctx->device));
-
+template <class G>
+int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N, int64_t n_fields,
+                 const double* d_g, int64_t ldg, double* d_y, int64_t ldy) {
     HistParams p;
     p.rule = rule;
     p.n_pass = rule == FRX_RULE_SIMPSON ? 2 : 1;
     p.N = N;
     p.n_alpha = n_alpha;
     p.n_fields = n_fields;
-    p.n_tiles = (N + 1 + kTI - 1) / kTI;
-    p.units_per_prob = tile_prefix(p.n_tiles - 1, p.n_pass) + p.n_pass * tile_chunks(p.n_tiles - 1, p.n_tiles, N);
+    p.n_tiles = (N + 1 + G::TI - 1) / G::TI;
+    p.units_per_prob = tile_prefix<G>(p.n_tiles - 1, p.n_pass) + p.n_pass * tile_chunks<G>(p.n_tiles - 1, p.n_tiles, N);
     p.total_units = p.units_per_prob * n_alpha * n_fields;
-    p.ldc = frx_table_ldc(N);
+    // tables are zero beyond d = N-1 up to the end of the last tile: whole-tile reads stay in bounds and finite
+    p.ldc = G::C_PAD + (frx_table_ldc(N) > p.n_tiles * G::TI ? frx_table_ldc(N) : p.n_tiles * G::TI);
     p.ldw = (N + 1 + 1) / 2 * 2;
-    p.ldgp = kPadF + p.n_tiles * kTI;
-    int64_t G = (int64_t)ctx->sm_count * kCtasPerSm;
-    if (G > p.total_units) G = p.total_units;
+    p.ldgp = G::PADF + p.n_tiles * G::TI;
+    int64_t NG = (int64_t)ctx->sm_count * G::CTAS_PER_SM;
+    if (NG > p.total_units) NG = p.total_units;
+    const int64_t n_tickets = n_alpha * n_fields * p.n_tiles;
 
     // workspace carve-up (all offsets multiples of 256 bytes)
     size_t off = 0;
-    auto carve = [&](size_t n_doubles) {
+    auto carve = [&](size_t bytes) {
         size_t o = off;
-        off += frx_align_up(n_doubles * sizeof(double), 256);
+        off += frx_align_up(bytes, 256);
         return o;
     };
-    const size_t o_cA = carve((size_t)n_alpha * p.ldc);
-    const size_t o_cB = carve(p.n_pass == 2 ? (size_t)n_alpha * p.ldc : 0);
-    const size_t o_w0 = carve((size_t)n_alpha * p.ldw);
-    const size_t o_mult = carve((size_t)n_alpha * p.ldw);
-    const size_t o_cm1 = carve((size_t)n_alpha);
-    const size_t o_gp = carve((size_t)n_fields * p.n_pass * p.ldgp);
-    const size_t o_part = carve((size_t)2 * G * kTI);
+    const size_t o_cA = carve(sizeof(double) * (size_t)n_alpha * p.ldc);
+    const size_t o_cB = carve(p.n_pass == 2 ? sizeof(double) * (size_t)n_alpha * p.ldc : 0);
+    const size_t o_w0 = carve(sizeof(double) * (size_t)n_alpha * p.ldw);
+    const size_t o_mult = carve(sizeof(double) * (size_t)n_alpha * p.ldw);
+    const size_t o_cm1 = carve(sizeof(double) * (size_t)n_alpha);
+    const size_t o_gp = carve(sizeof(double) * (size_t)n_fields * p.n_pass * p.ldgp);
+    const size_t o_part = carve(sizeof(double) * (size_t)2 * NG * G::TI);
+    const size_t o_tick = carve(sizeof(int) * (size_t)n_tickets);
     int rc = frx_ws_reserve(ctx, off);
     if (rc) return rc;
     char* ws = (char*)ctx->ws;
@@ -350,19 +504,57 @@ extern "C" int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double
     p.y = d_y;
     p.ldy = ldy;
     p.partial = (double*)(ws + o_part);
+    p.tickets = (int*)(ws + o_tick);
 
-    rc = frx_launch_weights_table(ctx, rule, n_alpha, d_alpha, h, N, cA, cB, p.ldc, w0, mult, p.ldw, cm1);
-    if (rc) return rc;
     {
-        dim3 grid((unsigned)((p.ldgp + 255) / 256), (unsigned)(n_fields * p.n_pass));
-        FRX_LAUNCH(ctx, FRX_K_PAD_FIELDS,
-                   frx_k2_pad_fields<<<grid, 256, 0, ctx->stream>>>(d_g, ldg, N, p.n_pass, p.ldgp, gp));
+        const int64_t tab_per_alpha = (p.ldc + kNT - 1) / kNT, n_tab = tab_per_alpha * n_alpha;
+        const int64_t n_fp = n_fields * p.n_pass;
+        int64_t n_pad = (n_fp * p.ldgp + 8 * kNT - 1) / (8 * kNT);
+        if (n_pad > 4096) n_pad = 4096;
+        FRX_REQUIRE(n_tab + n_pad < ((int64_t)1 << 31), FRX_ERR_INVALID_ARG, "problem too large for one launch");
+        FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
+                   frx_k12_prepare<<<(unsigned)(n_tab + n_pad), kNT, 0, ctx->stream>>>(
+                       rule, d_alpha, h, N, cA, cB, p.ldc, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
+                       n_fp, p.ldgp, G::PADF, gp, p.tickets, n_tickets));
     }
-    FRX_LAUNCH(ctx, FRX_K_HISTORY_MAIN, frx_k2_history_main<<<(unsigned)G, kNT, 0, ctx->stream>>>(p));
-    if (G > 1) {
-        FRX_LAUNCH(ctx, FRX_K_HISTORY_FIXUP, frx_k2_history_fixup<<<(unsigned)(G - 1), kNT, 0, ctx->stream>>>(p, G));
-    }
+    // dynamic shared memory: at least the double buffer, padded so that exactly CTAS_PER_SM CTAs fit per SM
+    int smem_sm = 0;
+    FRX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    int dyn = (smem_sm / G::CTAS_PER_SM - 1024 - 64) / 128 * 128;
+    if (dyn < 2 * G::STAGE_BYTES) dyn = 2 * G::STAGE_BYTES;
+    FRX_CUDA(cudaFuncSetAttribute(frx_k2_history_main<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    FRX_LAUNCH(ctx, FRX_K_HISTORY_MAIN, frx_k2_history_main<G><<<(unsigned)NG, kNT, dyn, ctx->stream>>>(p));
     return FRX_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t frx_table_ldc(int64_t N) { return (N + 1 + kLdcQuantum - 1) / kLdcQuantum * kLdcQuantum; }
+
+extern "C" int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                           int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
+    FRX_REQUIRE(N >= 1 && N < ((int64_t)1 << 30), FRX_ERR_INVALID_ARG, "N out of range");
+    FRX_REQUIRE(n_alpha >= 0 && n_alpha <= 65535 && n_fields >= 0 && n_fields <= 32767, FRX_ERR_INVALID_ARG,
+                "n_alpha (<= 65535) / n_fields (<= 32767) out of range");
+    const int64_t need_g = N + 1 + (rule == FRX_RULE_SIMPSON ? 1 : 0);
+    FRX_REQUIRE(n_g >= need_g && ldg >= n_g && ldy >= N + 1, FRX_ERR_INVALID_ARG,
+                "field too short (needs N+1 nodes, N+2 for 'simpson') or leading dimension too small");
+    if (n_alpha == 0 || n_fields == 0) return FRX_OK;
+    FRX_REQUIRE(d_alpha && d_g && d_y, FRX_ERR_INVALID_ARG, "NULL buffer");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    // tile geometry: FRX_K2_VARIANT is a tuning/experiment switch, the default is the measured best
+    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 4;
+    switch (variant) {
+        case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 2: return history_impl<Geo<8, 256, 5>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 3: return history_impl<Geo<8, 128, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 5: return history_impl<MGeo<4, 256, 2>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 6: return history_impl<MGeo<4, 128, 3>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        default: return history_impl<MGeo<4, 256, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+    }
 }
 
 extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_alpha, double h, int64_t N,
@@ -377,33 +569,22 @@ extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const d
     if (n_alpha == 0 || n_fields == 0) return FRX_OK;
     FRX_REQUIRE(ldg >= n_g && ldy >= N + 1, FRX_ERR_INVALID_ARG, "leading dimension too small");
     FRX_CUDA(cudaSetDevice(ctx->device));
-    // caller-facing device buffers live in their own allocation (the workspace is re-carved by frx_history)
+    // caller-facing device buffers: a grow-only allocation owned by the context (separate from the
+    // workspace, which frx_history re-carves)
     const size_t b_alpha = frx_align_up(sizeof(double) * n_alpha, 256);
     const size_t b_g = frx_align_up(sizeof(double) * (size_t)n_fields * ldg, 256);
     const size_t b_y = sizeof(double) * (size_t)n_alpha * n_fields * ldy;
-    char* io = nullptr;
-    FRX_CUDA(cudaMallocAsync((void**)&io, b_alpha + b_g + b_y, ctx->stream));
+    int rc = frx_io_reserve(ctx, b_alpha + b_g + b_y);
+    if (rc) return rc;
+    char* io = (char*)ctx->io;
     double* d_alpha = (double*)io;
     double* d_g = (double*)(io + b_alpha);
     double* d_y = (double*)(io + b_alpha + b_g);
-    int rc = FRX_OK;
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(d_alpha, h_alpha, sizeof(double) * n_alpha, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(d_g, h_g, sizeof(double) * (size_t)n_fields * ldg, cudaMemcpyHostToDevice, ctx->stream)) !=
-            cudaSuccess) {
-        frx_set_error("host->device copy failed: %s", cudaGetErrorString(e));
-        rc = FRX_ERR_CUDA;
-    }
-    if (!rc) rc = frx_history(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, n_g, d_y, ldy);
-    if (!rc && (e = cudaMemcpyAsync(h_y, d_y, b_y, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) {
-        frx_set_error("device->host copy failed: %s", cudaGetErrorString(e));
-        rc = FRX_ERR_CUDA;
-    }
-    cudaFreeAsync(io, ctx->stream);
-    e = cudaStreamSynchronize(ctx->stream);
-    if (!rc && e != cudaSuccess) {
-        frx_set_error("stream synchronize failed: %s", cudaGetErrorString(e));
-        rc = FRX_ERR_CUDA;
-    }
-    return rc;
+    FRX_CUDA(cudaMemcpyAsync(d_alpha, h_alpha, sizeof(double) * n_alpha, cudaMemcpyHostToDevice, ctx->stream));
+    FRX_CUDA(cudaMemcpyAsync(d_g, h_g, sizeof(double) * (size_t)n_fields * ldg, cudaMemcpyHostToDevice, ctx->stream));
+    rc = frx_history(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, n_g, d_y, ldy);
+    if (rc) return rc;
+    FRX_CUDA(cudaMemcpyAsync(h_y, d_y, b_y, cudaMemcpyDeviceToHost, ctx->stream));
+    FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FRX_OK;
 }

@@ -15,6 +15,9 @@ struct frx_ctx {
     // grow-only device workspace (weight tables, padded fields, stream-K partials)
     void* ws;
     size_t ws_bytes;
+    // grow-only device buffers behind the *_host entry points (caller-facing inputs / outputs)
+    void* io;
+    size_t io_bytes;
     // small pinned host staging for the *_host entry points
     void* pinned;
     size_t pinned_bytes;
@@ -64,6 +67,7 @@ void frx_set_error(const char* fmt, ...);
 // ensure ctx->ws holds at least `bytes`; contents are NOT preserved on growth
 int frx_ws_reserve(frx_ctx* ctx, size_t bytes);
 int frx_pinned_reserve(frx_ctx* ctx, size_t bytes);
+int frx_io_reserve(frx_ctx* ctx, size_t bytes);
 // host-side domain check of one Settings triple against the reference's behaviour
 int frx_check_settings(int rule, double alpha, double resolution);
 int frx_check_rule_alpha(int rule, double alpha);

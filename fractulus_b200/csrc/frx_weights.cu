@@ -2,6 +2,7 @@
 // growing-history operator).  FP64 ALU work: O(count) correctly rounded pow() per stencil / table.
 #include "frx_internal.h"
 #include "frx_rules.cuh"
+#include "frx_table.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K5: one CTA per Settings(alpha, lf, resolution); thread k produces the node at offset first + k.
@@ -126,23 +127,12 @@ __global__ void __launch_bounds__(128) frx_k1_weights_table(int rule, const doub
     __syncthreads();
     const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= ldc) return;
-    const double xd = (double)x;
-    double ca = 0.0, cb = 0.0;
-    if (x < N) {
-        ca = frx_raw_toeplitz(P, xd, true);
-        if (rule == FRX_R_SIMPSON) cb = frx_raw_toeplitz(P, xd, false);
-    }
-    cA[a * ldc + x] = ca;
-    if (cB) cB[a * ldc + x] = cb;
+    const frx_table_entry e = frx_table_at(P, x, N, h);
+    cA[a * ldc + x] = e.ca;
+    if (cB) cB[a * ldc + x] = e.cb;
     if (x <= N) {
-        double w = 0.0, m = 0.0;
-        if (x >= 1) {
-            const double lf = FRX_MUL(xd, h);               // lf = i * h at the call site
-            m = frx_multiplier(P, lf, xd);
-            if (rule != FRX_R_RECTANGLE && !(rule == FRX_R_SIMPSON && x < 2)) w = frx_raw_first(P, xd);
-        }
-        w0[a * ldw + x] = w;
-        mult[a * ldw + x] = m;
+        w0[a * ldw + x] = e.w0;
+        mult[a * ldw + x] = e.mult;
     }
     if (x == 0 && cm1) cm1[a] = rule == FRX_R_SIMPSON ? frx_raw_right_of_point(P) : 0.0;
 }

@@ -24,3 +24,21 @@ extern "C" int t_left_weights(int rule, double alpha, double lf, double res, int
     *count = (int)c;
     return 0;
 }
+
+// Toeplitz tables exactly as kernel K1 computes them (fractulus_b200/csrc/frx_weights.cu), on the host
+extern "C" int t_tables(int rule, double alpha, double h, long N, double* cA, double* cB, double* w0, double* mult,
+                        double* cm1) {
+    frx_par P = frx_par_init(rule, alpha);
+    for (long x = 0; x < N; ++x) {
+        cA[x] = frx_raw_toeplitz(P, (double)x, true);
+        if (rule == FRX_R_SIMPSON) cB[x] = frx_raw_toeplitz(P, (double)x, false);
+    }
+    w0[0] = mult[0] = 0.0;
+    for (long x = 1; x <= N; ++x) {
+        double xd = (double)x, lf = FRX_MUL(xd, h);
+        mult[x] = frx_multiplier(P, lf, xd);
+        w0[x] = (rule != FRX_R_RECTANGLE && !(rule == FRX_R_SIMPSON && x < 2)) ? frx_raw_first(P, xd) : 0.0;
+    }
+    *cm1 = rule == FRX_R_SIMPSON ? frx_raw_right_of_point(P) : 0.0;
+    return 0;
+}
