@@ -26,6 +26,7 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 N_NODES = 100000
+CFG3_NODES, CFG3_FIELDS = 16384, 4096
 RULE = 'caputo'
 METRIC = 'fractional_history_node_evals_per_sec'
 UNIT = 'node-evals/s'
@@ -170,7 +171,16 @@ def run_reference(args):
     return 0
 
 
-def workload_config(world, alphas_per_gpu):
+def workload_config(world, alphas_per_gpu, workload='cfg2'):
+    if workload == 'cfg3':
+        return {
+            'workload': 'cfg3: batched Toeplitz application, N=16384 nodes x %d fields per GPU (smooth family '
+                        "g_b = d/dx[sin((1+b/B)3x) + x^2]), rule 'caputo', alpha=0.5, FP64 tensor cores (DMMA); step = K1 weight "
+                        'table + K3 application' % CFG3_FIELDS,
+            'n_nodes': CFG3_NODES, 'n_fields': CFG3_FIELDS, 'rule': RULE,
+            'l2': 'inputs (%.0f MB per GPU) larger than L2; no flush needed' % (CFG3_FIELDS * (CFG3_NODES + 2) * 8 / 1e6),
+            'parallelism': 'independent fields per GPU' if world > 1 else 'single GPU',
+        }
     return {
         'workload': 'cfg2: 1D fractional derivative history sum, N=1e5 nodes, single smooth field '
                     "g=3cos3x+2x, rule 'caputo', FP64; %d alpha per GPU (%s); step = K1 weight tables + K2 history sum%s"
@@ -199,6 +209,8 @@ def run_b200(args):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    if args.workload == 'cfg3':
+        return run_b200_cfg3(args, world, rank, local_rank, dev)
     A = args.alphas_per_gpu
     steps, warmup = args.steps, max(args.warmup, 3)
     h = 1.0 / N_NODES
@@ -323,8 +335,10 @@ def run_b200(args):
                          'note': 'intensity ~6e3 flop/B: not HBM bound'},
             'timing': 'per-kernel CUDA events on the launching stream, separate pass of the same K steps',
         }
-        cpu = cpu_reference_leg(8.0)
+        cpu = cpu_reference_leg(8.0) if not args.skip_cpu else {'skipped': '--skip-cpu (tuning run, not a bench line)'}
         try:
+            if args.skip_cpu:
+                raise RuntimeError('skipped')
             cpu['python_port'] = python_reference_leg()
         except Exception as ex:      # never let the informational leg break the line
             cpu['python_port'] = {'error': repr(ex)}
@@ -346,6 +360,79 @@ def run_b200(args):
     return 0
 
 
+
+def run_b200_cfg3(args, world, rank, local_rank, dev):
+    """BASELINE cfg 3 (not the headline line; `--workload cfg3`): N = 16384 x 4096 fields per GPU through K3."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fractulus_b200 import _lib, batched
+    N, B = CFG3_NODES, CFG3_FIELDS
+    steps, warmup = args.steps, max(args.warmup, 3)
+    h = 1.0 / N
+    x = torch.arange(N + 2, dtype=torch.float64, device=dev) * h
+    k = 3.0 * (1.0 + (torch.arange(B, dtype=torch.float64, device=dev) + rank * B) / (B * world))
+    G = k[:, None] * torch.cos(k[:, None] * x[None, :]) + 2.0 * x[None, :]
+    Y = torch.empty((B, N + 1), dtype=torch.float64, device=dev)
+    ctx = _lib.context(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_load0 = time.time()
+    for _ in range(warmup):
+        batched.toeplitz_apply(RULE, 0.5, h, G, N=N, out=Y)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count()
+    ev0.record()
+    for _ in range(steps):
+        batched.toeplitz_apply(RULE, 0.5, h, G, N=N, out=Y)
+    ev1.record()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    ms_per_step = ev0.elapsed_time(ev1) / steps
+    if world > 1:
+        t = torch.tensor([ms_per_step], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = t.item()
+    ctx.set_timing(True)
+    for _ in range(steps):
+        batched.toeplitz_apply(RULE, 0.5, h, G, N=N, out=Y)
+    ktimes = ctx.kernel_times()
+    ctx.set_timing(False)
+    clocks = sampler.stop(t_load0, time.time()) if rank == 0 else None
+    if rank == 0:
+        peak_dfma, peak_dmma = ctx.fp64_peak()
+        main_ms = ktimes['history_main'][0] / max(ktimes['history_main'][1], 1)
+        flop = float(N) * (N + 1) * B
+        achieved = flop / (main_ms * 1e-3) / 1e12
+        line = {
+            'metric': METRIC, 'value': world * B * N / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': steps,
+            'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(world, 1, 'cfg3'), 'gpu_launches': launches,
+            'clocks': clocks,
+            'roofline': {'kernel': 'frx_k2_history_main (tensor variant, fields as problems)', 'bound': 'tensor',
+                         'achieved': achieved, 'peak': peak_dmma, 'unit': 'TFLOP/s', 'frac': achieved / peak_dmma,
+                         'traffic': None, 'peak_source': 'measured in this run: register-only DMMA m8n8k4 probe '
+                         '(frx_measure_fp64_peak); DFMA probe %.2f TFLOP/s' % peak_dfma,
+                         'algorithmic_flop_per_launch': flop, 'kernel_ms': main_ms,
+                         'per_step_kernel_ms': {kk: v[0] / steps for kk, v in ktimes.items() if v[1]}},
+            'e2e': None, 'cpu_baseline': None,
+            'note': 'secondary workload (BASELINE configs[2]); the headline line is the default cfg2 run',
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
 # dram__bytes_read.sum + dram__bytes_write.sum of frx_k2_history_main per launch from the committed
 # `ncu --set full` capture (profiles/); None until a capture exists.
 K2_DRAM_TRAFFIC_BYTES = None
@@ -358,6 +445,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=('b200', 'reference'))
     ap.add_argument('--alphas-per-gpu', type=int, default=1)
+    ap.add_argument('--workload', default='cfg2', choices=('cfg2', 'cfg3'),
+                    help='cfg2 (default, the headline line; with --alphas-per-gpu 1250 it is the cfg5 sweep) or cfg3')
+    ap.add_argument('--skip-cpu', action='store_true', help='tuning only: skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

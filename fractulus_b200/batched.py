@@ -5,6 +5,7 @@ number is produced by the hand-written kernels in fractulus_b200/csrc.
     stencil_weights(approximation, side, alpha, lf, resolution)  -> row_ptr, offsets, weights   (K5)
     weights_table(approximation, alpha, h, N)                    -> WeightTables                 (K1)
     history(approximation, alpha, h, g)                          -> y[n_alpha, n_fields, N+1]    (K1+K2)
+    toeplitz_apply(approximation, alpha, h, G)                   -> Y[n_fields, N+1]             (K1+K3)
     history_host(approximation, alpha, h, g)                     -> NumPy in / NumPy out, copies inside
 """
 import collections
@@ -137,6 +138,24 @@ def history(approximation, alpha, h, g, N=None, out=None, validate=True):
     if squeeze_a:
         y = y[0]
     return y
+
+
+def toeplitz_apply(approximation, alpha, h, G, N=None, out=None):
+    """K3: Y[f, i] = sum_j T[i, j] G[f, j] for ONE alpha and many fields (BASELINE cfg 3), T the lower-triangular
+    growing-history operator.  G: cuda float64 [n_fields, n_g], field-major; T is never materialised."""
+    rule = _lib.RULES[approximation]
+    if not torch.is_tensor(G) or not G.is_cuda or G.dim() != 2:
+        raise TypeError('G must be a 2-D CUDA tensor [n_fields, n_g]')
+    G = G.to(torch.float64).contiguous()
+    n_fields, n_g = G.shape
+    if N is None:
+        N = n_g - 1 - (1 if approximation == 'simpson' else 0)
+    ctx, idx = _ctx_for(G.device)
+    if out is None:
+        out = torch.empty((n_fields, N + 1), dtype=torch.float64, device=G.device)
+    _lib.check(_lib.lib().frx_toeplitz_apply(ctx.handle, rule, float(alpha), float(h), int(N), n_fields, _ptr(G), n_g, n_g,
+                                             _ptr(out), N + 1))
+    return out
 
 
 def history_host(approximation, alpha, h, g, N=None, device=None):

@@ -46,6 +46,7 @@ extern "C" int frx_ctx_create(int device, frx_ctx** out) {
     c->device = device;
     FRX_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     c->stream = 0;
+    FRX_CUDA(cudaMalloc(&c->scalars, 256));
     *out = c;
     return FRX_OK;
 }
@@ -55,6 +56,7 @@ extern "C" int frx_ctx_destroy(frx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->io) cudaFree(ctx->io);
+    if (ctx->scalars) cudaFree(ctx->scalars);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < FRX_EV_POOL; ++i) {
         if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);

@@ -54,7 +54,7 @@ struct Geo {
     static constexpr bool TENSOR = false;
     static_assert(TI % TD == 0, "tile rows must be a multiple of the distance chunk");
     static_assert((TD / R) % 2 == 0, "inner loop is unrolled by two blocks");
-    static_assert(kLdcQuantum % TD == 0, "table padding quantum must cover a chunk");
+    static_assert(kNT == FRX_TAB_THREADS && kLdcQuantum % TD == 0, "table padding quantum must cover a chunk");
 };
 
 
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
 // prepare kernel: blocks [0, n_tab) generate the weight tables (K1); the remaining blocks build the padded
 // copies of the fields, gp[(f*n_pass + pass)*ldgp + padf + j] = g_j for 1 <= j <= N (for 'simpson' only the
 // nodes of the pass's parity: pass 0 even, pass 1 odd) and 0 elsewhere, and clear the tickets.
-__global__ void __launch_bounds__(kNT) frx_k12_prepare(int rule, const double* __restrict__ alpha, double h, int64_t N,
+__global__ void __launch_bounds__(FRX_TAB_BLOCK, 7) frx_k12_prepare(int rule, const double* __restrict__ alpha, double h, int64_t N,
                                                        double* __restrict__ cA, double* __restrict__ cB, int64_t ldc,
                                                        double* __restrict__ w0, double* __restrict__ mult, int64_t ldw,
                                                        double* __restrict__ cm1, int c_pad, int c_perm, int64_t n_tab,
@@ -410,43 +410,24 @@ __global__ void __launch_bounds__(kNT) frx_k12_prepare(int rule, const double* _
                                                        const double* __restrict__ g, int64_t ldg, int n_pass, int64_t n_fp,
                                                        int64_t ldgp, int padf, double* __restrict__ gp, int* __restrict__ tickets,
                                                        int64_t n_tickets) {
-    __shared__ frx_par P;
+    __shared__ frx_table_smem S;
     const int64_t bx = blockIdx.x;
     if (bx < n_tab) {
         const int64_t a = bx / tab_per_alpha;
-        if (threadIdx.x == 0) P = frx_par_init(rule, alpha[a]);
-        __syncthreads();
-        // storage slot X <-> distance x = X - c_pad; the DMMA kernel wants every aligned group of 8
-        // distances stored as [0 4 1 5 2 6 3 7] so that one LDS.128 yields both k-halves of an A fragment
-        const int64_t X = (bx - a * tab_per_alpha) * kNT + threadIdx.x;
-        if (X >= ldc) return;
-        const int64_t x = X - c_pad;
-        if (x < 0) {
-            cA[a * ldc + X] = 0.0;
-            if (cB) cB[a * ldc + X] = 0.0;
-            return;
-        }
-        const frx_table_entry e = frx_table_at(P, x, N, h);
-        const int64_t slot = c_perm ? c_pad + (x & ~(int64_t)7) + ((x & 3) * 2 + ((x >> 2) & 1)) : X;
-        cA[a * ldc + slot] = e.ca;
-        if (cB) cB[a * ldc + slot] = e.cb;
-        if (x <= N) {
-            w0[a * ldw + x] = e.w0;
-            mult[a * ldw + x] = e.mult;
-        }
-        if (x == 0) cm1[a] = rule == FRX_R_SIMPSON ? frx_raw_right_of_point(P) : 0.0;
+        frx_table_block(S, rule, alpha[a], h, N, (bx - a * tab_per_alpha) * FRX_TAB_ENTRIES, c_pad, c_perm, cA + a * ldc,
+                        cB ? cB + a * ldc : nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 + a);
         return;
     }
     const int64_t n_pad_blocks = gridDim.x - n_tab, pb = bx - n_tab;
-    const int64_t total = n_fp * ldgp;
-    for (int64_t e = pb * kNT + threadIdx.x; e < total; e += n_pad_blocks * kNT) {
+    const int64_t total = n_fp * ldgp, stride = n_pad_blocks * blockDim.x;
+    for (int64_t e = pb * blockDim.x + threadIdx.x; e < total; e += stride) {
         const int64_t fp = e / ldgp, x = e - fp * ldgp;
         const int64_t f = fp / n_pass, pass = fp - f * n_pass, j = x - padf;
         double v = 0.0;
         if (j >= 1 && j <= N && (n_pass == 1 || (j & 1) == pass)) v = g[f * ldg + j];
         gp[e] = v;
     }
-    for (int64_t e = pb * kNT + threadIdx.x; e < n_tickets; e += n_pad_blocks * kNT) tickets[e] = 0;
+    for (int64_t e = pb * blockDim.x + threadIdx.x; e < n_tickets; e += stride) tickets[e] = 0;
 }
 
 template <class G>
@@ -507,13 +488,13 @@ int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha,
     p.tickets = (int*)(ws + o_tick);
 
     {
-        const int64_t tab_per_alpha = (p.ldc + kNT - 1) / kNT, n_tab = tab_per_alpha * n_alpha;
+        const int64_t tab_per_alpha = (p.ldc + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES, n_tab = tab_per_alpha * n_alpha;
         const int64_t n_fp = n_fields * p.n_pass;
         int64_t n_pad = (n_fp * p.ldgp + 8 * kNT - 1) / (8 * kNT);
         if (n_pad > 4096) n_pad = 4096;
         FRX_REQUIRE(n_tab + n_pad < ((int64_t)1 << 31), FRX_ERR_INVALID_ARG, "problem too large for one launch");
         FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
-                   frx_k12_prepare<<<(unsigned)(n_tab + n_pad), kNT, 0, ctx->stream>>>(
+                   frx_k12_prepare<<<(unsigned)(n_tab + n_pad), FRX_TAB_BLOCK, 0, ctx->stream>>>(
                        rule, d_alpha, h, N, cA, cB, p.ldc, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
                        n_fp, p.ldgp, G::PADF, gp, p.tickets, n_tickets));
     }
@@ -545,16 +526,25 @@ extern "C" int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double
     FRX_REQUIRE(d_alpha && d_g && d_y, FRX_ERR_INVALID_ARG, "NULL buffer");
     FRX_CUDA(cudaSetDevice(ctx->device));
     // tile geometry: FRX_K2_VARIANT is a tuning/experiment switch, the default is the measured best
-    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 4;
+    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 9;
     switch (variant) {
         case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
         case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        case 2: return history_impl<Geo<8, 256, 5>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        case 3: return history_impl<Geo<8, 128, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        case 5: return history_impl<MGeo<4, 256, 2>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        case 6: return history_impl<MGeo<4, 128, 3>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        default: return history_impl<MGeo<4, 256, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 4: return history_impl<MGeo<4, 256, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        default: return history_impl<MGeo<4, 512, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
     }
+}
+
+// K3: one alpha, many fields -- the same tensor-core kernel with the fields as independent problems (the c window
+// of a unit is shared by all fields through L2)
+extern "C" int frx_toeplitz_apply(frx_ctx* ctx, int rule, double alpha, double h, int64_t N, int64_t n_fields,
+                                  const double* d_G, int64_t ldg, int64_t n_g, double* d_Y, int64_t ldy) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    int rc = frx_check_rule_alpha(rule, alpha);
+    if (rc) return rc;
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_CUDA(cudaMemcpyAsync(ctx->scalars, &alpha, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return frx_history(ctx, rule, 1, (const double*)ctx->scalars, h, N, n_fields, d_G, ldg, n_g, d_Y, ldy);
 }
 
 extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_alpha, double h, int64_t N,

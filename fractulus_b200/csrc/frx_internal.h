@@ -18,6 +18,7 @@ struct frx_ctx {
     // grow-only device buffers behind the *_host entry points (caller-facing inputs / outputs)
     void* io;
     size_t io_bytes;
+    void* scalars;         // 256 bytes of device memory for by-value scalar arguments
     // small pinned host staging for the *_host entry points
     void* pinned;
     size_t pinned_bytes;

@@ -1,7 +1,7 @@
 // frx_math.cuh -- FP64 scalar math for the weight generators, written so that every operation is
 // an explicitly rounded IEEE-754 op (no compiler FMA contraction): the same source compiled for
 // the host (g++ -ffp-contract=off, tests/_build helper) and for sm_100a gives the same bits,
-// except through frx_log_seed() (libm / libdevice log, see frx_log_dd).
+// except through the log() seed of frx_log_dd (libm vs libdevice), which moves results by < 2^-100.
 //
 // Why this exists: the reference computes its weights with glibc pow() (CPython float **) and
 // CPython's Lanczos math.gamma (reference fractulus/equation.py:45-57,68,72,90-99,105-172).  Weights
@@ -18,9 +18,11 @@
 // the big routines (exp/pow/gamma) are real calls on the device: the rule functions use up to a dozen
 // pow() each and inlining them all costs minutes of compile time for no measurable speed
 #define FRX_HD_CALL static __host__ __device__ __noinline__
+#define FRX_HD_MEMBER __host__ __device__ __forceinline__
 #else
 #define FRX_HD static inline
 #define FRX_HD_CALL static __attribute__((noinline))
+#define FRX_HD_MEMBER inline
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -166,16 +168,26 @@ FRX_HD_CALL frx_dd frx_log_dd(double x) {
 // edges: x ** 0 == 1, 0 ** y == 0 for y > 0; 0 ** negative raises ZeroDivisionError and a negative
 // base gives a complex number in the reference -- both are rejected on the host before launch, the
 // device returns NaN for them.
+FRX_HD_CALL double frx_pow_core(frx_dd L, double y) {  // exp(y * L) rounded once, L = log(x) as a double-double
+    frx_dd z = frx_dd_mul_d(L, y);
+    int e;
+    frx_dd v = frx_exp_dd(z.hi, z.lo, &e);
+    return frx_scale2(FRX_ADD(v.hi, v.lo), e);
+}
+// same value as frx_pow_cr(x, y) given L = frx_log_dd(x) (L is ignored for the exact special cases)
+FRX_HD double frx_pow_from_log(double x, double y, frx_dd L) {
+    if (y == 0.0 || x == 1.0) return 1.0;
+    if (x == 0.0) return y > 0.0 ? 0.0 : NAN;
+    if (!(x > 0.0)) return NAN;
+    if (y == 1.0) return x;
+    return frx_pow_core(L, y);
+}
 FRX_HD_CALL double frx_pow_cr(double x, double y) {
     if (y == 0.0 || x == 1.0) return 1.0;
     if (x == 0.0) return y > 0.0 ? 0.0 : NAN;
     if (!(x > 0.0)) return NAN;
     if (y == 1.0) return x;
-    frx_dd L = frx_log_dd(x);
-    frx_dd z = frx_dd_mul_d(L, y);
-    int e;
-    frx_dd v = frx_exp_dd(z.hi, z.lo, &e);
-    return frx_scale2(FRX_ADD(v.hi, v.lo), e);
+    return frx_pow_core(frx_log_dd(x), y);
 }
 
 // CPython's math.gamma for positive arguments (Modules/mathmodule.c m_tgamma: Lanczos sum N = 13,

@@ -114,36 +114,27 @@ extern "C" int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: weight tables.  grid = (ceil(ldc / 128), n_alpha); thread <-> table index x, which serves both
-// as a distance d (cA/cB) and as a row number i (w0/mult).  Row i is Settings(alpha, fl(i*h), i).
+// K1: weight tables (stand-alone entry; frx_history runs the same block routine inside its prepare
+// kernel).  grid = (ceil(ldc / 124), n_alpha), see frx_table.cuh.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) frx_k1_weights_table(int rule, const double* __restrict__ alpha, double h, int64_t N,
-                                                            double* __restrict__ cA, double* __restrict__ cB, int64_t ldc,
-                                                            double* __restrict__ w0, double* __restrict__ mult, int64_t ldw,
-                                                            double* __restrict__ cm1) {
-    __shared__ frx_par P;
+__global__ void __launch_bounds__(FRX_TAB_BLOCK) frx_k1_weights_table(int rule, const double* __restrict__ alpha, double h,
+                                                                        int64_t N, double* __restrict__ cA,
+                                                                        double* __restrict__ cB, int64_t ldc,
+                                                                        double* __restrict__ w0, double* __restrict__ mult,
+                                                                        int64_t ldw, double* __restrict__ cm1) {
+    __shared__ frx_table_smem S;
     const int64_t a = blockIdx.y;
-    if (threadIdx.x == 0) P = frx_par_init(rule, alpha[a]);
-    __syncthreads();
-    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= ldc) return;
-    const frx_table_entry e = frx_table_at(P, x, N, h);
-    cA[a * ldc + x] = e.ca;
-    if (cB) cB[a * ldc + x] = e.cb;
-    if (x <= N) {
-        w0[a * ldw + x] = e.w0;
-        mult[a * ldw + x] = e.mult;
-    }
-    if (x == 0 && cm1) cm1[a] = rule == FRX_R_SIMPSON ? frx_raw_right_of_point(P) : 0.0;
+    frx_table_block(S, rule, alpha[a], h, N, (int64_t)blockIdx.x * FRX_TAB_ENTRIES, 0, 0, cA + a * ldc,
+                    cB ? cB + a * ldc : nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 ? cm1 + a : nullptr);
 }
 
 int frx_launch_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                              double* d_cA, double* d_cB, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
                              double* d_cm1) {
-    dim3 grid((unsigned)((ldc + 127) / 128), (unsigned)n_alpha);
+    dim3 grid((unsigned)((ldc + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES), (unsigned)n_alpha);
     FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
-               frx_k1_weights_table<<<grid, 128, 0, ctx->stream>>>(rule, d_alpha, h, N, d_cA, d_cB, ldc, d_w0, d_mult,
-                                                                   ldw, d_cm1));
+               frx_k1_weights_table<<<grid, FRX_TAB_BLOCK, 0, ctx->stream>>>(rule, d_alpha, h, N, d_cA, d_cB, ldc, d_w0,
+                                                                               d_mult, ldw, d_cm1));
     return FRX_OK;
 }
 

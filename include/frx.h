@@ -127,6 +127,15 @@ int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, 
 int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_alpha, double h, int64_t N,
                      int64_t n_fields, const double* h_g, int64_t ldg, int64_t n_g, double* h_y, int64_t ldy);
 
+/* ---- K3: batched Toeplitz application (one alpha, many fields) ----------------------------------
+ * Y[f*ldy + i] = sum_j T[i][j] * G[f*ldg + j], T the (N+1)x(N+1) lower-triangular growing-history operator of
+ * (rule, alpha, h) -- the dense contraction of BASELINE cfg 3 (N = 16384 x 4096 fields).  Fields are stored
+ * field-major (each field contiguous along the node index, like frx_history); T is never materialised: the
+ * kernel builds its FP64 tensor-core (DMMA m8n8k4) A-fragments straight from the 1-D weight table.
+ * Same call pattern as above: row i of T is the reference stencil of Settings(alpha, i*h, i). */
+int frx_toeplitz_apply(frx_ctx* ctx, int rule, double alpha, double h, int64_t N, int64_t n_fields,
+                       const double* d_G, int64_t ldg, int64_t n_g, double* d_Y, int64_t ldy);
+
 /* ---- measurement aid ------------------------------------------------------------------------------
  * Register-only probes of the FP64 DFMA pipe and of mma.sync m8n8k4 f64 (DMMA): the denominators of the
  * FP64 rooflines bench.py reports (MEASURED_PEAKS.json carries no FP64 figure).  Best of `repeats`. */

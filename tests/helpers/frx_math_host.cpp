@@ -6,6 +6,7 @@ extern "C" {
 double t_pow_cr(double x, double y) { return frx_pow_cr(x, y); }
 double t_exp_cr(double x) { return frx_exp_cr(x); }
 double t_gamma_py(double x) { return frx_gamma_py(x); }
+double t_pow_from_log(double x, double y) { return frx_pow_from_log(x, y, x > 1 ? frx_log_dd(x) : frx_dd{0.0, 0.0}); }
 void t_log_dd(double x, double* hi, double* lo) { frx_dd L = frx_log_dd(x); *hi = L.hi; *lo = L.lo; }
 void t_pow_cr_many(const double* x, const double* y, double* out, long n) {
     for (long i = 0; i < n; ++i) out[i] = frx_pow_cr(x[i], y[i]);
