@@ -211,6 +211,8 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     if args.workload == 'cfg3':
         return run_b200_cfg3(args, world, rank, local_rank, dev)
+    if args.workload == 'cfg4':
+        return run_b200_cfg4(args, world, rank, local_rank, dev)
     A = args.alphas_per_gpu
     steps, warmup = args.steps, max(args.warmup, 3)
     h = 1.0 / N_NODES
@@ -433,6 +435,80 @@ def run_b200_cfg3(args, world, rank, local_rank, dev):
         dist.destroy_process_group()
     return 0
 
+
+def run_b200_cfg4(args, world, rank, local_rank, dev):
+    """BASELINE cfg 4 (`--workload cfg4 --solve-n {64,128,256}`): assemble + batch-solve 1e5 systems per GPU over a
+    400 alpha x 250 length-scale sweep.  Metric: solves/s."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fractulus_b200 import _lib, batched
+    n, n_alpha, n_ls = args.solve_n, 400, 250
+    n_sys = n_alpha * n_ls
+    steps, warmup = args.steps, max(args.warmup, 3)
+    h = 1.0 / (n + 1)
+    alpha = np.repeat(np.linspace(0.05, 0.95, n_alpha), n_ls)
+    res = np.tile(1.0 + (np.arange(n_ls) % 32), n_alpha)
+    xg = torch.arange(1, n + 1, dtype=torch.float64, device=dev) * h
+    rhs = torch.sin(math.pi * xg).repeat(n_sys, 1).contiguous()
+    ctx = _lib.context(local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_load0 = time.time()
+    for _ in range(warmup):
+        x = batched.assemble_solve(RULE, alpha, h, res, rhs)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count()
+    ev0.record()
+    for _ in range(steps):
+        x = batched.assemble_solve(RULE, alpha, h, res, rhs)
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = ctx.launch_count() - launches0
+    ms_per_step = ev0.elapsed_time(ev1) / steps
+    if world > 1:
+        t = torch.tensor([ms_per_step], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = t.item()
+    ctx.set_timing(True)
+    for _ in range(steps):
+        x = batched.assemble_solve(RULE, alpha, h, res, rhs)
+    ktimes = ctx.kernel_times()
+    ctx.set_timing(False)
+    clocks = sampler.stop(t_load0, time.time()) if rank == 0 else None
+    if rank == 0:
+        peak_dfma, _ = ctx.fp64_peak()
+        solve_ms = ktimes['solve'][0] / max(ktimes['solve'][1], 1)
+        # flops the band-limited elimination needs: per column k, nb multipliers + nb x (2nb + 1) updates (x2) + b
+        nb = np.minimum(res + 1, n - 1)
+        flop = float(np.sum(n * (2.0 * nb * (2 * nb + 1) + 3 * nb) + n * (4 * nb + 1)))
+        dense_flop = n_sys * (2.0 / 3.0 * n ** 3 + 2.0 * n * n)
+        achieved = flop / (solve_ms * 1e-3) / 1e12
+        line = {
+            'metric': 'fractional_bvp_solves_per_sec', 'value': world * n_sys / (ms_per_step * 1e-3), 'unit': 'solves/s',
+            'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'cfg4: assemble + batch-solve %d systems per GPU, n=%d unknowns, 400 alpha in [0.05,0.95] x 250 '
+                                   "length scales (resolution 1..32), rule 'caputo' Riesz-Caputo operator, rhs sin(pi x); step = K5 "
+                                   'stencil weights + K4 in-kernel assembly + LU' % (n_sys, n), 'n_systems': n_sys, 'n': n},
+            'gpu_launches': launches, 'clocks': clocks,
+            'roofline': {'kernel': 'frx_k4_assemble_solve', 'bound': 'fp64', 'achieved': achieved, 'peak': peak_dfma,
+                         'unit': 'TFLOP/s', 'frac': achieved / peak_dfma, 'traffic': None, 'kernel_ms': solve_ms,
+                         'algorithmic_flop_per_launch': flop, 'dense_lu_flop_for_context': dense_flop,
+                         'peak_source': 'measured in this run: register-only DFMA probe',
+                         'per_step_kernel_ms': {kk: v[0] / steps for kk, v in ktimes.items() if v[1]},
+                         'note': 'band-limited LU: flop count is what the banded elimination needs, not 2/3 n^3'},
+            'e2e': None, 'cpu_baseline': None,
+            'note': 'secondary workload (BASELINE configs[3]); parity unpinned (no reference solver)',
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
 # dram__bytes_read.sum + dram__bytes_write.sum of frx_k2_history_main per launch from the committed
 # `ncu --set full` capture (profiles/); None until a capture exists.
 K2_DRAM_TRAFFIC_BYTES = None
@@ -445,8 +521,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=('b200', 'reference'))
     ap.add_argument('--alphas-per-gpu', type=int, default=1)
-    ap.add_argument('--workload', default='cfg2', choices=('cfg2', 'cfg3'),
+    ap.add_argument('--workload', default='cfg2', choices=('cfg2', 'cfg3', 'cfg4'),
                     help='cfg2 (default, the headline line; with --alphas-per-gpu 1250 it is the cfg5 sweep) or cfg3')
+    ap.add_argument('--solve-n', type=int, default=128, help='cfg4: unknowns per system (64..256)')
     ap.add_argument('--skip-cpu', action='store_true', help='tuning only: skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -158,6 +158,47 @@ def toeplitz_apply(approximation, alpha, h, G, N=None, out=None):
     return out
 
 
+def _solve_params(alpha, h, res, n_sys=None):
+    a = np.ascontiguousarray(np.atleast_1d(np.asarray(alpha, dtype=np.float64)))
+    n_sys = len(a) if n_sys is None else n_sys
+    hh = np.ascontiguousarray(np.broadcast_to(np.asarray(h, dtype=np.float64), (n_sys,)))
+    rr = np.ascontiguousarray(np.broadcast_to(np.asarray(res, dtype=np.float64), (n_sys,)))
+    a = np.ascontiguousarray(np.broadcast_to(a, (n_sys,)))
+    return a, hh, rr
+
+
+def assemble_solve(approximation, alpha, h, res, rhs, return_info=False):
+    """K4: for every system s assemble the matrix of d/dx o D^alpha_RC(lf = res*h) o d/dx on n interior nodes
+    (u = 0 outside) in shared memory and solve A x = rhs[s] by in-kernel LU with partial pivoting.
+
+    alpha, h, res: scalars or 1-D arrays of length n_sys (host); rhs: cuda float64 [n_sys, n].  -> x [n_sys, n]."""
+    rule = _lib.RULES[approximation]
+    if not torch.is_tensor(rhs) or not rhs.is_cuda or rhs.dim() != 2:
+        raise TypeError('rhs must be a 2-D CUDA tensor [n_sys, n]')
+    rhs = rhs.to(torch.float64).contiguous()
+    n_sys, n = rhs.shape
+    a, hh, rr = _solve_params(alpha, h, res, n_sys)
+    ctx, idx = _ctx_for(rhs.device)
+    x = torch.empty_like(rhs)
+    info = torch.empty((n_sys,), dtype=torch.int32, device=rhs.device)
+    _lib.check(_lib.lib().frx_assemble_solve(ctx.handle, rule, n_sys, n, a.ctypes.data_as(_lib.c_double_p),
+                                             hh.ctypes.data_as(_lib.c_double_p), rr.ctypes.data_as(_lib.c_double_p),
+                                             _ptr(rhs), n, _ptr(x), n, _ptr(info)))
+    return (x, info) if return_info else x
+
+
+def assemble_dense(approximation, alpha, h, res, n, device=None):
+    """Verification aid for K4: the assembled matrices [n_sys, n, n] (row-major) as the solve kernel builds them."""
+    rule = _lib.RULES[approximation]
+    device = torch.device(device) if device is not None else default_device()
+    a, hh, rr = _solve_params(alpha, h, res)
+    ctx, idx = _ctx_for(device)
+    A = torch.empty((len(a), n, n), dtype=torch.float64, device=device)
+    _lib.check(_lib.lib().frx_assemble_dense(ctx.handle, rule, len(a), n, a.ctypes.data_as(_lib.c_double_p),
+                                             hh.ctypes.data_as(_lib.c_double_p), rr.ctypes.data_as(_lib.c_double_p), _ptr(A)))
+    return A
+
+
 def history_host(approximation, alpha, h, g, N=None, device=None):
     """Same operator through the host-buffer entry point frx_history_host: NumPy in, NumPy out, the
     host<->device copies happen inside the call."""

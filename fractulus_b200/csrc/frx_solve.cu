@@ -1,0 +1,268 @@
+// frx_solve.cu -- K4: assemble and solve batches of small fractional boundary-value systems in one kernel.
+//
+// PARITY UNPINNED: the reference has no assembler and no solver (upstream that is `fdm`'s job); the
+// oracle is oracle/assemble.py (reference stencils composed through the fdm shim + numpy.linalg.solve).
+//
+// System s (n unknowns u_1..u_n at x_k = k*h, h = h[s]): the composed operator
+//     Operator(central(h), Operator(create_riesz_caputo_stencil(rule, Settings(alpha, res*h, res)), Operator(central(h))))
+// (d/dx o D^alpha_RC o d/dx; stencils: reference equation.py:13-25, central difference:
+// reference test/integration/test_equation.py:64) expanded at every interior node.  Boundary rule DEFINED HERE
+// (the reference has none): homogeneous Dirichlet data, u = 0 at and beyond both ends.  That makes
+//     A[i][j] = a_{j-i},   a_k = ((T1 + T2) + T4) + T3,   |k| <= res + 1,
+//     T1 = (-1/h)*(rc_k*(1/h)), T2 = (-1/h)*(rc_{k+1}*(-1/h)), T4 = (1/h)*(rc_{k-1}*(1/h)), T3 = (1/h)*(rc_k*(-1/h))
+// with rc_o the Riesz-Caputo stencil weights -- the terms and their order are those of the dict-merging
+// expansion, so the assembled matrix is bit-identical to the oracle's wherever the stencil weights are.
+//
+// The matrix never touches HBM: each CTA builds it in shared memory from the 2*res+1 stencil weights (produced
+// for the whole batch by kernel K5), factors it by LU with partial pivoting, and solves.  A is banded
+// (half-bandwidth nb = res+1; partial pivoting fills at most 2*nb above the diagonal), so it is stored in LAPACK
+// band layout (3*nb+1 rows per column) whenever that is smaller than dense, and the elimination skips the
+// structurally-zero part of the trailing matrix: n = 256, res = 32 fits in 205 KB of shared memory.
+// Algorithmic bytes per system: 8*(2*res+1) weights + 8n rhs in, 8n solution out.
+#include <math.h>
+
+#include "frx_internal.h"
+
+namespace {
+
+constexpr int kSolveThreads = 128;
+
+struct SolveParams {
+    int64_t n_sys;
+    int n;
+    const double* rcw;       // Riesz-Caputo weights, system s at rcw[wptr[s] .. wptr[s+1])
+    const int64_t* wptr;
+    const double* h;
+    const double* rhs;
+    int64_t ldb;
+    double* x;
+    int64_t ldx;
+    int32_t* info;
+    double* dense;           // != NULL: write the assembled matrices (row-major n x n per system) and skip the solve
+    int max_store;           // doubles of matrix storage reserved per CTA
+};
+
+__global__ void __launch_bounds__(kSolveThreads) frx_k4_assemble_solve(const SolveParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* As = sm;                       // matrix storage
+    double* b = sm + p.max_store;          // [n] right-hand side / solution
+    double* a = b + n;                     // [2*nbmax+1] band coefficients a_k at a[k + nb]
+    __shared__ int s_piv, s_info;
+    for (int64_t s = blockIdx.x; s < p.n_sys; s += gridDim.x) {
+        // half-width of the Riesz-Caputo stencil: resolution, except 'rectangle' (resolution - 1, equation.py:70-71)
+        const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
+        int nb = res + 1;
+        const double ih = 1.0 / p.h[s];
+        const double* rc = p.rcw + p.wptr[s] + res;   // rc[o], o = -res..res
+        // ---- band coefficients -------------------------------------------------------------------------
+        for (int k = -nb + tid; k <= nb; k += kSolveThreads) {
+            double acc = 0.0;
+            bool any = false;
+            auto add = [&](double t) { acc = any ? __dadd_rn(acc, t) : t; any = true; };
+            if (k >= -res && k <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k], ih)));          // T1
+            if (k + 1 >= -res && k + 1 <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k + 1], -ih)));  // T2
+            if (k - 1 >= -res && k - 1 <= res) add(__dmul_rn(ih, __dmul_rn(rc[k - 1], ih)));    // T4
+            if (k >= -res && k <= res) add(__dmul_rn(ih, __dmul_rn(rc[k], -ih)));          // T3
+            a[k + nb] = acc;
+        }
+        if (tid == 0) s_info = 0;
+        __syncthreads();
+        if (p.dense) {
+            double* D = p.dense + s * (int64_t)n * n;
+            for (int e = tid; e < n * n; e += kSolveThreads) {
+                const int i = e / n, j = e - i * n, k = j - i;
+                D[e] = (k >= -nb && k <= nb) ? a[k + nb] : 0.0;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- assemble into shared memory ------------------------------------------------------------------
+        if (nb > n - 1) nb = n - 1;
+        const bool band = 3 * nb + 1 < n;
+        const int lda = band ? 3 * nb : n;        // element (i, j) lives at As[off + i + j*lda]
+        const int off = band ? 2 * nb : 0;
+        const int nb_a = res + 1;                 // index base of a[]
+        for (int j = warp; j < n; j += kSolveThreads / 32) {
+            const int lo = band ? max(0, j - 2 * nb) : 0, hi = band ? min(n - 1, j + nb) : n - 1;
+            for (int i = lo + lane; i <= hi; i += 32) {
+                const int k = j - i;
+                As[off + i + j * lda] = (k >= -nb_a && k <= nb_a) ? a[k + nb_a] : 0.0;
+            }
+        }
+        for (int i = tid; i < n; i += kSolveThreads) b[i] = p.rhs[s * p.ldb + i];
+        __syncthreads();
+        // ---- LU with partial pivoting on the augmented matrix [A | b], band-limited ------------------------
+        for (int k = 0; k < n; ++k) {
+            const int rmax = min(n - 1, k + nb);          // rows below are structurally zero in column k
+            const int cmax = min(n - 1, k + 2 * nb);      // columns right of it are zero in rows k..rmax
+            if (warp == 0) {                              // pivot: first row of maximal |A[i][k]|
+                double best = -1.0;
+                int bi = k;
+                for (int i = k + lane; i <= rmax; i += 32) {
+                    const double v = fabs(As[off + i + k * lda]);
+                    if (v > best) { best = v; bi = i; }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (lane == 0) {
+                    s_piv = bi;
+                    if (best == 0.0 && s_info == 0) s_info = k + 1;
+                }
+            }
+            __syncthreads();
+            const int pv = s_piv;
+            if (pv != k) {                                // swap rows k and pv (columns k..cmax and b)
+                for (int j = k + tid; j <= cmax; j += kSolveThreads) {
+                    const double t = As[off + k + j * lda];
+                    As[off + k + j * lda] = As[off + pv + j * lda];
+                    As[off + pv + j * lda] = t;
+                }
+                if (tid == 0) { const double t = b[k]; b[k] = b[pv]; b[pv] = t; }
+                __syncthreads();
+            }
+            // every warp computes the multipliers it needs itself (no extra barrier), then updates its columns
+            const double pivot = As[off + k + k * lda];
+            const double bk = b[k];
+            for (int i0 = k + 1; i0 <= rmax; i0 += 32) {
+                const int i = i0 + lane;
+                double l = 0.0;
+                if (i <= rmax) l = As[off + i + k * lda] / pivot;
+                for (int j = k + 1 + warp; j <= cmax; j += kSolveThreads / 32) {
+                    const double u = As[off + k + j * lda];
+                    if (i <= rmax) As[off + i + j * lda] = fma(-l, u, As[off + i + j * lda]);
+                }
+                if (warp == 0 && i <= rmax) b[i] = fma(-l, bk, b[i]);
+            }
+            __syncthreads();
+        }
+        // ---- back substitution on U (upper bandwidth 2*nb), one warp, column oriented ---------------------
+        if (warp == 0) {
+            for (int k = n - 1; k >= 0; --k) {
+                const double xk = b[k] / As[off + k + k * lda];
+                __syncwarp();
+                if (lane == 0) b[k] = xk;
+                const int lo = max(0, k - 2 * nb);
+                for (int i = lo + lane; i < k; i += 32) b[i] = fma(-As[off + i + k * lda], xk, b[i]);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += kSolveThreads) p.x[s * p.ldx + i] = b[i];
+        if (tid == 0 && p.info) p.info[s] = s_info;
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
+                        const double* h_res, const double* d_rhs, int64_t ldb, double* d_x, int64_t ldx, int32_t* d_info,
+                        double* d_dense) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    FRX_REQUIRE(n_sys >= 0 && n >= 1 && n <= 4096, FRX_ERR_INVALID_ARG, "bad n_sys / n");
+    if (n_sys == 0) return FRX_OK;
+    FRX_REQUIRE(h_alpha && h_h && h_res, FRX_ERR_INVALID_ARG, "NULL parameter array");
+    FRX_REQUIRE(d_dense || (d_rhs && d_x && ldb >= n && ldx >= n), FRX_ERR_INVALID_ARG, "NULL buffer or bad leading dimension");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    // host pass: domain checks, stencil row pointers, storage requirement
+    int64_t* wptr = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_sys + 1));
+    double* lf = (double*)malloc(sizeof(double) * (size_t)n_sys);
+    FRX_REQUIRE(wptr && lf, FRX_ERR_ALLOC, "host allocation failed");
+    wptr[0] = 0;
+    int max_store = 0, max_res = 0, rc = FRX_OK;
+    for (int64_t s = 0; s < n_sys && !rc; ++s) {
+        int32_t first, count;
+        rc = frx_stencil_layout(rule, FRX_SIDE_RIESZ_CAPUTO, h_alpha[s], h_res[s], &first, &count);
+        if (!rc && !(h_h[s] > 0.0)) { frx_set_error("grid step must be positive"); rc = FRX_ERR_DOMAIN; }
+        if (!rc && (rule == FRX_RULE_SIMPSON && ((int64_t)h_res[s] & 1))) {
+            frx_set_error("'simpson' with odd resolution has a node right of the point; use an even resolution here");
+            rc = FRX_ERR_DOMAIN;
+        }
+        if (rc) break;
+        wptr[s + 1] = wptr[s] + count;
+        lf[s] = h_res[s] * h_h[s];
+        int res = (count - 1) / 2, nb = res + 1 > n - 1 ? n - 1 : res + 1;   // res = stencil half-width
+        int store = d_dense ? 0 : ((3 * nb + 1 < n) ? n * (3 * nb + 1) : n * n);  // band columns are 3nb+1 long
+        if (store > max_store) max_store = store;
+        if (res > max_res) max_res = res;
+    }
+    if (rc) { free(wptr); free(lf); return rc; }
+    const size_t smem = sizeof(double) * ((size_t)max_store + n + 2 * (max_res + 1) + 1 + 8);
+    int smem_max = 0;
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    if (!d_dense && smem > (size_t)smem_max) {
+        free(wptr); free(lf);
+        frx_set_error("system too large for shared memory: needs %zu bytes, device offers %d (n = %d, max resolution %d)",
+                      smem, smem_max, n, max_res);
+        return FRX_ERR_INVALID_ARG;
+    }
+    // workspace: [alpha | lf | res | h][wptr][rc weights]
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += frx_align_up(bytes, 256); return o; };
+    const size_t o_par = carve(sizeof(double) * 4 * (size_t)n_sys);
+    const size_t o_wptr = carve(sizeof(int64_t) * (size_t)(n_sys + 1) * 2);
+    const size_t o_w = carve(sizeof(double) * (size_t)wptr[n_sys]);
+    rc = frx_ws_reserve(ctx, off);
+    if (rc) { free(wptr); free(lf); return rc; }
+    char* ws = (char*)ctx->ws;
+    double* d_par = (double*)(ws + o_par);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, h_alpha, sizeof(double) * n_sys, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + n_sys, lf, sizeof(double) * n_sys, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + 2 * n_sys, h_res, sizeof(double) * n_sys, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + 3 * n_sys, h_h, sizeof(double) * n_sys, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + o_wptr, wptr, sizeof(int64_t) * (n_sys + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // host staging arrays are freed below
+    if (e != cudaSuccess) {
+        free(wptr); free(lf);
+        frx_set_error("parameter upload failed: %s", cudaGetErrorString(e));
+        return FRX_ERR_CUDA;
+    }
+    // K5 for the whole batch (row pointer already on the device)
+    extern int frx_launch_stencil_weights(frx_ctx*, int, int, int64_t, const double*, const double*, const double*,
+                                          const int64_t*, int32_t*, double*);
+    rc = frx_launch_stencil_weights(ctx, rule, FRX_SIDE_RIESZ_CAPUTO, n_sys, d_par, d_par + n_sys, d_par + 2 * n_sys,
+                                    (const int64_t*)(ws + o_wptr), nullptr, (double*)(ws + o_w));
+    free(wptr); free(lf);
+    if (rc) return rc;
+    SolveParams p;
+    p.n_sys = n_sys;
+    p.n = n;
+    p.rcw = (const double*)(ws + o_w);
+    p.wptr = (const int64_t*)(ws + o_wptr);
+    p.h = d_par + 3 * n_sys;
+    p.rhs = d_rhs;
+    p.ldb = ldb;
+    p.x = d_x;
+    p.ldx = ldx;
+    p.info = d_info;
+    p.dense = d_dense;
+    p.max_store = (max_store + 1) & ~1;
+    const size_t dyn = smem;
+    FRX_REQUIRE(dyn <= (size_t)smem_max, FRX_ERR_INVALID_ARG, "system too large for shared memory");
+    FRX_CUDA(cudaFuncSetAttribute(frx_k4_assemble_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    int per_sm = 1;
+    FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4_assemble_solve, kSolveThreads, dyn));
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)ctx->sm_count * per_sm;
+    if (grid > n_sys) grid = n_sys;
+    FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4_assemble_solve<<<(unsigned)grid, kSolveThreads, dyn, ctx->stream>>>(p));
+    return FRX_OK;
+}
+
+extern "C" int frx_assemble_solve(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
+                                  const double* h_res, const double* d_rhs, int64_t ldb, double* d_x, int64_t ldx,
+                                  int32_t* d_info) {
+    return solve_common(ctx, rule, n_sys, n, h_alpha, h_h, h_res, d_rhs, ldb, d_x, ldx, d_info, nullptr);
+}
+
+extern "C" int frx_assemble_dense(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
+                                  const double* h_res, double* d_A) {
+    FRX_REQUIRE(d_A != nullptr, FRX_ERR_INVALID_ARG, "d_A is NULL");
+    return solve_common(ctx, rule, n_sys, n, h_alpha, h_h, h_res, nullptr, 0, nullptr, 0, nullptr, d_A);
+}

@@ -62,6 +62,16 @@ __global__ void __launch_bounds__(128) frx_k5_stencil_weights(int rule, int side
     }
 }
 
+// K5 launch with the row pointer already on the device (used by frx_assemble_solve)
+int frx_launch_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_settings, const double* d_alpha,
+                               const double* d_lf, const double* d_resolution, const int64_t* d_row_ptr,
+                               int32_t* d_offsets, double* d_weights) {
+    FRX_LAUNCH(ctx, FRX_K_STENCIL,
+               frx_k5_stencil_weights<<<(unsigned)n_settings, 128, 0, ctx->stream>>>(
+                   rule, side, d_alpha, d_lf, d_resolution, d_row_ptr, d_offsets, d_weights));
+    return FRX_OK;
+}
+
 extern "C" int frx_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_settings, const double* d_alpha,
                                    const double* d_lf, const double* d_resolution, const int64_t* h_row_ptr,
                                    int32_t* d_offsets, double* d_weights) {
@@ -77,10 +87,8 @@ extern "C" int frx_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_s
     int rc = frx_ws_reserve(ctx, bytes);
     if (rc) return rc;
     FRX_CUDA(cudaMemcpyAsync(ctx->ws, h_row_ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    FRX_LAUNCH(ctx, FRX_K_STENCIL,
-               frx_k5_stencil_weights<<<(unsigned)n_settings, 128, 0, ctx->stream>>>(
-                   rule, side, d_alpha, d_lf, d_resolution, (const int64_t*)ctx->ws, d_offsets, d_weights));
-    return FRX_OK;
+    return frx_launch_stencil_weights(ctx, rule, side, n_settings, d_alpha, d_lf, d_resolution, (const int64_t*)ctx->ws,
+                                      d_offsets, d_weights);
 }
 
 extern "C" int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double alpha, double lf, double resolution,

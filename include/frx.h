@@ -136,6 +136,23 @@ int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_al
 int frx_toeplitz_apply(frx_ctx* ctx, int rule, double alpha, double h, int64_t N, int64_t n_fields,
                        const double* d_G, int64_t ldg, int64_t n_g, double* d_Y, int64_t ldy);
 
+/* ---- K4: assemble + batch-solve small fractional boundary-value systems -------------------------
+ * No counterpart in the reference (upstream `fdm` would do it): PARITY UNPINNED, see DESIGN.md section 6.
+ * System s has n unknowns u_1..u_n at x_k = k*h[s] and the matrix of
+ *   Operator(central(h), Operator(create_riesz_caputo_stencil(rule, Settings(alpha[s], res[s]*h[s], res[s])),
+ *            Operator(central(h))))
+ * (reference equation.py:13-25 for the stencil, test/integration/test_equation.py:64 for the central difference)
+ * expanded at every interior node, with u = 0 at and beyond both ends.  The matrix is built in shared memory from
+ * the 2*res+1 stencil weights and solved there by LU with partial pivoting; it never exists in HBM.
+ * Parameter arrays are HOST arrays (3 doubles per system); rhs / x are device arrays, system s at s*ldb / s*ldx.
+ * d_info[s] = 0, or k+1 if the k-th pivot is exactly zero (may be NULL).  All systems of a call share n. */
+int frx_assemble_solve(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
+                       const double* h_res, const double* d_rhs, int64_t ldb, double* d_x, int64_t ldx,
+                       int32_t* d_info);
+/* verification aid: the assembled matrices, row-major n x n per system, written to d_A (no solve) */
+int frx_assemble_dense(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
+                       const double* h_res, double* d_A);
+
 /* ---- measurement aid ------------------------------------------------------------------------------
  * Register-only probes of the FP64 DFMA pipe and of mma.sync m8n8k4 f64 (DMMA): the denominators of the
  * FP64 rooflines bench.py reports (MEASURED_PEAKS.json carries no FP64 figure).  Best of `repeats`. */

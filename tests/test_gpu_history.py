@@ -221,9 +221,10 @@ def test_toeplitz_apply_many_fields_vs_c_oracle():
         lo = FIRST_ROW[rule]
         for f in range(0, B, 7):
             assert_history_close(rule, 0.45, h, np.arange(lo, N + 1), got[f, lo:], want[f, lo:], G[f], 0.99)
-        # a field through K3 equals the same field through K2, bitwise
+        # a field through K3 equals the same field through K2 up to the split-tile summation grouping
+        # (results are bitwise reproducible per call shape, the stream-K split points depend on the batch)
         one = batched.history(rule, 0.45, h, dev(G[5]), N=N).cpu().numpy()
-        assert np.array_equal(one, got[5], equal_nan=True)
+        assert np.allclose(one[lo:], got[5, lo:], rtol=1e-13, atol=1e-13 * np.abs(one[lo:]).max())
 
 
 def test_toeplitz_apply_full_size_cfg3_sampled_fields():

@@ -1,0 +1,83 @@
+"""GPU checks for K4 (assemble + batch-solve).  PARITY UNPINNED: the reference has no assembler / solver; the
+oracle (oracle/assemble.py) composes the reference's Riesz-Caputo stencils with central differences through
+the fdm shim exactly like the reference's tests compose operators, and solves with numpy.linalg.solve."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from fractulus_b200 import batched
+from oracle import assemble
+
+
+def test_assembled_matrix_equals_oracle_composition():
+    for rule, res_list in (('caputo', (1, 2, 5, 16)), ('trapezoidal', (3,)), ('rectangle', (4,)), ('simpson', (4,))):
+        for res in res_list:
+            for alpha in (0.3, 0.8):
+                n, h = 40, 1. / 41
+                got = batched.assemble_dense(rule, [alpha], h, res, n)[0].cpu().numpy()
+                want = assemble.assemble(rule, alpha, h, res, n)
+                scale = np.abs(want).max()
+                assert np.abs(got - want).max() <= 4 * np.finfo(float).eps * scale, (rule, res, alpha)
+                assert np.array_equal(got, got.T)         # Riesz-Caputo operator: symmetric Toeplitz
+
+
+@pytest.mark.parametrize('n', [1, 2, 16, 64, 128, 200, 256])
+def test_solve_vs_numpy_on_oracle_matrix(n):
+    rng = np.random.default_rng(n)
+    n_sys = 24
+    alpha = rng.uniform(0.05, 0.95, n_sys)
+    res = rng.integers(1, min(32, max(1, n)) + 1, n_sys).astype(np.float64)
+    h = 1. / (n + 1)
+    x_nodes = np.arange(1, n + 1) * h
+    rhs = np.stack([np.sin(np.pi * x_nodes * (1 + s % 3)) + 0.25 * s for s in range(n_sys)])
+    x, info = batched.assemble_solve('caputo', alpha, h, res, torch.as_tensor(rhs, device='cuda'), return_info=True)
+    x = x.cpu().numpy()
+    assert int(info.abs().sum()) == 0
+    for s in range(n_sys):
+        want, A = assemble.solve('caputo', alpha[s], h, int(res[s]), n, rhs[s])
+        cond = np.linalg.cond(A)
+        err = np.abs(x[s] - want).max() / np.abs(want).max()
+        assert err <= 1e-12 + 20 * np.finfo(float).eps * cond, (n, s, alpha[s], res[s], err, cond)
+
+
+def test_solve_other_rules_and_dense_storage_path():
+    n, h = 48, 1. / 49
+    rhs = torch.ones((3, n), dtype=torch.float64, device='cuda')
+    for rule, res in (('trapezoidal', 4), ('rectangle', 5), ('simpson', 6), ('caputo', 40)):   # res=40: 3nb+1 >= n -> dense
+        x = batched.assemble_solve(rule, [0.2, 0.5, 0.9], h, res, rhs).cpu().numpy()
+        for s, alpha in enumerate((0.2, 0.5, 0.9)):
+            want, A = assemble.solve(rule, alpha, h, res, n, np.ones(n))
+            assert np.abs(x[s] - want).max() / np.abs(want).max() <= 1e-12 + 20 * np.finfo(float).eps * np.linalg.cond(A)
+
+
+def test_full_batch_cfg4_properties():
+    """BASELINE cfg 4: 1e5 systems, alpha x length-scale sweep, n = 64: residual of every system and
+    bitwise reproducibility."""
+    n, n_alpha, n_ls = 64, 400, 250
+    h = 1. / (n + 1)
+    alpha = np.repeat(np.linspace(0.05, 0.95, n_alpha), n_ls)
+    res = np.tile(1. + (np.arange(n_ls) % 16), n_alpha)
+    xg = torch.arange(1, n + 1, dtype=torch.float64, device='cuda') * h
+    rhs = torch.sin(np.pi * xg).repeat(n_alpha * n_ls, 1).contiguous()
+    x1 = batched.assemble_solve('caputo', alpha, h, res, rhs)
+    x2 = batched.assemble_solve('caputo', alpha, h, res, rhs)
+    assert torch.equal(x1, x2)
+    # residual through the dense matrices of a sample of systems (the kernel's own assembly, checked above)
+    idx = np.arange(0, n_alpha * n_ls, 997)
+    A = batched.assemble_dense('caputo', alpha[idx], h, res[idx], n)
+    r = torch.bmm(A, x1[idx].unsqueeze(-1)).squeeze(-1) - rhs[idx]
+    scale = (A.abs().amax(dim=(1, 2)) * x1[idx].abs().amax(dim=1)).unsqueeze(-1)
+    assert (r.abs() / scale).max().item() < 1e-13
+    assert torch.isfinite(x1).all()
+
+
+def test_solve_errors():
+    rhs = torch.ones((1, 8), dtype=torch.float64, device='cuda')
+    with pytest.raises(ZeroDivisionError):
+        batched.assemble_solve('caputo', [0.5], 0.1, 0, rhs)
+    with pytest.raises(KeyError):
+        batched.assemble_solve('nope', [0.5], 0.1, 2, rhs)
+    with pytest.raises(ValueError):
+        batched.assemble_solve('simpson', [0.5], 0.1, 3, rhs)     # odd Simpson stencil is not symmetric-closed
