@@ -102,11 +102,11 @@ def cpu_reference_leg(budget_s):
     from oracle import clib
     h = 1.0 / N_NODES
     g = smooth_field_np(N_NODES + 2, h)
-    cores = clib.num_threads()
+    cores = len(os.sched_getaffinity(0))     # all host threads we may use (torchrun pins OMP_NUM_THREADS=1: override)
     # calibrate on a thin sample, then size the stride for the time budget
     rows = np.arange(4096, N_NODES + 1, 4096, dtype=np.int64)
     t0 = time.perf_counter()
-    clib.history_rows_naive(RULE, 0.5, h, g, rows)
+    clib.history_rows_naive(RULE, 0.5, h, g, rows, n_threads=cores)
     t_cal = time.perf_counter() - t0
     w_cal = float(np.sum(rows + 1.0))
     total_w = N_NODES * (N_NODES + 3) / 2.0
@@ -116,7 +116,7 @@ def cpu_reference_leg(budget_s):
     if rows[-1] != N_NODES:
         rows = np.append(rows, N_NODES)
     t0 = time.perf_counter()
-    y = clib.history_rows_naive(RULE, 0.5, h, g, rows)
+    y = clib.history_rows_naive(RULE, 0.5, h, g, rows, n_threads=cores)
     dt = time.perf_counter() - t0
     t_full = dt * total_w / float(np.sum(rows + 1.0))
     assert np.all(np.isfinite(y))
@@ -241,14 +241,18 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     t_load0 = time.time()
-    # warm-up: W steps, and at least ~1 s of load so the sampled clocks are clocks under load
+    # warm-up: ~1 s of the compute part alone (rank-local loop, so no collective inside: every rank may run a
+    # different number of iterations) so that the sampled clocks are clocks under load, then W full steps
     t0 = time.perf_counter()
     n = 0
-    while n < warmup or time.perf_counter() - t0 < 1.0:
-        step()
+    while time.perf_counter() - t0 < 1.0:
+        batched.history(RULE, my_alphas, h, g, N=N_NODES, out=y, validate=False)
         n += 1
         if n % 16 == 0:
             torch.cuda.synchronize()
+    barrier()
+    for _ in range(warmup):
+        step()
     barrier()
 
     # ---- timed region: exactly K steps, device time per step, L2 flushed between steps -------------
@@ -355,7 +359,7 @@ def run_b200(args):
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
             'wall_s_timed_region': wall, 'ms_per_step_min': min(ms), 'ms_per_step_max': max(ms),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -429,7 +433,7 @@ def run_b200_cfg3(args, world, rank, local_rank, dev):
             'e2e': None, 'cpu_baseline': None,
             'note': 'secondary workload (BASELINE configs[2]); the headline line is the default cfg2 run',
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -503,11 +507,18 @@ def run_b200_cfg4(args, world, rank, local_rank, dev):
             'e2e': None, 'cpu_baseline': None,
             'note': 'secondary workload (BASELINE configs[3]); parity unpinned (no reference solver)',
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+_JSON_LINES = []
+
+
+def emit(line):
+    _JSON_LINES.append(json.dumps(line))
+
 
 # dram__bytes_read.sum + dram__bytes_write.sum of frx_k2_history_main per launch from the committed
 # `ncu --set full` capture (profiles/); None until a capture exists.
@@ -528,7 +539,20 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
-    return run_b200(args)
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        if _JSON_LINES:
+            sys.stdout.write('\n'.join(_JSON_LINES) + '\n')
+            sys.stdout.flush()
 
 
 if __name__ == '__main__':

@@ -40,6 +40,7 @@ struct SolveParams {
     int32_t* info;
     double* dense;           // != NULL: write the assembled matrices (row-major n x n per system) and skip the solve
     int max_store;           // doubles of matrix storage reserved per CTA
+    int a_len;               // doubles reserved for the band coefficients
 };
 
 __global__ void __launch_bounds__(kSolveThreads) frx_k4_assemble_solve(const SolveParams p) {
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(kSolveThreads) frx_k4_assemble_solve(const Sol
     double* As = sm;                       // matrix storage
     double* b = sm + p.max_store;          // [n] right-hand side / solution
     double* a = b + n;                     // [2*nbmax+1] band coefficients a_k at a[k + nb]
-    __shared__ int s_piv, s_info;
+    int* piv = reinterpret_cast<int*>(a + p.a_len);   // [n] pivot rows
+    __shared__ int s_info;
     for (int64_t s = blockIdx.x; s < p.n_sys; s += gridDim.x) {
         // half-width of the Riesz-Caputo stencil: resolution, except 'rectangle' (resolution - 1, equation.py:70-71)
         const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
@@ -92,51 +94,73 @@ __global__ void __launch_bounds__(kSolveThreads) frx_k4_assemble_solve(const Sol
         }
         for (int i = tid; i < n; i += kSolveThreads) b[i] = p.rhs[s * p.ldb + i];
         __syncthreads();
-        // ---- LU with partial pivoting on the augmented matrix [A | b], band-limited ------------------------
+        // ---- LU with partial pivoting on the augmented matrix [A | b], band-limited, ONE barrier per column ----
+        // Warp 0 is the pivot warp: as soon as it has updated column k+1 it finds that column's pivot, swaps it to
+        // the diagonal and scales the sub-column into multipliers in place (piv[k+1]).  Warps 1..3 update the other
+        // columns of the window (lanes over the <= nb rows, the row interchange folded into the update) and b.
+        auto AS = [&](int i, int j) -> double& { return As[off + i + j * lda]; };
+        auto finalize_column = [&](int c) {       // warp 0, all lanes
+            const int rm = min(n - 1, c + nb);
+            const int i0 = c + lane, i1 = c + lane + 32;
+            const double v0 = i0 <= rm ? AS(i0, c) : 0.0, v1 = i1 <= rm ? AS(i1, c) : 0.0;
+            double best = i0 <= rm ? fabs(v0) : -1.0;
+            int bi = i0;
+            if (i1 <= rm && fabs(v1) > best) { best = fabs(v1); bi = i1; }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            const int pv = bi;
+            const double pval = AS(pv, c), top = AS(c, c);
+            const double r = 1.0 / pval;
+            __syncwarp();
+            if (lane == 0) {
+                AS(c, c) = pval;
+                piv[c] = pv;
+                if (pval == 0.0 && s_info == 0) s_info = c + 1;
+            } else if (i0 <= rm) {
+                AS(i0, c) = (i0 == pv ? top : v0) * r;
+            }
+            if (i1 <= rm) AS(i1, c) = (i1 == pv ? top : v1) * r;
+            __syncwarp();
+        };
+        if (warp == 0) finalize_column(0);
+        __syncthreads();
+        constexpr int kWorkers = kSolveThreads / 32 - 1;
         for (int k = 0; k < n; ++k) {
             const int rmax = min(n - 1, k + nb);          // rows below are structurally zero in column k
             const int cmax = min(n - 1, k + 2 * nb);      // columns right of it are zero in rows k..rmax
-            if (warp == 0) {                              // pivot: first row of maximal |A[i][k]|
-                double best = -1.0;
-                int bi = k;
-                for (int i = k + lane; i <= rmax; i += 32) {
-                    const double v = fabs(As[off + i + k * lda]);
-                    if (v > best) { best = v; bi = i; }
+            const int pv = piv[k];
+            const int i0 = k + 1 + lane, i1 = k + 33 + lane;
+            const double l0 = i0 <= rmax ? AS(i0, k) : 0.0, l1 = i1 <= rmax ? AS(i1, k) : 0.0;
+            auto update_column = [&](int j) {
+                const double ak = AS(k, j), u = AS(pv, j);             // u: the pivot row's entry after the interchange
+                const double v0 = i0 <= rmax ? (i0 == pv ? ak : AS(i0, j)) : 0.0;
+                const double v1 = i1 <= rmax ? (i1 == pv ? ak : AS(i1, j)) : 0.0;
+                __syncwarp();
+                if (lane == 0) AS(k, j) = u;
+                if (i0 <= rmax) AS(i0, j) = fma(-l0, u, v0);
+                if (i1 <= rmax) AS(i1, j) = fma(-l1, u, v1);
+            };
+            if (warp == 0) {
+                if (k + 1 <= cmax) {
+                    update_column(k + 1);
+                    __syncwarp();
+                    finalize_column(k + 1);
                 }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, d);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            } else {
+                for (int j = k + 1 + warp; j <= cmax; j += kWorkers) update_column(j);
+                if (warp == 1 + (k % kWorkers)) {                     // right-hand side, rotated over the workers
+                    const double bk = b[k], u = b[pv];
+                    const double v0 = i0 <= rmax ? (i0 == pv ? bk : b[i0]) : 0.0;
+                    const double v1 = i1 <= rmax ? (i1 == pv ? bk : b[i1]) : 0.0;
+                    __syncwarp();
+                    if (lane == 0) b[k] = u;
+                    if (i0 <= rmax) b[i0] = fma(-l0, u, v0);
+                    if (i1 <= rmax) b[i1] = fma(-l1, u, v1);
                 }
-                if (lane == 0) {
-                    s_piv = bi;
-                    if (best == 0.0 && s_info == 0) s_info = k + 1;
-                }
-            }
-            __syncthreads();
-            const int pv = s_piv;
-            if (pv != k) {                                // swap rows k and pv (columns k..cmax and b)
-                for (int j = k + tid; j <= cmax; j += kSolveThreads) {
-                    const double t = As[off + k + j * lda];
-                    As[off + k + j * lda] = As[off + pv + j * lda];
-                    As[off + pv + j * lda] = t;
-                }
-                if (tid == 0) { const double t = b[k]; b[k] = b[pv]; b[pv] = t; }
-                __syncthreads();
-            }
-            // every warp computes the multipliers it needs itself (no extra barrier), then updates its columns
-            const double pivot = As[off + k + k * lda];
-            const double bk = b[k];
-            for (int i0 = k + 1; i0 <= rmax; i0 += 32) {
-                const int i = i0 + lane;
-                double l = 0.0;
-                if (i <= rmax) l = As[off + i + k * lda] / pivot;
-                for (int j = k + 1 + warp; j <= cmax; j += kSolveThreads / 32) {
-                    const double u = As[off + k + j * lda];
-                    if (i <= rmax) As[off + i + j * lda] = fma(-l, u, As[off + i + j * lda]);
-                }
-                if (warp == 0 && i <= rmax) b[i] = fma(-l, bk, b[i]);
             }
             __syncthreads();
         }
@@ -192,7 +216,8 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         if (res > max_res) max_res = res;
     }
     if (rc) { free(wptr); free(lf); return rc; }
-    const size_t smem = sizeof(double) * ((size_t)max_store + n + 2 * (max_res + 1) + 1 + 8);
+    const int a_len = (2 * (max_res + 1) + 1 + 1) & ~1;
+    const size_t smem = sizeof(double) * ((size_t)((max_store + 1) & ~1) + n + a_len) + sizeof(int) * (size_t)(n + 4);
     int smem_max = 0;
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     if (!d_dense && smem > (size_t)smem_max) {
@@ -243,6 +268,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     p.info = d_info;
     p.dense = d_dense;
     p.max_store = (max_store + 1) & ~1;
+    p.a_len = a_len;
     const size_t dyn = smem;
     FRX_REQUIRE(dyn <= (size_t)smem_max, FRX_ERR_INVALID_ARG, "system too large for shared memory");
     FRX_CUDA(cudaFuncSetAttribute(frx_k4_assemble_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
