@@ -74,3 +74,24 @@ int frx_check_settings(int rule, double alpha, double resolution);
 int frx_check_rule_alpha(int rule, double alpha);
 
 static inline size_t frx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#ifdef __CUDACC__
+#include <utility>
+// launch `kernel` as a programmatic dependent of the previous kernel in the stream: it may start while its
+// predecessor is still running and must execute griddepcontrol.wait before touching the predecessor's output
+template <typename... KArgs, typename... Args>
+static inline cudaError_t frx_launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                               cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif

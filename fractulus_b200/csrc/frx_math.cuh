@@ -96,7 +96,7 @@ FRX_HD frx_dd frx_dd_mul_d(frx_dd a, double b) {
 // z = (64 q + j) ln2/64 + r, |r| <= ln2/128: exp(z) = 2^q * 2^(j/64) * exp(r); exp(r) is a Taylor
 // series whose terms n >= 6 fit in plain double (they are < 2^-54 of the sum) and whose terms
 // n <= 5 are accumulated in double-double.
-FRX_HD_CALL frx_dd frx_exp_dd(double zh, double zl, int* scale2) {
+FRX_HD frx_dd frx_exp_dd_inline(double zh, double zl, int* scale2) {
     double kd = rint(FRX_MUL(zh, FRX_64_OVER_LN2));
     double a = FRX_FMA(-kd, FRX_LN2_64_C1, zh);               // exact: C1 has 30 bits
     frx_dd b = frx_two_prod(kd, FRX_LN2_64_C2);               // exact
@@ -129,6 +129,9 @@ FRX_HD_CALL frx_dd frx_exp_dd(double zh, double zl, int* scale2) {
 #endif
     return frx_dd_mul(acc, tj);
 }
+
+// out-of-line copy for the call sites where code size matters more than overlap (see FRX_HD_CALL above)
+FRX_HD_CALL frx_dd frx_exp_dd(double zh, double zl, int* scale2) { return frx_exp_dd_inline(zh, zl, scale2); }
 
 FRX_HD double frx_scale2(double v, int e) {  // v * 2^e, exact while the result stays normal
 #if defined(__CUDA_ARCH__)
@@ -174,6 +177,13 @@ FRX_HD_CALL double frx_pow_core(frx_dd L, double y) {  // exp(y * L) rounded onc
     frx_dd v = frx_exp_dd(z.hi, z.lo, &e);
     return frx_scale2(FRX_ADD(v.hi, v.lo), e);
 }
+// inlined variant of frx_pow_core: independent calls side by side overlap their dependency chains (same bits)
+FRX_HD double frx_pow_core_inline(frx_dd L, double y) {
+    frx_dd z = frx_dd_mul_d(L, y);
+    int e;
+    frx_dd v = frx_exp_dd_inline(z.hi, z.lo, &e);
+    return frx_scale2(FRX_ADD(v.hi, v.lo), e);
+}
 // same value as frx_pow_cr(x, y) given L = frx_log_dd(x) (L is ignored for the exact special cases)
 FRX_HD double frx_pow_from_log(double x, double y, frx_dd L) {
     if (y == 0.0 || x == 1.0) return 1.0;
@@ -194,7 +204,10 @@ FRX_HD_CALL double frx_pow_cr(double x, double y) {
 // g = 6.024680040776729583740234375), which is what the reference's math.gamma calls evaluate
 // (reference fractulus/equation.py:23,57,72,99,114-139,158-162); NOT C tgamma.  exp and pow inside
 // are the correctly rounded ones above where CPython uses libm's.
-FRX_HD_CALL double frx_gamma_py(double x) {
+// the three independent pieces of CPython's m_tgamma for 0 < x: the Lanczos rational sum, exp(y) and
+// y ** (x - 0.5) with y = x + g - 0.5, and the final combination.  frx_gamma_py chains them; kernel K0 evaluates
+// the pieces on different warps (fractulus_b200/csrc/frx_table.cuh) -- same operations, same bits.
+FRX_HD_CALL double frx_lanczos_sum(double x) {
     const double num_c[13] = {
         23531376880.410759688572007674451636754734846804940, 42919803642.649098768957899047001988850926355848959,
         35711959237.355668049440185451547166705960488635843, 17921034426.037209699919755754458931112671403265390,
@@ -205,12 +218,6 @@ FRX_HD_CALL double frx_gamma_py(double x) {
         2.5066282746310002701649081771338373386264310793408};
     const double den_c[13] = {0.0,        39916800.0, 120543840.0, 150917976.0, 105258076.0, 45995730.0, 13339535.0,
                               2637558.0,  357423.0,   32670.0,     1925.0,      66.0,        1.0};
-    const double g = 6.024680040776729583740234375, gmh = 5.524680040776729583740234375;
-    if (x == floor(x) && x >= 1.0 && x <= 23.0) {  // exact factorials
-        double f = 1.0;
-        for (int k = 2; k < (int)x; ++k) f = FRX_MUL(f, (double)k);
-        return f;
-    }
     double num = 0.0, den = 0.0;
     if (x < 5.0) {
         for (int i = 12; i >= 0; --i) {
@@ -223,6 +230,18 @@ FRX_HD_CALL double frx_gamma_py(double x) {
             den = FRX_ADD(FRX_DIV(den, x), den_c[i]);
         }
     }
+    return FRX_DIV(num, den);
+}
+FRX_HD bool frx_gamma_is_factorial(double x) { return x == floor(x) && x >= 1.0 && x <= 23.0; }
+FRX_HD double frx_gamma_factorial(double x) {
+    double f = 1.0;
+    for (int k = 2; k < (int)x; ++k) f = FRX_MUL(f, (double)k);
+    return f;
+}
+// sum = frx_lanczos_sum(x), ex = exp(y), pw = y ** (x - 0.5), y = x + g - 0.5 (0 < x < 140)
+FRX_HD double frx_gamma_py_combine(double x, double sum, double ex, double pw) {
+    const double g = 6.024680040776729583740234375, gmh = 5.524680040776729583740234375;
+    if (frx_gamma_is_factorial(x)) return frx_gamma_factorial(x);
     double y = FRX_ADD(x, gmh), z;
     if (x > gmh) {
         double q = FRX_SUB(y, x);
@@ -232,8 +251,13 @@ FRX_HD_CALL double frx_gamma_py(double x) {
         z = FRX_SUB(q, x);
     }
     z = FRX_DIV(FRX_MUL(z, g), y);
-    double r = FRX_DIV(FRX_DIV(num, den), frx_exp_cr(y));
+    double r = FRX_DIV(sum, ex);
     r = FRX_ADD(r, FRX_MUL(z, r));
-    r = FRX_MUL(r, frx_pow_cr(y, FRX_SUB(x, 0.5)));
+    r = FRX_MUL(r, pw);
     return r;
+}
+FRX_HD_CALL double frx_gamma_py(double x) {
+    if (frx_gamma_is_factorial(x)) return frx_gamma_factorial(x);
+    const double y = FRX_ADD(x, 5.524680040776729583740234375);
+    return frx_gamma_py_combine(x, frx_lanczos_sum(x), frx_exp_cr(y), frx_pow_cr(y, FRX_SUB(x, 0.5)));
 }

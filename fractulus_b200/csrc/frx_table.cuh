@@ -1,4 +1,4 @@
-// frx_table.cuh -- kernel K1: Toeplitz weight tables of the growing-history operator, one CTA (128 + 64 threads) per
+// frx_table.cuh -- kernel K1: Toeplitz weight tables of the growing-history operator, one CTA of 128 threads per
 // 124 consecutive table entries of one alpha.
 //
 // Entry x serves as a distance d (cA/cB: raw weights, reference equation.py:54,68,95,119-139) and as a row
@@ -9,20 +9,68 @@
 // the CTA evaluates log(x) once per base (double-double), the <= 3 powers per base once, and shares them through
 // shared memory: ~4 double-double exp() per entry instead of ~12, with the same bits as calling frx_pow_cr for
 // every power (frx_pow_from_log).  The per-alpha scalars (Lanczos gammas, the multiplier of the three step values
-// fl(fl(i*h)/i) can take) are evaluated on separate lanes of warp 0 while the other threads do their powers.
+// fl(fl(i*h)/i) can take) come from a one-warp-per-alpha kernel (K0) that runs ahead; the table kernel is launched
+// as its programmatic dependent and only waits for it after its own powers are done.
 #pragma once
 #include "frx_rules.cuh"
 
-constexpr int FRX_TAB_THREADS = 128;              // threads that evaluate powers / entries
-constexpr int FRX_TAB_BLOCK = FRX_TAB_THREADS + 64; // + warp 4: gammas, warp 5: multiplier candidates
+constexpr int FRX_TAB_THREADS = 128;              // threads per CTA: one power base / table entry each
+constexpr int FRX_TAB_BLOCK = FRX_TAB_THREADS;
 constexpr int FRX_TAB_HALO = 2;
 constexpr int FRX_TAB_ENTRIES = FRX_TAB_THREADS - 2 * FRX_TAB_HALO;  // entries per CTA
 
-struct frx_table_smem {
-    frx_par P;
-    double pw[3][FRX_TAB_THREADS];  // pw[slot][t] = (x0 + t) ** expo[slot]
-    double step[3], mult[3];        // candidate steps h-, h, h+ and their final multipliers
+// per-alpha scalars, produced once per alpha by frx_alpha_scalars_warp (kernel K0) and read by every table CTA
+struct frx_alpha_scalars {
+    frx_par P;                      // exponents + Lanczos gammas
+    double step[3], mult[3];        // the steps fl(fl(i*h)/i) can take (h-, h, h+) and step ** e_mult for each
 };
+
+struct frx_table_smem {
+    frx_alpha_scalars sc;
+    double pw[3][FRX_TAB_THREADS];  // pw[slot][t] = (x0 + t) ** expo[slot]
+};
+
+// K0, one CTA of 4 warps per alpha.  The pieces are independent chains of ~200-400 dependent FP64 operations, so
+// each kind runs on its own warp (lanes of one warp on different code paths would serialise):
+//   warp 0: Lanczos rational sums of the <= 3 gammas      warp 1: exp(y) of each gamma
+//   warp 2: y ** (x - 0.5) of each gamma                  warp 3: step ** e_mult for the 3 candidate steps
+// then warp 0 combines them exactly as frx_gamma_py does (same operations, same bits).
+struct frx_k0_smem {
+    double sum[3], ex[3], pw[3];
+};
+__device__ __forceinline__ void frx_alpha_scalars_block(frx_k0_smem& W, int rule, double alpha, double h,
+                                                        frx_alpha_scalars* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const frx_par E = frx_par_exponents(rule, alpha);
+    const int ng = frx_par_gamma_count(rule);
+    const double gmh = 5.524680040776729583740234375;
+    if (lane < 3) {
+        if (warp == 3) {
+            const double s = lane == 1 ? h : nextafter(h, lane == 0 ? 0.0 : 2.0 * h + 1.0);
+            out->step[lane] = s;
+            out->mult[lane] = frx_pow_cr(s, E.e_mult);
+        } else if (lane < ng) {
+            const double x = frx_par_gamma_arg(E, lane), y = FRX_ADD(x, gmh);
+            if (warp == 0) W.sum[lane] = frx_lanczos_sum(x);
+            else if (warp == 1) W.ex[lane] = frx_exp_cr(y);
+            else W.pw[lane] = frx_pow_cr(y, FRX_SUB(x, 0.5));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        frx_par P = E;
+        for (int k = 0; k < ng; ++k)
+            frx_par_set_gamma(P, k, frx_gamma_py_combine(frx_par_gamma_arg(E, k), W.sum[k], W.ex[k], W.pw[k]));
+        out->P = P;
+    }
+}
+
+__device__ __forceinline__ void frx_grid_dependency_wait() {   // no-op unless launched as a programmatic dependent
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void frx_grid_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 struct frx_pow_shared {
     const frx_table_smem* S;
@@ -30,40 +78,48 @@ struct frx_pow_shared {
     __device__ __forceinline__ double operator()(double base, int slot) const {
         const long long t = (long long)base - x0;
         if (t >= 0 && t < FRX_TAB_THREADS) return S->pw[slot][t];
-        return frx_pow_cr(base, S->P.expo[slot]);  // never taken for in-range entries; keeps the provider total
+        return frx_pow_cr(base, S->sc.P.expo[slot]);  // never taken for in-range entries; keeps the provider total
     }
 };
 
-// X0: storage index of the CTA's first entry; logical distance / row x = X - c_pad.
-__device__ __forceinline__ void frx_table_block(frx_table_smem& S, int rule, double alpha, double h, int64_t N, int64_t X0,
-                                                int c_pad, int c_perm, double* __restrict__ cA, double* __restrict__ cB,
-                                                int64_t ldc, double* __restrict__ w0, double* __restrict__ mult,
+// X0: storage index of the CTA's first entry; logical distance / row x = X - c_pad.  `sc` (this alpha's scalars)
+// is written by the preceding kernel K0: it is read only after the grid-dependency wait, so under programmatic
+// dependent launch the power evaluation overlaps K0.
+__device__ __forceinline__ void frx_table_block(frx_table_smem& S, const frx_alpha_scalars* __restrict__ sc, int rule,
+                                                double alpha, double h, int64_t N, int64_t X0, int c_pad, int c_perm,
+                                                double* __restrict__ cA, double* __restrict__ cB, int64_t ldc,
+                                                double* __restrict__ w0, double* __restrict__ mult,
                                                 double* __restrict__ cm1) {
     const int t = threadIdx.x;
     const frx_par E = frx_par_exponents(rule, alpha);  // cheap: every thread has the exponents at once
     const long long x0 = X0 - c_pad - FRX_TAB_HALO;    // base of thread 0
-    if (t == 0) S.P = E;
-    __syncthreads();
-    if (t >= FRX_TAB_THREADS) {
-        // the per-alpha scalars run on their own warps so that they overlap the power evaluation below
-        const int k = t & 31;
-        if (t < FRX_TAB_THREADS + 32) {
-            if (k < frx_par_gamma_count(rule)) frx_par_set_gamma(S.P, k, frx_gamma_py(frx_par_gamma_arg(E, k)));
-        } else if (k < 3) {
-            const double s = k == 1 ? h : nextafter(h, k == 0 ? 0.0 : 2.0 * h + 1.0);
-            S.step[k] = s;
-            S.mult[k] = frx_pow_cr(s, E.e_mult);  // divided by the gamma after the barrier
-        }
-    } else {
+    {
         const long long xs = x0 + t;
         if (xs >= 0) {
             const double xd = (double)xs;
             frx_dd L{0.0, 0.0};
             if (xs > 1) L = frx_log_dd(xd);
             const int ns = rule == FRX_R_SIMPSON ? 3 : (rule == FRX_R_RECTANGLE ? 1 : 2);
-            for (int s = 0; s < ns; ++s) S.pw[s][t] = frx_pow_from_log(xd, E.expo[s], L);
+            if (xs > 1) {
+                // the <= 3 powers of one base are independent chains of ~160 dependent FP64 ops: evaluate them
+                // side by side (inlined) so that they overlap
+                double r[3];
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const double y = E.expo[s];
+                    r[s] = (s < ns && y != 0.0 && y != 1.0) ? frx_pow_core_inline(L, y) : (y == 0.0 ? 1.0 : xd);
+                }
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+                    if (s < ns) S.pw[s][t] = r[s];
+            } else {
+                for (int s = 0; s < ns; ++s) S.pw[s][t] = frx_pow_from_log(xd, E.expo[s], L);   // bases 0 and 1: exact cases
+            }
         }
     }
+    frx_grid_dependency_wait();
+    if (t < (int)(sizeof(frx_alpha_scalars) / sizeof(double)))
+        reinterpret_cast<double*>(&S.sc)[t] = reinterpret_cast<const double*>(sc)[t];
     __syncthreads();
     if (t < FRX_TAB_HALO || t >= FRX_TAB_THREADS - FRX_TAB_HALO) return;  // halo threads and the scalar warps
     const int64_t X = X0 + (t - FRX_TAB_HALO);
@@ -74,7 +130,7 @@ __device__ __forceinline__ void frx_table_block(frx_table_smem& S, int rule, dou
         if (cB) cB[X] = 0.0;
         return;
     }
-    const frx_par& P = S.P;
+    const frx_par& P = S.sc.P;
     const frx_pow_shared pw{&S, x0};
     const double xd = (double)x;
     double ca = 0.0, cb = 0.0;
@@ -91,9 +147,9 @@ __device__ __forceinline__ void frx_table_block(frx_table_smem& S, int rule, dou
         if (x >= 1) {
             const double step = FRX_DIV(FRX_MUL(xd, h), xd);  // (lf = i * h) / i at the reference's call site
             double pm;
-            if (step == S.step[1]) pm = S.mult[1];
-            else if (step == S.step[0]) pm = S.mult[0];
-            else if (step == S.step[2]) pm = S.mult[2];
+            if (step == S.sc.step[1]) pm = S.sc.mult[1];
+            else if (step == S.sc.step[0]) pm = S.sc.mult[0];
+            else if (step == S.sc.step[2]) pm = S.sc.mult[2];
             else pm = frx_pow_cr(step, P.e_mult);
             m = rule == FRX_R_SIMPSON ? pm : FRX_DIV(pm, P.g_mult);
             if (rule != FRX_R_RECTANGLE && !(rule == FRX_R_SIMPSON && x < 2)) w = frx_raw_first_pw(P, xd, pw);

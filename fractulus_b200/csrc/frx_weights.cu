@@ -122,27 +122,48 @@ extern "C" int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: weight tables (stand-alone entry; frx_history runs the same block routine inside its prepare
-// kernel).  grid = (ceil(ldc / 124), n_alpha), see frx_table.cuh.
+// K0: per-alpha scalars (one warp per alpha), K1: weight tables (stand-alone entry; frx_history runs the same
+// block routine inside its prepare kernel).  K1 grid = (ceil(ldc / 124), n_alpha), see frx_table.cuh.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FRX_TAB_BLOCK) frx_k1_weights_table(int rule, const double* __restrict__ alpha, double h,
-                                                                        int64_t N, double* __restrict__ cA,
-                                                                        double* __restrict__ cB, int64_t ldc,
-                                                                        double* __restrict__ w0, double* __restrict__ mult,
-                                                                        int64_t ldw, double* __restrict__ cm1) {
+__global__ void __launch_bounds__(128) frx_k0_alpha_scalars(int rule, const double* __restrict__ alpha, double h,
+                                                            frx_alpha_scalars* __restrict__ out) {
+    __shared__ frx_k0_smem W;
+    frx_grid_launch_dependents();   // the table kernel may start its power evaluation right away
+    frx_alpha_scalars_block(W, rule, alpha[blockIdx.x], h, out + blockIdx.x);
+}
+
+int frx_launch_alpha_scalars(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, void* d_scalars) {
+    FRX_LAUNCH(ctx, FRX_K_OTHER,
+               frx_k0_alpha_scalars<<<(unsigned)n_alpha, 128, 0, ctx->stream>>>(rule, d_alpha, h,
+                                                                               (frx_alpha_scalars*)d_scalars));
+    return FRX_OK;
+}
+size_t frx_alpha_scalars_bytes(void) { return sizeof(frx_alpha_scalars); }
+
+__global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k1_weights_table(int rule, const double* __restrict__ alpha, double h,
+                                                                           int64_t N, const frx_alpha_scalars* __restrict__ sc,
+                                                                           double* __restrict__ cA, double* __restrict__ cB,
+                                                                           int64_t ldc, double* __restrict__ w0,
+                                                                           double* __restrict__ mult, int64_t ldw,
+                                                                           double* __restrict__ cm1) {
     __shared__ frx_table_smem S;
     const int64_t a = blockIdx.y;
-    frx_table_block(S, rule, alpha[a], h, N, (int64_t)blockIdx.x * FRX_TAB_ENTRIES, 0, 0, cA + a * ldc,
+    frx_table_block(S, sc + a, rule, alpha[a], h, N, (int64_t)blockIdx.x * FRX_TAB_ENTRIES, 0, 0, cA + a * ldc,
                     cB ? cB + a * ldc : nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 ? cm1 + a : nullptr);
 }
 
 int frx_launch_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                              double* d_cA, double* d_cB, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
                              double* d_cm1) {
+    int rc = frx_ws_reserve(ctx, sizeof(frx_alpha_scalars) * (size_t)n_alpha);
+    if (rc) return rc;
+    rc = frx_launch_alpha_scalars(ctx, rule, n_alpha, d_alpha, h, ctx->ws);
+    if (rc) return rc;
     dim3 grid((unsigned)((ldc + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES), (unsigned)n_alpha);
     FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
-               frx_k1_weights_table<<<grid, FRX_TAB_BLOCK, 0, ctx->stream>>>(rule, d_alpha, h, N, d_cA, d_cB, ldc, d_w0,
-                                                                               d_mult, ldw, d_cm1));
+               FRX_CUDA(frx_launch_dependent(frx_k1_weights_table, grid, dim3(FRX_TAB_BLOCK), 0, ctx->stream, rule, d_alpha, h,
+                                             N, (const frx_alpha_scalars*)ctx->ws, d_cA, d_cB, ldc, d_w0, d_mult, ldw,
+                                             d_cm1)));
     return FRX_OK;
 }
 

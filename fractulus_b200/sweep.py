@@ -45,11 +45,28 @@ def gather_blocks(local, n_total, group=None):
     return torch.cat([buf[r * nmax:r * nmax + (e - b)] for r, (b, e) in enumerate(sizes)], dim=0)
 
 
-def history_sweep(approximation, alphas, h, g, N=None, group=None, compute=None):
+_pinned = {}
+
+
+def _to_host(t):
+    """device -> pinned host buffer (cached per shape) -> NumPy view; synchronises."""
+    key = (tuple(t.shape), t.dtype)
+    buf = _pinned.get(key)
+    if buf is None:
+        _pinned.clear()
+        buf = _pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy()
+
+
+def history_sweep(approximation, alphas, h, g, N=None, group=None, compute=None, host_result='all'):
     """Growing-history derivative of ONE field for many alpha, sharded over the ranks of `group`.
 
     alphas: 1-D array-like (the same on every rank); g: NumPy array (host: copied in, result copied
     out, like the reference's user would hold it) or CUDA tensor (result stays on the device).
+    host_result (host g only): 'all' = every rank returns the gathered NumPy result; 'root' = only rank 0
+    copies it out (the other ranks return None), which avoids world-size-fold PCIe traffic.
     `compute` (tests only) replaces the per-rank kernel call so the sharding/gather logic can run on
     CPU tensors with the gloo backend."""
     world, rank = _world(group)
@@ -64,4 +81,8 @@ def history_sweep(approximation, alphas, h, g, N=None, group=None, compute=None)
     else:
         local = compute(alphas[begin:end], g)
     full = gather_blocks(local, len(alphas), group)
-    return full.cpu().numpy() if host_io else full
+    if not host_io:
+        return full
+    if host_result == 'root' and rank != 0:
+        return None
+    return _to_host(full) if full.is_cuda else full.numpy()
