@@ -31,6 +31,10 @@
 #include "frx_internal.h"
 #include "frx_table.cuh"
 
+// defined in frx_weights.cu
+int frx_launch_alpha_scalars(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, void* d_scalars);
+size_t frx_alpha_scalars_bytes(void);
+
 namespace {
 
 constexpr int kNT = 128;      // threads per CTA
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
     const int64_t ubeg = k * p.total_units / NG, uend = (k + 1) * p.total_units / NG;
     if (ubeg >= uend) return;
     Cursor cur = cursor_at<G>(p, ubeg), nxt = cur;
+    frx_grid_dependency_wait();   // tables / padded fields / tickets come from the prepare kernel
     double acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
@@ -402,7 +407,8 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
 // prepare kernel: blocks [0, n_tab) generate the weight tables (K1); the remaining blocks build the padded
 // copies of the fields, gp[(f*n_pass + pass)*ldgp + padf + j] = g_j for 1 <= j <= N (for 'simpson' only the
 // nodes of the pass's parity: pass 0 even, pass 1 odd) and 0 elsewhere, and clear the tickets.
-__global__ void __launch_bounds__(FRX_TAB_BLOCK, 7) frx_k12_prepare(int rule, const double* __restrict__ alpha, double h, int64_t N,
+__global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, const double* __restrict__ alpha, double h, int64_t N,
+                                                          const frx_alpha_scalars* __restrict__ sc,
                                                        double* __restrict__ cA, double* __restrict__ cB, int64_t ldc,
                                                        double* __restrict__ w0, double* __restrict__ mult, int64_t ldw,
                                                        double* __restrict__ cm1, int c_pad, int c_perm, int64_t n_tab,
@@ -412,9 +418,10 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 7) frx_k12_prepare(int rule, co
                                                        int64_t n_tickets) {
     __shared__ frx_table_smem S;
     const int64_t bx = blockIdx.x;
+    frx_grid_launch_dependents();   // the history kernel may be scheduled as this grid drains; it waits before reading
     if (bx < n_tab) {
         const int64_t a = bx / tab_per_alpha;
-        frx_table_block(S, rule, alpha[a], h, N, (bx - a * tab_per_alpha) * FRX_TAB_ENTRIES, c_pad, c_perm, cA + a * ldc,
+        frx_table_block(S, sc + a, rule, alpha[a], h, N, (bx - a * tab_per_alpha) * FRX_TAB_ENTRIES, c_pad, c_perm, cA + a * ldc,
                         cB ? cB + a * ldc : nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 + a);
         return;
     }
@@ -465,6 +472,7 @@ int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha,
     const size_t o_gp = carve(sizeof(double) * (size_t)n_fields * p.n_pass * p.ldgp);
     const size_t o_part = carve(sizeof(double) * (size_t)2 * NG * G::TI);
     const size_t o_tick = carve(sizeof(int) * (size_t)n_tickets);
+    const size_t o_scal = carve(frx_alpha_scalars_bytes() * (size_t)n_alpha);
     int rc = frx_ws_reserve(ctx, off);
     if (rc) return rc;
     char* ws = (char*)ctx->ws;
@@ -493,10 +501,12 @@ int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha,
         int64_t n_pad = (n_fp * p.ldgp + 8 * kNT - 1) / (8 * kNT);
         if (n_pad > 4096) n_pad = 4096;
         FRX_REQUIRE(n_tab + n_pad < ((int64_t)1 << 31), FRX_ERR_INVALID_ARG, "problem too large for one launch");
+        rc = frx_launch_alpha_scalars(ctx, rule, n_alpha, d_alpha, h, ws + o_scal);
+        if (rc) return rc;
         FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
-                   frx_k12_prepare<<<(unsigned)(n_tab + n_pad), FRX_TAB_BLOCK, 0, ctx->stream>>>(
-                       rule, d_alpha, h, N, cA, cB, p.ldc, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
-                       n_fp, p.ldgp, G::PADF, gp, p.tickets, n_tickets));
+                   FRX_CUDA(frx_launch_dependent(frx_k12_prepare, dim3((unsigned)(n_tab + n_pad)), dim3(FRX_TAB_BLOCK), 0,
+                                                 ctx->stream, rule, d_alpha, h, N, (const frx_alpha_scalars*)(ws + o_scal), cA, cB, p.ldc, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
+                                                 n_fp, p.ldgp, (int)G::PADF, gp, p.tickets, n_tickets)));
     }
     // dynamic shared memory: at least the double buffer, padded so that exactly CTAS_PER_SM CTAs fit per SM
     int smem_sm = 0;
@@ -504,7 +514,8 @@ int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha,
     int dyn = (smem_sm / G::CTAS_PER_SM - 1024 - 64) / 128 * 128;
     if (dyn < 2 * G::STAGE_BYTES) dyn = 2 * G::STAGE_BYTES;
     FRX_CUDA(cudaFuncSetAttribute(frx_k2_history_main<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    FRX_LAUNCH(ctx, FRX_K_HISTORY_MAIN, frx_k2_history_main<G><<<(unsigned)NG, kNT, dyn, ctx->stream>>>(p));
+    FRX_LAUNCH(ctx, FRX_K_HISTORY_MAIN,
+               FRX_CUDA(frx_launch_dependent(frx_k2_history_main<G>, dim3((unsigned)NG), dim3(kNT), (size_t)dyn, ctx->stream, p)));
     return FRX_OK;
 }
 
