@@ -454,7 +454,7 @@ def run_b200_cfg4(args, world, rank, local_rank, dev):
     steps, warmup = args.steps, max(args.warmup, 3)
     h = 1.0 / (n + 1)
     alpha = np.repeat(np.linspace(0.05, 0.95, n_alpha), n_ls)
-    res = np.tile(1.0 + (np.arange(n_ls) % 32), n_alpha)
+    res = np.tile(1.0 + (np.arange(n_ls) % 30), n_alpha)
     xg = torch.arange(1, n + 1, dtype=torch.float64, device=dev) * h
     rhs = torch.sin(math.pi * xg).repeat(n_sys, 1).contiguous()
     ctx = _lib.context(local_rank)
@@ -497,7 +497,7 @@ def run_b200_cfg4(args, world, rank, local_rank, dev):
             'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': 'cfg4: assemble + batch-solve %d systems per GPU, n=%d unknowns, 400 alpha in [0.05,0.95] x 250 '
-                                   "length scales (resolution 1..32), rule 'caputo' Riesz-Caputo operator, rhs sin(pi x); step = K5 "
+                                   "length scales (resolution 1..30), rule 'caputo' Riesz-Caputo operator, rhs sin(pi x); step = K5 "
                                    'stencil weights + K4 in-kernel assembly + LU' % (n_sys, n), 'n_systems': n_sys, 'n': n},
             'gpu_launches': launches, 'clocks': clocks,
             'roofline': {'kernel': 'frx_k4_assemble_solve', 'bound': 'fp64', 'achieved': achieved, 'peak': peak_dfma,

@@ -53,6 +53,7 @@ struct Geo {
     static constexpr int WIN_CHUNKS = WIN_ELEMS / R;
     static constexpr int WIN_BYTES = WIN_CHUNKS * CHUNK_STRIDE;
     static constexpr int STAGE_BYTES = (TD * 8 + WIN_BYTES + 127) / 128 * 128;
+    static constexpr int SUBS = 1;               // a unit is not divisible between CTAs
     static constexpr int C_PAD = 0;              // c tables: natural order, no front padding
     static constexpr int C_PERM = 0;
     static constexpr bool TENSOR = false;
@@ -74,6 +75,7 @@ struct MGeo {
     static constexpr int R = 2 * T;              // accumulator doubles per thread
     static constexpr int TD = TD_;               // columns per unit
     static constexpr int MC = TD / 8;            // column blocks per unit
+    static constexpr int SUBS = MC / T_;         // groups of T column blocks: the granularity at which spans are cut
     static constexpr int CTAS_PER_SM = CTAS_;
     static constexpr int WARPS = kNT / 32;
     static constexpr int TI = WARPS * 64 * T;    // rows per tile
@@ -189,7 +191,7 @@ __device__ inline void dmma884(double& d0, double& d1, double a, double b) {
 
 // tensor variant: acc[2t], acc[2t+1] = D fragment of tile t (rows 8(P0w + t + T k) + 2 s' + {0,1})
 template <class G>
-__device__ inline void compute_unit_mma(double (&acc)[G::R], const char* stage) {
+__device__ inline void compute_unit_mma(double (&acc)[G::R], const char* stage, int s0, int s1) {
     constexpr int T = G::T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = lane >> 2, sp = lane & 3;
@@ -199,9 +201,9 @@ __device__ inline void compute_unit_mma(double (&acc)[G::R], const char* stage) 
     const double* gch = reinterpret_cast<const double*>(stage + G::CWIN_BYTES) + (4 + k - sp);
     double2 af[T];
 #pragma unroll
-    for (int t = 1; t < T; ++t) af[t] = *reinterpret_cast<const double2*>(arow + t * G::ROW_STRIDE);
+    for (int t = 1; t < T; ++t) af[t] = *reinterpret_cast<const double2*>(arow + (t - s0 * T) * G::ROW_STRIDE);
 #pragma unroll 1
-    for (int mg = 0; mg < G::MC; mg += T) {
+    for (int mg = s0 * T; mg < s1 * T; mg += T) {
 #pragma unroll
         for (int j = 0; j < T; ++j) {
             const int mi = mg + j;
@@ -278,9 +280,9 @@ __device__ inline void fma_block(double (&acc)[G::R], const double* cs, const do
 }
 
 template <class G>
-__device__ inline void compute_unit(double (&acc)[G::R], const char* stage) {
+__device__ inline void compute_unit(double (&acc)[G::R], const char* stage, int s0, int s1) {
     if constexpr (G::TENSOR) {
-        compute_unit_mma<G>(acc, stage);
+        compute_unit_mma<G>(acc, stage, s0, s1);
         return;
     } else {
     constexpr int R = G::R;
@@ -339,15 +341,19 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
     extern __shared__ __align__(128) char smem[];
     __shared__ int s_last;
     constexpr int R = G::R;
+    // spans are cut at sub-step granularity (groups of T column blocks for the tensor variant): every CTA gets
+    // total_groups / grid groups to within one, so a span may start and end in the middle of a unit
     const int64_t NG = gridDim.x, k = blockIdx.x;
-    const int64_t ubeg = k * p.total_units / NG, uend = (k + 1) * p.total_units / NG;
-    if (ubeg >= uend) return;
+    const int64_t total_groups = p.total_units * G::SUBS;
+    const int64_t gbeg = k * total_groups / NG, gend = (k + 1) * total_groups / NG;
+    if (gbeg >= gend) return;
+    const int64_t ubeg = gbeg / G::SUBS, uend = (gend + G::SUBS - 1) / G::SUBS;
     Cursor cur = cursor_at<G>(p, ubeg), nxt = cur;
     frx_grid_dependency_wait();   // tables / padded fields / tickets come from the prepare kernel
     double acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
-    bool from_start = (cur.v == 0);
+    bool from_start = (cur.v == 0 && gbeg == ubeg * G::SUBS);
     stage_unit<G>(p, cur, smem);
     cp_async_commit();
     for (int64_t u = ubeg; u < uend; ++u) {
@@ -359,9 +365,11 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        compute_unit<G>(acc, stage);
+        const int s0 = u == ubeg ? (int)(gbeg - ubeg * G::SUBS) : 0;
+        const int s1 = u + 1 == uend ? (int)(gend - u * G::SUBS) : G::SUBS;
+        compute_unit<G>(acc, stage, s0, s1);
         __syncthreads();
-        const bool tile_done = (cur.v + 1 == cur.units), span_done = (u + 1 == uend);
+        const bool tile_done = (cur.v + 1 == cur.units && s1 == G::SUBS), span_done = (u + 1 == uend);
         if (tile_done || span_done) {
             if (tile_done && from_start) {
                 finish_rows<G>(p, cur.prob, cur.I, acc);
@@ -372,8 +380,8 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
 #pragma unroll
                 for (int r = 0; r < R; r += 2)
                     *reinterpret_cast<double2*>(dst + acc_pair_row<G>(r >> 1)) = make_double2(acc[r], acc[r + 1]);
-                const int64_t tile_begin = u - cur.v, tile_end = tile_begin + cur.units;
-                const int64_t k0 = span_owner(tile_begin, p.total_units, NG), k1 = span_owner(tile_end - 1, p.total_units, NG);
+                const int64_t tile_begin = (u - cur.v) * G::SUBS, tile_end = tile_begin + cur.units * G::SUBS;   // in groups
+                const int64_t k0 = span_owner(tile_begin, total_groups, NG), k1 = span_owner(tile_end - 1, total_groups, NG);
                 __threadfence();
                 __syncthreads();
                 if (threadIdx.x == 0) {
@@ -454,7 +462,7 @@ int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha,
     p.ldw = (N + 1 + 1) / 2 * 2;
     p.ldgp = G::PADF + p.n_tiles * G::TI;
     int64_t NG = (int64_t)ctx->sm_count * G::CTAS_PER_SM;
-    if (NG > p.total_units) NG = p.total_units;
+    if (NG > p.total_units * G::SUBS) NG = p.total_units * G::SUBS;
     const int64_t n_tickets = n_alpha * n_fields * p.n_tiles;
 
     // workspace carve-up (all offsets multiples of 256 bytes)

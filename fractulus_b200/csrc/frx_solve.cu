@@ -20,6 +20,7 @@
 // structurally-zero part of the trailing matrix: n = 256, res = 32 fits in 205 KB of shared memory.
 // Algorithmic bytes per system: 8*(2*res+1) weights + 8n rhs in, 8n solution out.
 #include <math.h>
+#include <stdlib.h>
 
 #include "frx_internal.h"
 
@@ -182,6 +183,174 @@ __global__ void __launch_bounds__(kSolveThreads) frx_k4_assemble_solve(const Sol
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Streaming variant: ONE WARP PER SYSTEM, no block barriers.  Only the active window of the band elimination
+// lives on chip: rows k..k+nb (lane r owns one row slot) x columns k..k+2nb (ring of C = 2nb+1 column slots) in
+// shared memory, C odd -> the lanes' row-strided accesses are bank-conflict free.  Per column k:
+//   pivot = lane with the largest |entry| in column k (ties: lowest row index, like LAPACK) -- rows are never
+//   moved: the pivot lane's row simply retires as row k of U (implicit pivoting, row labels are swapped instead);
+//   every other active lane subtracts l * (pivot row) from its row; the retired slot is refilled with matrix row
+//   k+nb+1 straight from the 2nb+1 band coefficients; column slot k%C is zeroed and becomes column k+C.
+// Retired U rows (2nb+1 entries) and the transformed right-hand side stream to a per-warp scratch in global memory
+// (L2) and are read back, prefetched four rows ahead, by the back substitution.  Needs nb <= 31.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kStreamWarps = 4;
+constexpr int kStreamMaxNb = 31;
+constexpr int kStreamC = 2 * kStreamMaxNb + 1;
+constexpr int kStreamMaxN = 256;
+constexpr int kStreamWarpDoubles = 32 * kStreamC + kStreamC + 1 + kStreamMaxN;   // window + band coefficients (+1 pad) + rhs
+
+struct StreamParams {
+    int64_t n_sys;
+    int n;
+    const double* rcw;
+    const int64_t* wptr;
+    const double* h;
+    const double* rhs;
+    int64_t ldb;
+    double* x;
+    int64_t ldx;
+    int32_t* info;
+    double* uscratch;   // [total warps][n * kStreamC]
+};
+
+__global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const StreamParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
+    double* W = sm + warp * kStreamWarpDoubles;          // W[slot * C + column slot]
+    double* a = W + 32 * kStreamC;                       // a[k + nb]
+    double* bs = a + kStreamC + 1;                       // right-hand side, overwritten in place by the transformed one
+    const int64_t gw = (int64_t)blockIdx.x * kStreamWarps + warp, nw = (int64_t)gridDim.x * kStreamWarps;
+    double* U = p.uscratch + gw * (int64_t)n * kStreamC;
+    for (int64_t s = gw; s < p.n_sys; s += nw) {
+        const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
+        const int nb_a = res + 1;
+        const int nb = nb_a > n - 1 ? n - 1 : nb_a;      // rows below k+nb are zero in column k
+        const int C = 2 * nb + 1;
+        const double ih = 1.0 / p.h[s];
+        const double* rc = p.rcw + p.wptr[s] + res;
+        const double* rhs = p.rhs + s * p.ldb;
+        double* xo = p.x + s * p.ldx;
+        __syncwarp();
+        for (int k = -nb_a + lane; k <= nb_a; k += 32) {   // band coefficients, same terms and order as the CTA kernel
+            double acc = 0.0;
+            bool any = false;
+            auto add = [&](double t) { acc = any ? __dadd_rn(acc, t) : t; any = true; };
+            if (k >= -res && k <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k], ih)));
+            if (k + 1 >= -res && k + 1 <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k + 1], -ih)));
+            if (k - 1 >= -res && k - 1 <= res) add(__dmul_rn(ih, __dmul_rn(rc[k - 1], ih)));
+            if (k >= -res && k <= res) add(__dmul_rn(ih, __dmul_rn(rc[k], -ih)));
+            if (k >= -nb && k <= nb) a[k + nb] = acc;
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) bs[i] = rhs[i];
+        __syncwarp();
+        // initial window: rows 0..nb (lane = row), columns 0..2nb (column slot = column)
+        int logical = (lane <= nb && lane < n) ? lane : -1;
+        double bval = logical >= 0 ? bs[lane] : 0.0;
+        if (logical >= 0)
+            for (int j = 0; j < C; ++j) {
+                const int d = j - lane;
+                W[lane * C + j] = (d >= -nb && d <= nb && j < n) ? a[d + nb] : 0.0;
+            }
+        int info = 0, kc = 0;                              // kc = k % C
+        __syncwarp();
+        for (int k = 0; k < n; ++k) {
+            const bool active = logical >= 0;
+            const double v = active ? W[lane * C + kc] : 0.0;
+            double best = active ? fabs(v) : -1.0;
+            int blog = active ? logical : 0x7fffffff, bl = lane;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+                const int ol = __shfl_xor_sync(0xffffffffu, blog, d), oln = __shfl_xor_sync(0xffffffffu, bl, d);
+                if (ob > best || (ob == best && ol < blog)) { best = ob; blog = ol; bl = oln; }
+            }
+            const int P = bl;                              // pivot lane; blog = its row label
+            const double pval = __shfl_sync(0xffffffffu, v, P), bt = __shfl_sync(0xffffffffu, bval, P);
+            if (pval == 0.0 && info == 0) info = k + 1;
+            const bool worker = active && lane != P;
+            const double l = worker ? v * (1.0 / pval) : 0.0;
+            if (worker && logical == k) logical = blog;    // the interchange, on labels only
+            const int cmax = min(n - 1, k + 2 * nb), len = cmax - k;   // U row k: columns k..cmax
+            const double* prow = W + P * C;
+            // retire the pivot row: U[k][0..len] and the transformed right-hand side
+            for (int c = lane; c <= len; c += 32) {
+                int cs = kc + c; if (cs >= C) cs -= C;
+                U[(int64_t)k * kStreamC + c] = prow[cs];
+            }
+            if (lane == 0) bs[k] = bt;                     // slot k is free: rhs[k] entered the window long ago
+            // eliminate
+            if (worker) {
+                // columns k+1..cmax occupy ring slots kc+1..kc+len, i.e. at most two straight runs; the pivot row is
+                // another lane's row, hence __restrict__ (lets the loads of later columns pass earlier stores)
+                double* __restrict__ myrow = W + lane * C;
+                const double* __restrict__ pr = prow;
+                const int cend = kc + len, e1 = cend < C ? cend : C - 1;
+#pragma unroll 4
+                for (int cs = kc + 1; cs <= e1; ++cs) myrow[cs] = fma(-l, pr[cs], myrow[cs]);
+#pragma unroll 4
+                for (int cs = 0; cs <= cend - C; ++cs) myrow[cs] = fma(-l, pr[cs], myrow[cs]);
+                bval = fma(-l, bt, bval);
+                myrow[kc] = 0.0;                           // column slot kc becomes column k + C
+            }
+            __syncwarp();
+            // refill the retired slot with matrix row k+nb+1 (columns k+1 .. k+2nb+1 = the whole new window)
+            const int inew = k + nb + 1;
+            if (inew < n) {
+                double* nrow = W + P * C;
+                for (int c = lane; c < C; c += 32) {
+                    const int j = k + 1 + c;
+                    int cs = kc + 1 + c; if (cs >= C) cs -= C;
+                    nrow[cs] = j < n ? a[j - inew + nb] : 0.0;
+                }
+                if (lane == P) { logical = inew; bval = bs[inew]; }
+            } else if (lane == P) {
+                logical = -1;
+            }
+            kc = kc + 1 == C ? 0 : kc + 1;
+            __syncwarp();
+        }
+        // back substitution: x_k = (bt_k - sum_{c=1..len} U[k][c] x_{k+c}) / U[k][0]; U rows prefetched 4 ahead
+        double* xs = W;                                    // the window is free now: xs[n] (n <= 32*C is checked on the host)
+        constexpr int PF = 4;
+        double u0[PF], u1[PF], u2[PF];
+        auto load_row = [&](int k, double& r0, double& r1, double& r2) {
+            const int len = min(n - 1, k + 2 * nb) - k;
+            const double* ur = U + (int64_t)k * kStreamC;
+            r0 = (k >= 0 && lane <= len) ? __ldcg(ur + lane) : 0.0;
+            r1 = (k >= 0 && lane + 32 <= len) ? __ldcg(ur + lane + 32) : 0.0;
+            r2 = 0.0;
+        };
+#pragma unroll
+        for (int q = 0; q < PF; ++q) load_row(n - 1 - q, u0[q], u1[q], u2[q]);
+        for (int kb = n - 1; kb >= 0; kb -= PF) {
+#pragma unroll
+            for (int q = 0; q < PF; ++q) {
+                const int k = kb - q;
+                if (k < 0) break;
+                const int len = min(n - 1, k + 2 * nb) - k;
+                // lane holds U[k][lane], U[k][lane+32]; entry c multiplies x_{k+c}, c >= 1
+                double sum = 0.0;
+                if (lane >= 1 && lane <= len) sum = u0[q] * xs[k + lane];
+                if (lane + 32 <= len) sum = fma(u1[q], xs[k + lane + 32], sum);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+                const double diag = __shfl_sync(0xffffffffu, u0[q], 0);
+                const double xk = (bs[k] - sum) / diag;
+                if (lane == 0) { xs[k] = xk; }
+                load_row(k - PF, u0[q], u1[q], u2[q]);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) xo[i] = xs[i];
+        if (lane == 0 && p.info) p.info[s] = info;
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
@@ -255,6 +424,34 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                                     (const int64_t*)(ws + o_wptr), nullptr, (double*)(ws + o_w));
     free(wptr); free(lf);
     if (rc) return rc;
+    // every band narrow enough: one warp per system, window in shared memory, U streamed through L2
+    static const int force_cta = getenv("FRX_K4_VARIANT") ? atoi(getenv("FRX_K4_VARIANT")) == 1 : 0;
+    if (!d_dense && !force_cta && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
+        StreamParams q;
+        q.n_sys = n_sys;
+        q.n = n;
+        q.rcw = (const double*)(ws + o_w);
+        q.wptr = (const int64_t*)(ws + o_wptr);
+        q.h = d_par + 3 * n_sys;
+        q.rhs = d_rhs;
+        q.ldb = ldb;
+        q.x = d_x;
+        q.ldx = ldx;
+        q.info = d_info;
+        const size_t dyn_s = sizeof(double) * (size_t)kStreamWarps * kStreamWarpDoubles;
+        FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_s));
+        int per_sm_s = 1;
+        FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, frx_k4_band_stream, kStreamWarps * 32, dyn_s));
+        if (per_sm_s < 1) per_sm_s = 1;
+        int64_t grid_s = (int64_t)ctx->sm_count * per_sm_s;
+        if (grid_s * kStreamWarps > n_sys) grid_s = (n_sys + kStreamWarps - 1) / kStreamWarps;
+        // per-warp U scratch lives in the io buffer (the workspace holds the stencil weights)
+        rc = frx_io_reserve(ctx, sizeof(double) * (size_t)grid_s * kStreamWarps * n * kStreamC);
+        if (rc) return rc;
+        q.uscratch = (double*)ctx->io;
+        FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4_band_stream<<<(unsigned)grid_s, kStreamWarps * 32, dyn_s, ctx->stream>>>(q));
+        return FRX_OK;
+    }
     SolveParams p;
     p.n_sys = n_sys;
     p.n = n;
