@@ -43,6 +43,9 @@ SIGNATURES = {
                                          ctypes.c_int64, c_void_p]),
     'frx_history': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, c_void_p, ctypes.c_double, ctypes.c_int64,
                                    ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p, ctypes.c_int64]),
+    'frx_history_sided': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_void_p, ctypes.c_double,
+                                         ctypes.c_int64, ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
+                                         ctypes.c_int64]),
     'frx_history_host': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, c_double_p, ctypes.c_double,
                                         ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64,
                                         c_double_p, ctypes.c_int64]),

@@ -101,12 +101,14 @@ def weights_table(approximation, alpha, h, N, device=None):
     return WeightTables(cA, cB, w0, mult, cm1, N)
 
 
-def history(approximation, alpha, h, g, N=None, out=None, validate=True):
+def history(approximation, alpha, h, g, N=None, out=None, validate=True, side='left'):
     """K1 + K2: y[a, f, i] = (D^alpha_a g_f)(x_i), i = 0..N, of the growing-history operator whose row i
     is the reference stencil of Settings(alpha, i*h, i) (reference test/integration/test_equation.py:51-66).
 
     alpha: scalar / 1-D (host or cuda); g: cuda float64 [n_g] or [n_fields, n_g]; N defaults to
-    n_g - 1 (n_g - 2 for 'simpson', whose odd rows read one node to the right)."""
+    n_g - 1 (n_g - 2 for 'simpson', whose odd rows read one node to the right).
+    side: 'left' (default), 'right' (row i = create_right_stencil(Settings(alpha, (N-i)*h, N-i))) or
+    'riesz_caputo' (1/2 gamma(2-alpha) (left + (-1)**n right), reference equation.py:20-25)."""
     rule = _lib.RULES[approximation]
     if not torch.is_tensor(g) or not g.is_cuda:
         raise TypeError('g must be a CUDA tensor (use history_host for NumPy buffers)')
@@ -130,8 +132,8 @@ def history(approximation, alpha, h, g, N=None, out=None, validate=True):
         out = torch.empty((n_alpha, n_fields, N + 1), dtype=torch.float64, device=device)
     else:
         assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == n_alpha * n_fields * (N + 1)
-    _lib.check(_lib.lib().frx_history(ctx.handle, rule, n_alpha, _ptr(d_alpha), float(h), int(N), n_fields, _ptr(g2),
-                                      n_g, n_g, _ptr(out), N + 1))
+    _lib.check(_lib.lib().frx_history_sided(ctx.handle, rule, _lib.SIDES[side], n_alpha, _ptr(d_alpha), float(h), int(N),
+                                            n_fields, _ptr(g2), n_g, n_g, _ptr(out), N + 1))
     y = out.view(n_alpha, n_fields, N + 1)
     if squeeze_f:
         y = y[:, 0]

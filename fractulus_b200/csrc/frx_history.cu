@@ -106,6 +106,9 @@ struct HistParams {
     int64_t ldg;
     double* y;
     int64_t ldy;
+    int side;          // FRX_SIDE_LEFT; FRX_SIDE_RIGHT: field read reversed, y[N-i] = -value; FRX_SIDE_RIESZ_CAPUTO: second
+                       // pass over a y that holds the left result: y[N-i] = krc * (y[N-i] + sgn * (-value))
+    const frx_alpha_scalars* sc;
     double* partial;   // [2 * grid][TI]
     int* tickets;      // [n_alpha * n_fields * n_tiles], zero on entry, zero again on exit
 };
@@ -313,7 +316,8 @@ template <class G>
 __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I, const double (&acc)[G::R]) {
     const int64_t a = prob / p.n_fields, f = prob - a * p.n_fields;
     const double* gf = p.g + f * p.ldg;
-    const double g0 = gf[0];
+    const bool rev = p.side != FRX_SIDE_LEFT;
+    const double g0 = rev ? gf[p.N] : gf[0];
     const double cm1 = p.rule == FRX_RULE_SIMPSON ? p.cm1[a] : 0.0;
 #pragma unroll
     for (int r = 0; r < G::R; ++r) {
@@ -329,7 +333,18 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
             if (p.rule == FRX_RULE_SIMPSON && (i & 1)) s = fma(cm1, gf[i + 1], s);
             v = p.mult[a * p.ldw + i] * s;
         }
-        p.y[prob * p.ldy + i] = v;
+        if (!rev) {
+            p.y[prob * p.ldy + i] = v;
+        } else {
+            // row i of the mirrored problem is node N-i; create_right_stencil negates the weights (equation.py:38-39)
+            double* dst = p.y + prob * p.ldy + (p.N - i);
+            if (p.side == FRX_SIDE_RIGHT) {
+                *dst = -v;
+            } else {
+                const bool boundary = (i == 0 || i == p.N);   // one of the two one-sided stencils does not exist there
+                *dst = boundary ? nan("") : p.sc[a].krc * (*dst + p.sc[a].sgn * (-v));
+            }
+        }
     }
 }
 
@@ -423,7 +438,7 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
                                                        int64_t tab_per_alpha,
                                                        const double* __restrict__ g, int64_t ldg, int n_pass, int64_t n_fp,
                                                        int64_t ldgp, int padf, double* __restrict__ gp, int* __restrict__ tickets,
-                                                       int64_t n_tickets) {
+                                                       int64_t n_tickets, int reverse) {
     __shared__ frx_table_smem S;
     const int64_t bx = blockIdx.x;
     frx_grid_launch_dependents();   // the history kernel may be scheduled as this grid drains; it waits before reading
@@ -439,17 +454,18 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
         const int64_t fp = e / ldgp, x = e - fp * ldgp;
         const int64_t f = fp / n_pass, pass = fp - f * n_pass, j = x - padf;
         double v = 0.0;
-        if (j >= 1 && j <= N && (n_pass == 1 || (j & 1) == pass)) v = g[f * ldg + j];
+        if (j >= 1 && j <= N && (n_pass == 1 || (j & 1) == pass)) v = g[f * ldg + (reverse ? N - j : j)];
         gp[e] = v;
     }
     for (int64_t e = pb * blockDim.x + threadIdx.x; e < n_tickets; e += stride) tickets[e] = 0;
 }
 
 template <class G>
-int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N, int64_t n_fields,
-                 const double* d_g, int64_t ldg, double* d_y, int64_t ldy) {
+int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                 int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy) {
     HistParams p;
     p.rule = rule;
+    p.side = side;
     p.n_pass = rule == FRX_RULE_SIMPSON ? 2 : 1;
     p.N = N;
     p.n_alpha = n_alpha;
@@ -500,6 +516,7 @@ int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha,
     p.ldg = ldg;
     p.y = d_y;
     p.ldy = ldy;
+    p.sc = (const frx_alpha_scalars*)(ws + o_scal);
     p.partial = (double*)(ws + o_part);
     p.tickets = (int*)(ws + o_tick);
 
@@ -514,7 +531,8 @@ int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha,
         FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
                    FRX_CUDA(frx_launch_dependent(frx_k12_prepare, dim3((unsigned)(n_tab + n_pad)), dim3(FRX_TAB_BLOCK), 0,
                                                  ctx->stream, rule, d_alpha, h, N, (const frx_alpha_scalars*)(ws + o_scal), cA, cB, p.ldc, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
-                                                 n_fp, p.ldgp, (int)G::PADF, gp, p.tickets, n_tickets)));
+                                                 n_fp, p.ldgp, (int)G::PADF, gp, p.tickets, n_tickets,
+                                                 (int)(side != FRX_SIDE_LEFT))));
     }
     // dynamic shared memory: at least the double buffer, padded so that exactly CTAS_PER_SM CTAs fit per SM
     int smem_sm = 0;
@@ -531,27 +549,44 @@ int history_impl(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha,
 
 extern "C" int64_t frx_table_ldc(int64_t N) { return (N + 1 + kLdcQuantum - 1) / kLdcQuantum * kLdcQuantum; }
 
-extern "C" int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
-                           int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy) {
+static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                            int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy) {
+    // tile geometry: FRX_K2_VARIANT is a tuning/experiment switch, the default is the measured best
+    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 9;
+    switch (variant) {
+        case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 4: return history_impl<MGeo<4, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        default: return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+    }
+}
+
+extern "C" int frx_history_sided(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                                 int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
     FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
+    FRX_REQUIRE(side >= FRX_SIDE_LEFT && side <= FRX_SIDE_RIESZ_CAPUTO, FRX_ERR_INVALID_ARG, "bad side");
     FRX_REQUIRE(N >= 1 && N < ((int64_t)1 << 30), FRX_ERR_INVALID_ARG, "N out of range");
     FRX_REQUIRE(n_alpha >= 0 && n_alpha <= 65535 && n_fields >= 0 && n_fields <= 32767, FRX_ERR_INVALID_ARG,
                 "n_alpha (<= 65535) / n_fields (<= 32767) out of range");
+    FRX_REQUIRE(side == FRX_SIDE_LEFT || rule != FRX_RULE_SIMPSON, FRX_ERR_DOMAIN,
+                "'simpson' rows of odd resolution read one node beyond the evaluation point: only the left operator is offered");
     const int64_t need_g = N + 1 + (rule == FRX_RULE_SIMPSON ? 1 : 0);
     FRX_REQUIRE(n_g >= need_g && ldg >= n_g && ldy >= N + 1, FRX_ERR_INVALID_ARG,
                 "field too short (needs N+1 nodes, N+2 for 'simpson') or leading dimension too small");
     if (n_alpha == 0 || n_fields == 0) return FRX_OK;
     FRX_REQUIRE(d_alpha && d_g && d_y, FRX_ERR_INVALID_ARG, "NULL buffer");
     FRX_CUDA(cudaSetDevice(ctx->device));
-    // tile geometry: FRX_K2_VARIANT is a tuning/experiment switch, the default is the measured best
-    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 9;
-    switch (variant) {
-        case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        case 4: return history_impl<MGeo<4, 256, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        default: return history_impl<MGeo<4, 512, 4>>(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+    if (side == FRX_SIDE_RIESZ_CAPUTO) {   // K * (left + (-1.)**n * right): the left pass leaves its result in y
+        int rc = history_dispatch(ctx, rule, FRX_SIDE_LEFT, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        if (rc) return rc;
     }
+    return history_dispatch(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+}
+
+extern "C" int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                           int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy) {
+    return frx_history_sided(ctx, rule, FRX_SIDE_LEFT, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, n_g, d_y, ldy);
 }
 
 // K3: one alpha, many fields -- the same tensor-core kernel with the fields as independent problems (the c window

@@ -23,6 +23,7 @@ constexpr int FRX_TAB_ENTRIES = FRX_TAB_THREADS - 2 * FRX_TAB_HALO;  // entries 
 struct frx_alpha_scalars {
     frx_par P;                      // exponents + Lanczos gammas
     double step[3], mult[3];        // the steps fl(fl(i*h)/i) can take (h-, h, h+) and step ** e_mult for each
+    double krc, sgn;                // Riesz-Caputo: 1./2.*gamma(2.-alpha)/gamma(2.) and (-1.)**n  (equation.py:22-24)
 };
 
 struct frx_table_smem {
@@ -36,7 +37,7 @@ struct frx_table_smem {
 //   warp 2: y ** (x - 0.5) of each gamma                  warp 3: step ** e_mult for the 3 candidate steps
 // then warp 0 combines them exactly as frx_gamma_py does (same operations, same bits).
 struct frx_k0_smem {
-    double sum[3], ex[3], pw[3];
+    double sum[4], ex[4], pw[4];    // slot 3: gamma(2. - alpha) of the Riesz-Caputo constant
 };
 __device__ __forceinline__ void frx_alpha_scalars_block(frx_k0_smem& W, int rule, double alpha, double h,
                                                         frx_alpha_scalars* out) {
@@ -44,13 +45,15 @@ __device__ __forceinline__ void frx_alpha_scalars_block(frx_k0_smem& W, int rule
     const frx_par E = frx_par_exponents(rule, alpha);
     const int ng = frx_par_gamma_count(rule);
     const double gmh = 5.524680040776729583740234375;
-    if (lane < 3) {
+    if (lane < 4) {
         if (warp == 3) {
-            const double s = lane == 1 ? h : nextafter(h, lane == 0 ? 0.0 : 2.0 * h + 1.0);
-            out->step[lane] = s;
-            out->mult[lane] = frx_pow_cr(s, E.e_mult);
-        } else if (lane < ng) {
-            const double x = frx_par_gamma_arg(E, lane), y = FRX_ADD(x, gmh);
+            if (lane < 3) {
+                const double s = lane == 1 ? h : nextafter(h, lane == 0 ? 0.0 : 2.0 * h + 1.0);
+                out->step[lane] = s;
+                out->mult[lane] = frx_pow_cr(s, E.e_mult);
+            }
+        } else if (lane < ng || lane == 3) {
+            const double x = lane == 3 ? FRX_SUB(2.0, alpha) : frx_par_gamma_arg(E, lane), y = FRX_ADD(x, gmh);
             if (warp == 0) W.sum[lane] = frx_lanczos_sum(x);
             else if (warp == 1) W.ex[lane] = frx_exp_cr(y);
             else W.pw[lane] = frx_pow_cr(y, FRX_SUB(x, 0.5));
@@ -62,6 +65,10 @@ __device__ __forceinline__ void frx_alpha_scalars_block(frx_k0_smem& W, int rule
         for (int k = 0; k < ng; ++k)
             frx_par_set_gamma(P, k, frx_gamma_py_combine(frx_par_gamma_arg(E, k), W.sum[k], W.ex[k], W.pw[k]));
         out->P = P;
+        // Number(1. / 2. * math.gamma(2. - alpha) / math.gamma(2.)), Number((-1.) ** n)        equation.py:23-24
+        const double g2 = frx_gamma_py_combine(FRX_SUB(2.0, alpha), W.sum[3], W.ex[3], W.pw[3]);
+        out->krc = FRX_DIV(FRX_MUL(0.5, g2), 1.0);
+        out->sgn = (((long long)E.n) & 1) ? -1.0 : 1.0;
     }
 }
 

@@ -124,6 +124,12 @@ int frx_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_a
  * Weight tables are generated on the fly inside the call (K1) into the context workspace. */
 int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                 int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy);
+/* The same for the right-sided operator (row i = create_right_stencil(rule, Settings(alpha, (N-i)*h, N-i)),
+ * equation.py:32-39; y_N = 0) and for the two-sided Riesz-Caputo combination of both growing histories,
+ * 1./2.*gamma(2.-alpha)/gamma(2.) * (left + (-1.)**n * right) (equation.py:20-25; nodes 0 and N = NaN).
+ * side: frx_side.  'simpson' is offered for FRX_SIDE_LEFT only. */
+int frx_history_sided(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                      int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy);
 int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_alpha, double h, int64_t N,
                      int64_t n_fields, const double* h_g, int64_t ldg, int64_t n_g, double* h_y, int64_t ldy);
 

@@ -242,3 +242,40 @@ def test_toeplitz_apply_full_size_cfg3_sampled_fields():
         gf = G[f].cpu().numpy()
         want = clib.history_full('caputo', 0.5, h, N, gf)
         assert_history_close('caputo', 0.5, h, np.arange(1, N + 1), Y[f, 1:].cpu().numpy(), want[1:], gf, 0.99)
+
+
+def _oracle_sided_rows(rule, alpha, h, g, N, rows):
+    """left / right growing-history values at `rows` from the C oracle's stencils (reference equation.py:28-39)."""
+    yl, yr = [], []
+    for i in rows:
+        first, w = clib.left_arrays(rule, (alpha, i * h, i))
+        yl.append(sum(float(g[i + first + k]) * float(wk) for k, wk in enumerate(w)))
+        first, w = clib.right_arrays(rule, (alpha, (N - i) * h, N - i))
+        yr.append(sum(float(g[i + first + k]) * float(wk) for k, wk in enumerate(w)))
+    return np.array(yl), np.array(yr)
+
+
+def test_right_and_riesz_caputo_growing_history_vs_oracle():
+    """the right-sided operator (create_right_stencil rows, equation.py:32-39) and the two-sided
+    Riesz-Caputo combination 1/2 gamma(2-alpha) (left + (-1)**n right) (equation.py:20-25) of the growing histories."""
+    N, h = 700, 1. / 700
+    x = np.arange(N + 1) * h
+    g = np.exp(-x) * (1. + x) + 0.3 * np.sin(5 * x)
+    rows = list(range(2, N - 1, 23)) + [N - 2]
+    for rule in ('caputo', 'trapezoidal', 'rectangle'):
+        for alpha in (0.3, 0.8):
+            yl, yr = _oracle_sided_rows(rule, alpha, h, g, N, rows)
+            got_r = batched.history(rule, alpha, h, dev(g), N=N, side='right').cpu().numpy()
+            got_rc = batched.history(rule, alpha, h, dev(g), N=N, side='riesz_caputo').cpu().numpy()
+            scale_r, scale = np.abs(yr).max(), None
+            assert np.abs(got_r[rows] - yr).max() <= 1e-12 * scale_r, (rule, alpha)
+            K, sgn = 0.5 * math.gamma(2. - alpha) / math.gamma(2.), (-1.) ** (math.floor(alpha) + 1.)
+            want = K * (yl + sgn * yr)
+            assert np.abs(got_rc[rows] - want).max() <= 1e-12 * np.abs(want).max(), (rule, alpha)
+            assert got_r[N] == 0. and np.isnan(got_rc[0]) and np.isnan(got_rc[N])
+    # mirror symmetry: the right operator of the reversed field is minus the reversed left operator
+    yl_full = batched.history('caputo', 0.5, h, dev(g), N=N).cpu().numpy()
+    yr_rev = batched.history('caputo', 0.5, h, dev(g[::-1].copy()), N=N, side='right').cpu().numpy()
+    assert np.array_equal(yr_rev[::-1][1:], -yl_full[1:])
+    with pytest.raises(ValueError):
+        batched.history('simpson', 0.5, h, dev(np.append(g, 0.)), N=N, side='right')
