@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_build', 'libfrx_b200.so')
 
 FRX_OK = 0
-RULES = {'caputo': 0, 'rectangle': 1, 'trapezoidal': 2, 'simpson': 3}   # reference equation.py:179-184
+RULES = {'caputo': 0, 'rectangle': 1, 'trapezoidal': 2, 'simpson': 3,   # reference equation.py:179-184
+         'grunwald_letnikov': 4}   # extension, not a key of the reference (include/frx.h)
 SIDES = {'left': 0, 'right': 1, 'riesz_caputo': 2}
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

@@ -203,7 +203,7 @@ int frx_pinned_reserve(frx_ctx* ctx, size_t bytes) {
 
 // ---- domain checks mirroring what the reference does with such settings -------------------------
 int frx_check_rule_alpha(int rule, double alpha) {
-    if (rule < FRX_RULE_CAPUTO || rule > FRX_RULE_SIMPSON) {
+    if (rule < FRX_RULE_CAPUTO || rule > FRX_RULE_LAST) {
         frx_set_error("unknown approximation key (reference: KeyError at equation.py:29)");
         return FRX_ERR_UNKNOWN_RULE;
     }
@@ -211,6 +211,7 @@ int frx_check_rule_alpha(int rule, double alpha) {
         frx_set_error("alpha must be finite and >= 0");
         return FRX_ERR_DOMAIN;
     }
+    if (rule == FRX_RULE_GRUNWALD_LETNIKOV) return FRX_OK;
     if (rule == FRX_RULE_RECTANGLE && alpha > 1.0) {
         frx_set_error("'rectangle' with alpha > 1: 0.0 ** negative (reference: ZeroDivisionError, equation.py:68)");
         return FRX_ERR_ZERO_DIVISION;
@@ -248,6 +249,8 @@ extern "C" int frx_stencil_layout(int rule, int side, double alpha, double resol
                                   int32_t* count) {
     FRX_REQUIRE(first_offset && count, FRX_ERR_INVALID_ARG, "NULL output pointer");
     FRX_REQUIRE(side >= FRX_SIDE_LEFT && side <= FRX_SIDE_RIESZ_CAPUTO, FRX_ERR_INVALID_ARG, "bad side");
+    FRX_REQUIRE(rule != FRX_RULE_GRUNWALD_LETNIKOV || side == FRX_SIDE_LEFT, FRX_ERR_DOMAIN,
+                "the Gruenwald-Letnikov extension offers the left stencil only");
     int rc = frx_check_settings(rule, alpha, resolution);
     if (rc) return rc;
     long long f, c;

@@ -34,6 +34,9 @@
 // defined in frx_weights.cu
 int frx_launch_alpha_scalars(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, void* d_scalars);
 size_t frx_alpha_scalars_bytes(void);
+int frx_launch_gl_table(frx_ctx* ctx, int64_t n_alpha, const double* d_alpha, double h, int64_t N, const void* d_scalars,
+                        int c_pad, int c_perm, double* d_cA, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
+                        double* d_cm1);
 
 namespace {
 
@@ -521,13 +524,18 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     p.tickets = (int*)(ws + o_tick);
 
     {
-        const int64_t tab_per_alpha = (p.ldc + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES, n_tab = tab_per_alpha * n_alpha;
+        const bool gl = rule == FRX_RULE_GRUNWALD_LETNIKOV;   // extension: its tables come from their own scan kernel
+        const int64_t tab_per_alpha = (p.ldc + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES, n_tab = gl ? 0 : tab_per_alpha * n_alpha;
         const int64_t n_fp = n_fields * p.n_pass;
         int64_t n_pad = (n_fp * p.ldgp + 8 * kNT - 1) / (8 * kNT);
         if (n_pad > 4096) n_pad = 4096;
         FRX_REQUIRE(n_tab + n_pad < ((int64_t)1 << 31), FRX_ERR_INVALID_ARG, "problem too large for one launch");
         rc = frx_launch_alpha_scalars(ctx, rule, n_alpha, d_alpha, h, ws + o_scal);
         if (rc) return rc;
+        if (gl) {
+            rc = frx_launch_gl_table(ctx, n_alpha, d_alpha, h, N, ws + o_scal, G::C_PAD, G::C_PERM, cA, p.ldc, w0, mult, p.ldw, cm1);
+            if (rc) return rc;
+        }
         FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
                    FRX_CUDA(frx_launch_dependent(frx_k12_prepare, dim3((unsigned)(n_tab + n_pad)), dim3(FRX_TAB_BLOCK), 0,
                                                  ctx->stream, rule, d_alpha, h, N, (const frx_alpha_scalars*)(ws + o_scal), cA, cB, p.ldc, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
@@ -564,11 +572,13 @@ static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, c
 extern "C" int frx_history_sided(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                                  int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
+    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_LAST, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
     FRX_REQUIRE(side >= FRX_SIDE_LEFT && side <= FRX_SIDE_RIESZ_CAPUTO, FRX_ERR_INVALID_ARG, "bad side");
     FRX_REQUIRE(N >= 1 && N < ((int64_t)1 << 30), FRX_ERR_INVALID_ARG, "N out of range");
     FRX_REQUIRE(n_alpha >= 0 && n_alpha <= 65535 && n_fields >= 0 && n_fields <= 32767, FRX_ERR_INVALID_ARG,
                 "n_alpha (<= 65535) / n_fields (<= 32767) out of range");
+    FRX_REQUIRE(side == FRX_SIDE_LEFT || rule != FRX_RULE_GRUNWALD_LETNIKOV, FRX_ERR_DOMAIN,
+                "the Gruenwald-Letnikov extension offers the left operator only");
     FRX_REQUIRE(side == FRX_SIDE_LEFT || rule != FRX_RULE_SIMPSON, FRX_ERR_DOMAIN,
                 "'simpson' rows of odd resolution read one node beyond the evaluation point: only the left operator is offered");
     const int64_t need_g = N + 1 + (rule == FRX_RULE_SIMPSON ? 1 : 0);

@@ -6,7 +6,7 @@
 #pragma once
 #include "frx_math.cuh"
 
-enum { FRX_R_CAPUTO = 0, FRX_R_RECTANGLE = 1, FRX_R_TRAPEZOIDAL = 2, FRX_R_SIMPSON = 3 };
+enum { FRX_R_CAPUTO = 0, FRX_R_RECTANGLE = 1, FRX_R_TRAPEZOIDAL = 2, FRX_R_SIMPSON = 3, FRX_R_GL = 4 };
 
 struct frx_par {
     int rule;
@@ -51,6 +51,8 @@ FRX_HD frx_par frx_par_exponents(int rule, double alpha) {
         P.e_main = FRX_SUB(2.0, alpha);
         P.e_first = FRX_SUB(1.0, alpha);
         P.e_mult = FRX_SUB(1.0, alpha);                    // ** (1. - alpha) / gamma(3. - alpha)  :99
+    } else if (rule == FRX_R_GL) {
+        P.e_mult = -alpha;                                 // extension: h ** (-alpha) * w_k
     } else {
         P.e3 = FRX_SUB(3.0, alpha);
         P.e2 = FRX_SUB(2.0, alpha);
@@ -67,7 +69,7 @@ FRX_HD frx_par frx_par_exponents(int rule, double alpha) {
 
 // the rule needs frx_par_gamma_count gamma values; value k is gamma(frx_par_gamma_arg(P, k)) and is
 // stored by frx_par_set_gamma.  Split like this so that a warp can evaluate them on different lanes.
-FRX_HD int frx_par_gamma_count(int rule) { return rule == FRX_R_SIMPSON ? 3 : 1; }
+FRX_HD int frx_par_gamma_count(int rule) { return rule == FRX_R_SIMPSON ? 3 : (rule == FRX_R_GL ? 0 : 1); }
 FRX_HD double frx_par_gamma_arg(const frx_par& P, int k) {
     if (P.rule == FRX_R_CAPUTO) return FRX_ADD(FRX_SUB(P.n, P.alpha), 2.0);   // gamma(n - alpha + 2.)  :57
     if (P.rule == FRX_R_RECTANGLE) return FRX_SUB(2.0, P.alpha);               // gamma(2. - alpha)      :72
@@ -167,7 +169,7 @@ FRX_HD double frx_raw_right_of_point(const frx_par& P) {
 FRX_HD double frx_multiplier(const frx_par& P, double lf, double p) {
     double step = FRX_DIV(lf, p);
     double m = frx_pow_cr(step, P.e_mult);
-    return P.rule == FRX_R_SIMPSON ? m : FRX_DIV(m, P.g_mult);
+    return (P.rule == FRX_R_SIMPSON || P.rule == FRX_R_GL) ? m : FRX_DIV(m, P.g_mult);
 }
 
 // raw weight of the left stencil of resolution p at integer offset `off` (distance d = -off)
@@ -191,4 +193,16 @@ FRX_HD void frx_left_layout(int rule, long long p, long long* first, long long* 
         *first = -p;
         *count = p + 1;
     }
+}
+
+// ---- Gruenwald-Letnikov extension: w_k = prod_{d=1..k} (1 - (alpha+1)/d), accumulated in double-double ----------
+// factor d as a double-double: (alpha+1)/d with the exact remainder, then 1 - q
+FRX_HD frx_dd frx_gl_factor(double alpha, double d) {
+    const double ap1 = FRX_ADD(alpha, 1.0);                 // rounding of alpha+1 is part of the definition used here
+    const double q = FRX_DIV(ap1, d);
+    const double r = FRX_FMA(-q, d, ap1);                   // exact: ap1 - q*d
+    const double ql = FRX_DIV(r, d);
+    frx_dd one_minus = frx_two_sum(1.0, -q);
+    one_minus.lo = FRX_SUB(one_minus.lo, ql);
+    return frx_fast_two_sum(one_minus.hi, one_minus.lo);
 }

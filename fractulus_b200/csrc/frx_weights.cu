@@ -3,6 +3,7 @@
 #include "frx_internal.h"
 #include "frx_rules.cuh"
 #include "frx_table.cuh"
+#include "frx_gl.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K5: one CTA per Settings(alpha, lf, resolution); thread k produces the node at offset first + k.
@@ -17,9 +18,24 @@ __global__ void __launch_bounds__(128) frx_k5_stencil_weights(int rule, int side
                                                               int32_t* __restrict__ offsets, double* __restrict__ weights) {
     __shared__ frx_par P;
     __shared__ double s_mult, s_K, s_sgn;
+    __shared__ frx_gl_smem<128> GS;
     const int64_t s = blockIdx.x;
     const double a = alpha[s], L = lf[s], res = resolution[s];
     const long long p = (long long)res;
+    if (rule == FRX_R_GL) {   // extension: weight h**(-alpha) * w_x at offset -x, x = 0..p (left side only)
+        if (threadIdx.x == 0) {
+            P = frx_par_exponents(rule, a);
+            s_mult = frx_multiplier(P, L, res);
+        }
+        __syncthreads();
+        const double mult = s_mult;
+        const int64_t base = row_ptr[s];
+        frx_gl_block<128>(GS, a, p + 1, [&](long long x, double w) {
+            weights[base + (p - x)] = FRX_MUL(mult, w);
+            if (offsets) offsets[base + (p - x)] = (int32_t)(-x);
+        });
+        return;
+    }
     if (threadIdx.x == 0) {
         P = frx_par_init(rule, a);
         s_mult = frx_multiplier(P, L, res);
@@ -76,7 +92,7 @@ extern "C" int frx_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_s
                                    const double* d_lf, const double* d_resolution, const int64_t* h_row_ptr,
                                    int32_t* d_offsets, double* d_weights) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
+    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_LAST, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
     FRX_REQUIRE(side >= FRX_SIDE_LEFT && side <= FRX_SIDE_RIESZ_CAPUTO, FRX_ERR_INVALID_ARG, "bad side");
     FRX_REQUIRE(n_settings >= 0 && n_settings < ((int64_t)1 << 31), FRX_ERR_INVALID_ARG, "bad n_settings");
     if (n_settings == 0) return FRX_OK;
@@ -152,6 +168,44 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k1_weights_table(int rul
                     cB ? cB + a * ldc : nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 ? cm1 + a : nullptr);
 }
 
+// Gruenwald-Letnikov tables (extension): one CTA per alpha walks the whole table as a chunked prefix product.
+// cA[c_pad + x] = w_x (x < N; permuted like the other rules if c_perm), w0[i] = w_i, mult[i] = step_i ** (-alpha).
+__global__ void __launch_bounds__(256) frx_k1_gl_table(const double* __restrict__ alpha, double h, int64_t N,
+                                                       const frx_alpha_scalars* __restrict__ sc, int c_pad, int c_perm,
+                                                       double* __restrict__ cA, int64_t ldc, double* __restrict__ w0,
+                                                       double* __restrict__ mult, int64_t ldw, double* __restrict__ cm1) {
+    __shared__ frx_gl_smem<256> GS;
+    const int64_t a = blockIdx.x;
+    const frx_alpha_scalars* S = sc + a;
+    double* ca = cA + a * ldc;
+    for (int64_t X = threadIdx.x; X < ldc; X += 256) ca[X] = 0.0;   // front padding and the tail beyond N
+    if (threadIdx.x == 0 && cm1) cm1[a] = 0.0;
+    __syncthreads();
+    frx_gl_block<256>(GS, alpha[a], N + 1, [&](long long x, double w) {
+        if (x < N) ca[c_perm ? c_pad + (x & ~7LL) + ((x & 3) * 2 + ((x >> 2) & 1)) : c_pad + x] = w;
+        double m = 0.0, wf = 0.0;
+        if (x >= 1) {
+            const double xd = (double)x, step = FRX_DIV(FRX_MUL(xd, h), xd);
+            if (step == S->step[1]) m = S->mult[1];
+            else if (step == S->step[0]) m = S->mult[0];
+            else if (step == S->step[2]) m = S->mult[2];
+            else m = frx_pow_cr(step, S->P.e_mult);
+            wf = w;                                               // node number 0 of row i sits at distance i
+        }
+        w0[a * ldw + x] = wf;
+        mult[a * ldw + x] = m;
+    });
+}
+
+int frx_launch_gl_table(frx_ctx* ctx, int64_t n_alpha, const double* d_alpha, double h, int64_t N, const void* d_scalars,
+                        int c_pad, int c_perm, double* d_cA, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
+                        double* d_cm1) {
+    FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
+               frx_k1_gl_table<<<(unsigned)n_alpha, 256, 0, ctx->stream>>>(d_alpha, h, N, (const frx_alpha_scalars*)d_scalars,
+                                                                           c_pad, c_perm, d_cA, ldc, d_w0, d_mult, ldw, d_cm1));
+    return FRX_OK;
+}
+
 int frx_launch_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                              double* d_cA, double* d_cB, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
                              double* d_cm1) {
@@ -159,6 +213,8 @@ int frx_launch_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const doub
     if (rc) return rc;
     rc = frx_launch_alpha_scalars(ctx, rule, n_alpha, d_alpha, h, ctx->ws);
     if (rc) return rc;
+    if (rule == FRX_RULE_GRUNWALD_LETNIKOV)
+        return frx_launch_gl_table(ctx, n_alpha, d_alpha, h, N, ctx->ws, 0, 0, d_cA, ldc, d_w0, d_mult, ldw, d_cm1);
     dim3 grid((unsigned)((ldc + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES), (unsigned)n_alpha);
     FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
                FRX_CUDA(frx_launch_dependent(frx_k1_weights_table, grid, dim3(FRX_TAB_BLOCK), 0, ctx->stream, rule, d_alpha, h,
@@ -171,7 +227,7 @@ extern "C" int frx_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const 
                                  double* d_cA, double* d_cB, int64_t ldc, double* d_w0, double* d_mult, int64_t ldw,
                                  double* d_cm1) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
+    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_LAST, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
     FRX_REQUIRE(n_alpha >= 0 && n_alpha <= 65535 && N >= 1, FRX_ERR_INVALID_ARG, "bad n_alpha (<= 65535) or N");
     FRX_REQUIRE(ldc >= frx_table_ldc(N) && ldw >= N + 1, FRX_ERR_INVALID_ARG, "leading dimension too small");
     FRX_REQUIRE(d_alpha && d_cA && d_w0 && d_mult, FRX_ERR_INVALID_ARG, "NULL buffer");

@@ -42,8 +42,13 @@ typedef enum {                  /* keys of _factory, reference fractulus/equatio
     FRX_RULE_CAPUTO = 0,        /* _create_left_caputo_stencil,           equation.py:42-59   */
     FRX_RULE_RECTANGLE = 1,     /* _create_left_rectangle_rule_stencil,   equation.py:62-73   */
     FRX_RULE_TRAPEZOIDAL = 2,   /* _create_left_trapezoidal_rule_stencil, equation.py:84-100  */
-    FRX_RULE_SIMPSON = 3        /* _create_left_simpson_rule_stencil,     equation.py:103-176 */
+    FRX_RULE_SIMPSON = 3,       /* _create_left_simpson_rule_stencil,     equation.py:103-176 */
+    /* EXTENSION, not a key of the reference: Gruenwald-Letnikov weights of the Riemann-Liouville
+     * derivative, w_0 = 1, w_k = w_{k-1} * (1 - (alpha+1)/k), stencil weight h**(-alpha) * w_k at offset -k,
+     * k = 0..resolution.  Left side only.  Python key 'grunwald_letnikov'. */
+    FRX_RULE_GRUNWALD_LETNIKOV = 4
 } frx_rule;
+#define FRX_RULE_LAST FRX_RULE_GRUNWALD_LETNIKOV
 
 typedef enum {
     FRX_SIDE_LEFT = 0,          /* create_left_stencil,         equation.py:28-29 */

@@ -279,3 +279,23 @@ def test_right_and_riesz_caputo_growing_history_vs_oracle():
     assert np.array_equal(yr_rev[::-1][1:], -yl_full[1:])
     with pytest.raises(ValueError):
         batched.history('simpson', 0.5, h, dev(np.append(g, 0.)), N=N, side='right')
+
+
+def test_grunwald_letnikov_history_extension():
+    """EXTENSION: y_i = (fl(i*h)/i)**(-alpha) * sum_{k=0..i} w_k g_{i-k}; exact weights from mpmath, O(N^2) sum in NumPy."""
+    from oracle import gl_exact
+    N, h, alpha = 3000, 1. / 3000, 0.6
+    x = np.arange(N + 1) * h
+    g = np.sin(3 * x) + x * x
+    w = gl_exact.weights(alpha, N + 1)
+    want = np.array([math.fsum(w[:i + 1] * g[i::-1]) for i in range(N + 1)])
+    steps = (np.arange(1, N + 1) * h) / np.arange(1, N + 1)
+    want[1:] *= np.array([gl_exact.multiplier(alpha, s, 1) for s in np.unique(steps)])[np.searchsorted(np.unique(steps), steps)]
+    got = batched.history('grunwald_letnikov', alpha, h, dev(g), N=N).cpu().numpy()
+    assert got[0] == 0.
+    ref = np.maximum(np.abs(want[1:]), 1e-3 * np.abs(want[1:]).max())
+    assert np.max(np.abs(got[1:] - want[1:]) / ref) <= 1e-12
+    # first-order consistency with the Riemann-Liouville derivative of f = x: x**(1-alpha)/gamma(2-alpha)
+    y = batched.history('grunwald_letnikov', alpha, h, dev(x), N=N).cpu().numpy()
+    exact = x[1:] ** (1 - alpha) / math.gamma(2 - alpha)
+    assert np.max(np.abs(y[N // 2:] - exact[N // 2 - 1:]) / exact[N // 2 - 1:]) < 5e-3

@@ -173,3 +173,18 @@ def test_caputo_alpha_between_one_and_two_vs_c_oracle():
                 first, w = orc('caputo', s)
                 assert st.first_offset == first
                 assert np.array_equal(st.weights_array, w), (alpha, res)
+
+
+def test_grunwald_letnikov_extension_vs_mpmath():
+    """EXTENSION key 'grunwald_letnikov' (not a key of the reference): prefix-product kernel in
+    double-double against an exact mpmath evaluation of the recurrence."""
+    from oracle import gl_exact
+    for alpha, lf, p in ((0.5, 1.0, 10), (0.3, 0.7, 257), (1.6, 2.0, 1500), (0.9, 1.0, 5000)):
+        st = fr.create_left_stencil('grunwald_letnikov', Settings(alpha, lf, p))
+        first, want = gl_exact.left_arrays(alpha, lf, p)
+        assert st.first_offset == first == -p and len(st.weights_array) == p + 1
+        err = np.abs(st.weights_array - want)
+        assert np.all(err <= np.spacing(np.abs(want))), (alpha, p, err.max())
+        assert np.mean(st.weights_array == want) > 0.98
+    with pytest.raises(ValueError):
+        fr.create_right_stencil('grunwald_letnikov', Settings(0.5, 1.0, 8))
