@@ -331,11 +331,13 @@ def run_b200(args):
             pass
         algo_bytes = A * 8.0 * (N_NODES + 1) + 8.0 * (N_NODES + 2)
         roofline = {
-            'kernel': 'frx_k2_history_main', 'bound': 'fp64', 'achieved': achieved, 'peak': peak_dfma,
-            'unit': 'TFLOP/s', 'frac': achieved / peak_dfma if peak_dfma else None,
-            'traffic': K2_DRAM_TRAFFIC_BYTES,
-            'peak_source': 'measured in this run: register-only DFMA probe (frx_measure_fp64_peak); '
-                           'MEASURED_PEAKS.json has no FP64 figure (bf16/HBM only); DMMA probe %.2f TFLOP/s' % peak_dmma,
+            'kernel': 'frx_k2_history_main (FP64 tensor cores, mma.m8n8k4.f64 = SASS DMMA)', 'bound': 'tensor',
+            'achieved': achieved, 'peak': peak_dmma,
+            'unit': 'TFLOP/s', 'frac': achieved / peak_dmma if peak_dmma else None,
+            'traffic': K2_DRAM_TRAFFIC_BYTES * A if A == 1 else None,
+            'peak_source': 'measured in this run: register-only DMMA m8n8k4 f64 probe (frx_measure_fp64_peak); '
+                           'MEASURED_PEAKS.json has no FP64 figure (bf16/HBM only); the DFMA-pipe probe reads %.2f TFLOP/s '
+                           '(frac of that: %.3f)' % (peak_dfma, achieved / peak_dfma if peak_dfma else float('nan')),
             'algorithmic_flop_per_launch': algo_flop, 'algorithmic_bytes_per_launch': algo_bytes,
             'kernel_ms': main_avg_ms, 'kernel_share_of_step': main_avg_ms / sum(per_step_kernel_ms.values()),
             'per_step_kernel_ms': per_step_kernel_ms,
@@ -522,9 +524,10 @@ def emit(line):
     _JSON_LINES.append(json.dumps(line))
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of frx_k2_history_main per launch from the committed
-# `ncu --set full` capture (profiles/); None until a capture exists.
-K2_DRAM_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of frx_k2_history_main per launch (cfg 2, one alpha) from the committed
+# `ncu --set full` capture profiles/r01_k2_history_main_v3_final_ncu_full.txt: 3.26 MB read (weight tables + padded
+# field; the algorithmic 1.6 MB are the field in and y out), 0 B written back during the kernel (y stays in L2).
+K2_DRAM_TRAFFIC_BYTES = 3263744
 
 
 def main():
