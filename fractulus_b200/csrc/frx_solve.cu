@@ -288,10 +288,31 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
                 double* __restrict__ myrow = W + lane * C;
                 const double* __restrict__ pr = prow;
                 const int cend = kc + len, e1 = cend < C ? cend : C - 1;
-#pragma unroll 4
-                for (int cs = kc + 1; cs <= e1; ++cs) myrow[cs] = fma(-l, pr[cs], myrow[cs]);
-#pragma unroll 4
-                for (int cs = 0; cs <= cend - C; ++cs) myrow[cs] = fma(-l, pr[cs], myrow[cs]);
+                // a warp issues in order: load 8 columns' operands back to back, then the FMAs, then the stores,
+                // so that one shared-memory latency is paid per 8 columns instead of per column
+                auto run = [&](int cs, int ce) {       // slots cs..ce inclusive
+                    for (; cs + 7 <= ce; cs += 8) {
+                        double pu[8], mv[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { pu[q] = pr[cs + q]; mv[q] = myrow[cs + q]; }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) myrow[cs + q] = fma(-l, pu[q], mv[q]);
+                    }
+                    if (cs <= ce) {                    // tail of up to 7 columns, same shape with predicates
+                        double pu[7], mv[7];
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) {
+                            const int c2 = cs + q <= ce ? cs + q : ce;
+                            pu[q] = pr[c2];
+                            mv[q] = myrow[c2];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 7; ++q)
+                            if (cs + q <= ce) myrow[cs + q] = fma(-l, pu[q], mv[q]);
+                    }
+                };
+                run(kc + 1, e1);
+                run(0, cend - C);
                 bval = fma(-l, bt, bval);
                 myrow[kc] = 0.0;                           // column slot kc becomes column k + C
             }
