@@ -186,7 +186,7 @@ def workload_config(world, alphas_per_gpu, workload='cfg2'):
                     "g=3cos3x+2x, rule 'caputo', FP64; %d alpha per GPU (%s); step = K1 weight tables + K2 history sum%s"
                     % (alphas_per_gpu, 'alpha=0.5' if world * alphas_per_gpu == 1 else
                        'alpha sweep linspace(0.1,0.9,%d) in contiguous blocks per rank' % (world * alphas_per_gpu),
-                       '' if world == 1 else ' + NCCL all_gather of results'),
+                       '' if world == 1 else ' + gather of all results on every GPU (see config.gather)'),
         'n_nodes': N_NODES, 'n_fields': 1, 'alphas_per_gpu': alphas_per_gpu, 'rule': RULE,
         'l2': 'flushed between timed steps by writing a %d MiB buffer' % (FLUSH_BYTES >> 20),
         'parallelism': 'independent alpha per GPU' if world > 1 else 'single GPU',
@@ -226,7 +226,31 @@ def run_b200(args):
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     ctx = _lib.context(local_rank)
 
+    # N > 1: the gather is fused into the history kernel (its epilogue stores every row into all peers' copies of
+    # the gathered array through symmetric-memory peer pointers; a device barrier ends the step).  NCCL all_gather
+    # is the fallback when symmetric memory cannot be set up (or with --nccl-gather).
+    peer, gather_mode = None, 'none'
+    if world > 1:
+        gather_mode = 'nccl all_gather'
+        if not args.nccl_gather:
+            ok = 1
+            try:
+                peer = sweep.PeerGather(world * A, N_NODES + 1)
+            except Exception as ex:      # noqa: BLE001 -- any failure means: use NCCL
+                ok, peer = 0, None
+                sys.stderr.write('PeerGather unavailable on rank %d: %r\n' % (rank, ex))
+            t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if t.item() == 0:
+                peer = None
+            else:
+                gather_mode = 'fused P2P stores from the kernel epilogue + symmetric-memory barrier'
+
     def step():
+        if peer is not None:
+            batched.history_gather(RULE, my_alphas, h, g, peer.ptrs, b, N_NODES)
+            peer.barrier()
+            return
         batched.history(RULE, my_alphas, h, g, N=N_NODES, out=y, validate=False)
         if world > 1:
             dist.all_gather_into_tensor(gathered, y.view(A, N_NODES + 1))
@@ -312,7 +336,11 @@ def run_b200(args):
         e2e_s = t.item()
     e2e_value = world * A * N_NODES / e2e_s
     # the host-buffer path and the device path give the same bits
-    y_dev = y.cpu().numpy().reshape(A, N_NODES + 1)
+    if peer is not None:     # the timed path wrote into the gathered array only
+        torch.cuda.synchronize()
+        y_dev = peer.buffer[b:e].cpu().numpy().reshape(A, N_NODES + 1)
+    else:
+        y_dev = y.cpu().numpy().reshape(A, N_NODES + 1)
     same = None
     if y_e2e is not None:
         same = bool(np.array_equal(np.asarray(y_e2e).reshape(-1, N_NODES + 1)[b:e], y_dev, equal_nan=True))
@@ -355,7 +383,7 @@ def run_b200(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(world, A),
+            'dtype': 'f64', 'data': 'synthetic', 'config': dict(workload_config(world, A), gather=gather_mode),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_s * 1e3, 'api': 'frx_history_host (C ABI, host buffers)' if world == 1 else
                     'fractulus_b200.sweep.history_sweep (host field in on every rank, gathered host result out on rank 0)',
@@ -540,6 +568,7 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=('cfg2', 'cfg3', 'cfg4'),
                     help='cfg2 (default, the headline line; with --alphas-per-gpu 1250 it is the cfg5 sweep) or cfg3')
     ap.add_argument('--solve-n', type=int, default=128, help='cfg4: unknowns per system (64..256)')
+    ap.add_argument('--nccl-gather', action='store_true', help='N > 1: gather with NCCL all_gather instead of the fused path')
     ap.add_argument('--skip-cpu', action='store_true', help='tuning only: skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':

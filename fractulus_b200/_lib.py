@@ -47,6 +47,9 @@ SIGNATURES = {
     'frx_history_sided': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_void_p, ctypes.c_double,
                                          ctypes.c_int64, ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p,
                                          ctypes.c_int64]),
+    'frx_history_gather': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, c_void_p, ctypes.c_double, ctypes.c_int64,
+                                          ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                          ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64, ctypes.c_int64]),
     'frx_history_host': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, c_double_p, ctypes.c_double,
                                         ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64,
                                         c_double_p, ctypes.c_int64]),

@@ -142,6 +142,23 @@ def history(approximation, alpha, h, g, N=None, out=None, validate=True, side='l
     return y
 
 
+def history_gather(approximation, alpha, h, g, peer_ptrs, row0, N, validate=False):
+    """Fused compute + gather: like history(side='left') but every result row is written into all the buffers in
+    `peer_ptrs` (device pointers to each GPU's copy of the gathered [rows, N+1] array) at row `row0 + problem`.
+    The caller synchronises the GPUs (sweep.PeerGather.barrier) before reading the gathered array."""
+    rule = _lib.RULES[approximation]
+    g2 = g.to(torch.float64).reshape(-1, g.shape[-1]).contiguous()
+    n_fields, n_g = g2.shape
+    if torch.is_tensor(alpha) and alpha.is_cuda and not validate:
+        d_alpha = alpha.to(torch.float64).reshape(-1).contiguous()
+    else:
+        d_alpha = _as_f64(_check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha), g.device)
+    ctx, idx = _ctx_for(g.device)
+    ptrs = (ctypes.c_uint64 * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+    _lib.check(_lib.lib().frx_history_gather(ctx.handle, rule, d_alpha.numel(), _ptr(d_alpha), float(h), int(N), n_fields,
+                                             _ptr(g2), n_g, n_g, len(peer_ptrs), ptrs, int(row0), N + 1))
+
+
 def toeplitz_apply(approximation, alpha, h, G, N=None, out=None):
     """K3: Y[f, i] = sum_j T[i, j] G[f, j] for ONE alpha and many fields (BASELINE cfg 3), T the lower-triangular
     growing-history operator.  G: cuda float64 [n_fields, n_g], field-major; T is never materialised."""

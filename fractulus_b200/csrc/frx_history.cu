@@ -112,6 +112,11 @@ struct HistParams {
     int side;          // FRX_SIDE_LEFT; FRX_SIDE_RIGHT: field read reversed, y[N-i] = -value; FRX_SIDE_RIESZ_CAPUTO: second
                        // pass over a y that holds the left result: y[N-i] = krc * (y[N-i] + sgn * (-value))
     const frx_alpha_scalars* sc;
+    // fused gather (left side only): every result row is stored into n_peers buffers -- this GPU's and its NVLink
+    // peers' copies of the gathered array -- at row y_row0 + prob instead of into y
+    int n_peers;
+    int64_t y_row0;
+    double* peer_y[FRX_MAX_PEERS];
     double* partial;   // [2 * grid][TI]
     int* tickets;      // [n_alpha * n_fields * n_tiles], zero on entry, zero again on exit
 };
@@ -337,7 +342,12 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
             v = p.mult[a * p.ldw + i] * s;
         }
         if (!rev) {
-            p.y[prob * p.ldy + i] = v;
+            if (p.n_peers == 0) {
+                p.y[prob * p.ldy + i] = v;
+            } else {
+                const int64_t at = (p.y_row0 + prob) * p.ldy + i;
+                for (int q = 0; q < p.n_peers; ++q) p.peer_y[q][at] = v;   // P2P stores over NVLink for q != self
+            }
         } else {
             // row i of the mirrored problem is node N-i; create_right_stencil negates the weights (equation.py:38-39)
             double* dst = p.y + prob * p.ldy + (p.N - i);
@@ -463,12 +473,21 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
     for (int64_t e = pb * blockDim.x + threadIdx.x; e < n_tickets; e += stride) tickets[e] = 0;
 }
 
+struct PeerTargets {
+    int n_peers;
+    int64_t row0;
+    double* y[FRX_MAX_PEERS];
+};
+
 template <class G>
 int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
-                 int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy) {
+                 int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy, const PeerTargets* peers) {
     HistParams p;
     p.rule = rule;
     p.side = side;
+    p.n_peers = peers ? peers->n_peers : 0;
+    p.y_row0 = peers ? peers->row0 : 0;
+    for (int q = 0; q < FRX_MAX_PEERS; ++q) p.peer_y[q] = (peers && q < peers->n_peers) ? peers->y[q] : nullptr;
     p.n_pass = rule == FRX_RULE_SIMPSON ? 2 : 1;
     p.N = N;
     p.n_alpha = n_alpha;
@@ -558,14 +577,15 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
 extern "C" int64_t frx_table_ldc(int64_t N) { return (N + 1 + kLdcQuantum - 1) / kLdcQuantum * kLdcQuantum; }
 
 static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
-                            int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy) {
+                            int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy,
+                            const PeerTargets* peers = nullptr) {
     // tile geometry: FRX_K2_VARIANT is a tuning/experiment switch, the default is the measured best
     static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 9;
     switch (variant) {
-        case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        case 4: return history_impl<MGeo<4, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
-        default: return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+        case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        case 4: return history_impl<MGeo<4, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        default: return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
     }
 }
 
@@ -592,6 +612,33 @@ extern "C" int frx_history_sided(frx_ctx* ctx, int rule, int side, int64_t n_alp
         if (rc) return rc;
     }
     return history_dispatch(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
+}
+
+// Fused compute + gather for sweeps sharded over the GPUs of one box: the history kernel's epilogue stores every
+// result row straight into each peer's copy of the gathered array (peer pointers obtained by the caller through CUDA
+// IPC / symmetric memory), so the transfer rides on NVLink while the remaining tiles are still being computed and no
+// collective follows -- only a barrier before the gathered array is read.
+extern "C" int frx_history_gather(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                                  int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, int32_t n_peers,
+                                  const uint64_t* h_peer_ptrs, int64_t row0, int64_t ldy) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    FRX_REQUIRE(rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_LAST, FRX_ERR_UNKNOWN_RULE, "unknown approximation key");
+    FRX_REQUIRE(n_peers >= 1 && n_peers <= FRX_MAX_PEERS && h_peer_ptrs != nullptr, FRX_ERR_INVALID_ARG, "bad peer list");
+    FRX_REQUIRE(N >= 1 && N < ((int64_t)1 << 30) && row0 >= 0, FRX_ERR_INVALID_ARG, "N / row offset out of range");
+    FRX_REQUIRE(n_alpha >= 0 && n_alpha <= 65535 && n_fields >= 0 && n_fields <= 32767, FRX_ERR_INVALID_ARG,
+                "n_alpha (<= 65535) / n_fields (<= 32767) out of range");
+    const int64_t need_g = N + 1 + (rule == FRX_RULE_SIMPSON ? 1 : 0);
+    FRX_REQUIRE(n_g >= need_g && ldg >= n_g && ldy >= N + 1, FRX_ERR_INVALID_ARG,
+                "field too short (needs N+1 nodes, N+2 for 'simpson') or leading dimension too small");
+    if (n_alpha == 0 || n_fields == 0) return FRX_OK;
+    FRX_REQUIRE(d_alpha && d_g, FRX_ERR_INVALID_ARG, "NULL buffer");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    PeerTargets pt;
+    pt.n_peers = n_peers;
+    pt.row0 = row0;
+    for (int q = 0; q < FRX_MAX_PEERS; ++q) pt.y[q] = q < n_peers ? (double*)(uintptr_t)h_peer_ptrs[q] : nullptr;
+    for (int q = 0; q < n_peers; ++q) FRX_REQUIRE(pt.y[q] != nullptr, FRX_ERR_INVALID_ARG, "NULL peer pointer");
+    return history_dispatch(ctx, rule, FRX_SIDE_LEFT, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, pt.y[0], ldy, &pt);
 }
 
 extern "C" int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,

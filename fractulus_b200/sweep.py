@@ -45,6 +45,29 @@ def gather_blocks(local, n_total, group=None):
     return torch.cat([buf[r * nmax:r * nmax + (e - b)] for r, (b, e) in enumerate(sizes)], dim=0)
 
 
+class PeerGather(object):
+    """The gathered result array [n_rows, row_len] of a sweep, allocated as symmetric memory so that every rank
+    holds device pointers to every peer's copy: batched.history_gather stores results straight into all copies
+    from the history kernel's epilogue (P2P stores over NVLink), and barrier() replaces the collective.
+    Raises if symmetric memory is unavailable; callers fall back to gather_blocks (NCCL all_gather)."""
+
+    def __init__(self, n_rows, row_len, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.buffer = symm_mem.empty((n_rows, row_len), dtype=torch.float64, device=dev)
+        self.handle = symm_mem.rendezvous(self.buffer, group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        # this rank's own copy first: frx_history_gather treats entry 0 like any other target
+        self.ptrs = [self.ptrs[self.rank]] + [p for r, p in enumerate(self.ptrs) if r != self.rank]
+
+    def barrier(self):
+        """All ranks' stores issued before this point are visible in every copy afterwards (device-side barrier
+        on the current stream)."""
+        self.handle.barrier(channel=0)
+
+
 _pinned = {}
 
 

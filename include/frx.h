@@ -135,6 +135,15 @@ int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, 
  * side: frx_side.  'simpson' is offered for FRX_SIDE_LEFT only. */
 int frx_history_sided(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                       int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy);
+/* Fused compute + gather (sweeps sharded over the GPUs of one box): like frx_history for
+ * FRX_SIDE_LEFT, but result row (a*n_fields + f) is stored at row row0 + a*n_fields + f of EVERY buffer in
+ * h_peer_ptrs (host array of n_peers device pointers: this GPU's and its NVLink peers' copies of the gathered
+ * [rows][ldy] array, mapped by the caller through CUDA IPC / symmetric memory).  The stores are issued by the
+ * history kernel's epilogue tile by tile; the caller only needs a barrier before reading the gathered array. */
+#define FRX_MAX_PEERS 8
+int frx_history_gather(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                       int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, int32_t n_peers,
+                       const uint64_t* h_peer_ptrs, int64_t row0, int64_t ldy);
 int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_alpha, double h, int64_t N,
                      int64_t n_fields, const double* h_g, int64_t ldg, int64_t n_g, double* h_y, int64_t ldy);
 

@@ -299,3 +299,16 @@ def test_grunwald_letnikov_history_extension():
     y = batched.history('grunwald_letnikov', alpha, h, dev(x), N=N).cpu().numpy()
     exact = x[1:] ** (1 - alpha) / math.gamma(2 - alpha)
     assert np.max(np.abs(y[N // 2:] - exact[N // 2 - 1:]) / exact[N // 2 - 1:]) < 5e-3
+
+
+def test_fused_gather_entry_point_single_gpu():
+    """frx_history_gather with the only peer being this GPU: rows land at row0 + problem of the target array and
+    equal the plain history bit for bit."""
+    N, h = 3000, 1. / 3000
+    g = dev(smooth_field(N + 2, h))
+    alphas = [0.25, 0.5, 0.75]
+    want = batched.history('caputo', alphas, h, g, N=N)
+    out = torch.full((7, N + 1), -1.0, dtype=torch.float64, device='cuda')
+    batched.history_gather('caputo', alphas, h, g, [out.data_ptr()], 2, N, validate=True)
+    assert torch.equal(out[2:5], want)
+    assert bool((out[:2] == -1).all()) and bool((out[5:] == -1).all())
