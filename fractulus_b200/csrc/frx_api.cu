@@ -57,7 +57,6 @@ extern "C" int frx_ctx_destroy(frx_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->scalars) cudaFree(ctx->scalars);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < FRX_EV_POOL; ++i) {
         if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
         if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
@@ -184,20 +183,6 @@ int frx_io_reserve(frx_ctx* ctx, size_t bytes) {
         return FRX_ERR_ALLOC;
     }
     ctx->io_bytes = want;
-    return FRX_OK;
-}
-
-int frx_pinned_reserve(frx_ctx* ctx, size_t bytes) {
-    if (bytes <= ctx->pinned_bytes) return FRX_OK;
-    if (ctx->pinned) {
-        FRX_CUDA(cudaStreamSynchronize(ctx->stream));
-        FRX_CUDA(cudaFreeHost(ctx->pinned));
-        ctx->pinned = nullptr;
-        ctx->pinned_bytes = 0;
-    }
-    size_t want = frx_align_up(bytes, (size_t)1 << 16);
-    FRX_CUDA(cudaMallocHost(&ctx->pinned, want));
-    ctx->pinned_bytes = want;
     return FRX_OK;
 }
 

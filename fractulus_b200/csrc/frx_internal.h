@@ -19,9 +19,6 @@ struct frx_ctx {
     void* io;
     size_t io_bytes;
     void* scalars;         // 256 bytes of device memory for by-value scalar arguments
-    // small pinned host staging for the *_host entry points
-    void* pinned;
-    size_t pinned_bytes;
     // optional per-kernel CUDA-event timing (frx_ctx_set_timing): bench.py's roofline numbers
     int timing;
     int ev_n;
@@ -67,7 +64,6 @@ void frx_set_error(const char* fmt, ...);
 
 // ensure ctx->ws holds at least `bytes`; contents are NOT preserved on growth
 int frx_ws_reserve(frx_ctx* ctx, size_t bytes);
-int frx_pinned_reserve(frx_ctx* ctx, size_t bytes);
 int frx_io_reserve(frx_ctx* ctx, size_t bytes);
 // host-side domain check of one Settings triple against the reference's behaviour
 int frx_check_settings(int rule, double alpha, double resolution);
