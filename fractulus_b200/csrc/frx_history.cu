@@ -19,7 +19,8 @@
 //     makes the per-thread LDS.128 bank-conflict free (consecutive lanes land on distinct 16-byte bank
 //     groups: stride/16 is odd).
 //   * the triangular edge and the first column are handled by zero padding (a padded copy of the field
-//     with g_j = 0 for j <= 0 is made by the prepare kernel), so the inner loop has no predicates.
+//     with zeros in front is made by the prepare kernel; rows/columns are shifted by one so that the operator is
+//     exactly N x N), so the inner loop has no predicates.
 //   * a row tile finished inside one CTA is scaled and written directly; a tile split between CTAs
 //     goes through per-CTA partial slots, and the LAST CTA to arrive (atomic ticket per tile) adds
 //     the slots in CTA order -> bitwise deterministic results, no floating-point atomics.
@@ -121,11 +122,13 @@ struct HistParams {
     int* tickets;      // [n_alpha * n_fields * n_tiles], zero on entry, zero again on exit
 };
 
+// Rows and columns are tiled in SHIFTED coordinates i' = i - 1, j' = j - 1 (row 0 is identically 0 and column 0 is
+// the first column, handled in the epilogue), so the operator is exactly N x N lower triangular incl. the diagonal:
+// S_{i'} = sum_{j' <= i'} c[i' - j'] g_{j'+1}.  Tile I holds rows i' in [I*TI, (I+1)*TI) and needs the chunks
+// (of columns j' for the tensor variant, of distances for the DFMA variant) up to i'_last.
 template <class G>
 __host__ __device__ inline int64_t tile_chunks(int64_t I, int64_t n_tiles, int64_t N) {
-    // DFMA variant: chunks of distances, the rows of tile I need d <= i_last - 1;
-    // tensor variant: chunks of columns, they need j <= i_last
-    return I + 1 < n_tiles ? (I + 1) * (G::TI / G::TD) : (N + (G::TENSOR ? 1 : 0) + G::TD - 1) / G::TD;
+    return I + 1 < n_tiles ? (I + 1) * (G::TI / G::TD) : (N + G::TD - 1) / G::TD;
 }
 template <class G>
 __host__ __device__ inline int64_t tile_prefix(int64_t I, int n_pass) {  // units before tile I (tiles < I are full)
@@ -327,20 +330,7 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
     const bool rev = p.side != FRX_SIDE_LEFT;
     const double g0 = rev ? gf[p.N] : gf[0];
     const double cm1 = p.rule == FRX_RULE_SIMPSON ? p.cm1[a] : 0.0;
-#pragma unroll
-    for (int r = 0; r < G::R; ++r) {
-        const int64_t i = I * G::TI + acc_pair_row<G>(r >> 1) + (r & 1);
-        if (i > p.N) continue;
-        double v;
-        if (i == 0) {
-            v = 0.0;
-        } else if (i == 1 && (p.rule == FRX_RULE_RECTANGLE || p.rule == FRX_RULE_SIMPSON)) {
-            v = nan("");  // the reference cannot build this stencil
-        } else {
-            double s = fma(p.w0[a * p.ldw + i], g0, acc[r]);
-            if (p.rule == FRX_RULE_SIMPSON && (i & 1)) s = fma(cm1, gf[i + 1], s);
-            v = p.mult[a * p.ldw + i] * s;
-        }
+    auto store_row = [&](int64_t i, double v) {   // v: value of row i of the (possibly mirrored) left operator
         if (!rev) {
             if (p.n_peers == 0) {
                 p.y[prob * p.ldy + i] = v;
@@ -358,6 +348,22 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
                 *dst = boundary ? nan("") : p.sc[a].krc * (*dst + p.sc[a].sgn * (-v));
             }
         }
+    };
+#pragma unroll
+    for (int r = 0; r < G::R; ++r) {
+        const int64_t ip = I * G::TI + acc_pair_row<G>(r >> 1) + (r & 1);   // shifted row i' = i - 1
+        const int64_t i = ip + 1;
+        if (i > p.N) continue;
+        if (ip == 0) store_row(0, 0.0);               // row 0 has no stencil: y_0 = 0 by convention
+        double v;
+        if (i == 1 && (p.rule == FRX_RULE_RECTANGLE || p.rule == FRX_RULE_SIMPSON)) {
+            v = nan("");  // the reference cannot build this stencil
+        } else {
+            double s = fma(p.w0[a * p.ldw + i], g0, acc[r]);
+            if (p.rule == FRX_RULE_SIMPSON && (i & 1)) s = fma(cm1, gf[i + 1], s);
+            v = p.mult[a * p.ldw + i] * s;
+        }
+        store_row(i, v);
     }
 }
 
@@ -441,7 +447,7 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
 }
 
 // prepare kernel: blocks [0, n_tab) generate the weight tables (K1); the remaining blocks build the padded
-// copies of the fields, gp[(f*n_pass + pass)*ldgp + padf + j] = g_j for 1 <= j <= N (for 'simpson' only the
+// copies of the fields, gp[(f*n_pass + pass)*ldgp + padf + j'] = g_{j'+1} for 0 <= j' < N (for 'simpson' only the
 // nodes of the pass's parity: pass 0 even, pass 1 odd) and 0 elsewhere, and clear the tickets.
 __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, const double* __restrict__ alpha, double h, int64_t N,
                                                           const frx_alpha_scalars* __restrict__ sc,
@@ -467,7 +473,9 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
         const int64_t fp = e / ldgp, x = e - fp * ldgp;
         const int64_t f = fp / n_pass, pass = fp - f * n_pass, j = x - padf;
         double v = 0.0;
-        if (j >= 1 && j <= N && (n_pass == 1 || (j & 1) == pass)) v = g[f * ldg + (reverse ? N - j : j)];
+        // slot padf + j' holds column j = j' + 1 (shifted coordinates, see tile_chunks)
+        const int64_t jj = j + 1;
+        if (jj >= 1 && jj <= N && (n_pass == 1 || (jj & 1) == pass)) v = g[f * ldg + (reverse ? N - jj : jj)];
         gp[e] = v;
     }
     for (int64_t e = pb * blockDim.x + threadIdx.x; e < n_tickets; e += stride) tickets[e] = 0;
@@ -492,7 +500,7 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     p.N = N;
     p.n_alpha = n_alpha;
     p.n_fields = n_fields;
-    p.n_tiles = (N + 1 + G::TI - 1) / G::TI;
+    p.n_tiles = (N + G::TI - 1) / G::TI;
     p.units_per_prob = tile_prefix<G>(p.n_tiles - 1, p.n_pass) + p.n_pass * tile_chunks<G>(p.n_tiles - 1, p.n_tiles, N);
     p.total_units = p.units_per_prob * n_alpha * n_fields;
     // tables are zero beyond d = N-1 up to the end of the last tile: whole-tile reads stay in bounds and finite
