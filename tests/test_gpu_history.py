@@ -312,3 +312,33 @@ def test_fused_gather_entry_point_single_gpu():
     batched.history_gather('caputo', alphas, h, g, [out.data_ptr()], 2, N, validate=True)
     assert torch.equal(out[2:5], want)
     assert bool((out[:2] == -1).all()) and bool((out[5:] == -1).all())
+
+
+def test_empty_batches_and_argument_errors():
+    g = dev(smooth_field(102, 0.01))
+    y = batched.history('caputo', np.zeros(0), 0.01, g, N=100)
+    assert tuple(y.shape) == (0, 101)
+    Y = batched.toeplitz_apply('caputo', 0.5, 0.01, torch.zeros((0, 102), dtype=torch.float64, device='cuda'), N=100)
+    assert tuple(Y.shape) == (0, 101)
+    with pytest.raises(ValueError):
+        batched.history('caputo', 0.5, 0.01, g, N=200)              # field shorter than N+1 nodes
+    with pytest.raises(ValueError):
+        batched.history('simpson', 0.5, 0.01, g, N=101)             # 'simpson' needs N+2 nodes
+    with pytest.raises(ZeroDivisionError):
+        batched.history('rectangle', 1.5, 0.01, g, N=100)           # like equation.py:68
+    with pytest.raises(KeyError):
+        batched.history('nope', 0.5, 0.01, g, N=100)
+    with pytest.raises(ValueError):
+        batched.history('caputo', np.full(70000, 0.5), 0.01, g, N=100)   # documented batch limit
+
+
+def test_beyond_baseline_size_sampled_rows():
+    """N = 262144 (2^18, 2.6x BASELINE's N): sampled rows against the reference algorithm (C oracle, bit-identical to
+    the reference), incl. the last row -- guards the tile / 64-bit index arithmetic at sizes the fixtures do not reach."""
+    N = 1 << 18
+    h = 1. / N
+    g = np.array(smooth_field(N + 2, h))
+    y = batched.history('caputo', 0.35, h, dev(g), N=N).cpu().numpy()
+    rows = np.array([1, 2, 1023, 1024, 1025, 65536, 131071, 131072, 200001, N - 1, N])
+    want = clib.history_rows_naive('caputo', 0.35, h, g, rows)
+    assert_history_close('caputo', 0.35, h, rows, y[rows], want, g, 0.8)

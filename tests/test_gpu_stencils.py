@@ -188,3 +188,19 @@ def test_grunwald_letnikov_extension_vs_mpmath():
         assert np.mean(st.weights_array == want) > 0.98
     with pytest.raises(ValueError):
         fr.create_right_stencil('grunwald_letnikov', Settings(0.5, 1.0, 8))
+
+
+def test_large_single_stencil_and_float_resolution():
+    """a 20001-node stencil through the API path, and resolution given as a float like the reference's own
+    fr.Settings(alpha, lf, lf) (test/integration/test_equation.py:91)."""
+    s = Settings(0.45, 2.0, 20000)
+    st = fr.create_left_stencil('trapezoidal', s)
+    first, w = clib.left_arrays('trapezoidal', s)
+    assert st.first_offset == first and len(st.weights_array) == len(w) == 20001
+    assert np.all(np.abs(st.weights_array - w) <= weight_tolerance('trapezoidal', 0.45, 2.0, 20000))
+    assert np.mean(st.weights_array == w) > 0.99
+    a = fr.create_riesz_caputo_stencil('caputo', Settings(0.8, 4, 4.0))
+    b = fr.create_riesz_caputo_stencil('caputo', Settings(0.8, 4, 4))
+    assert a == b
+    with pytest.raises(ValueError):
+        fr.create_left_stencil('caputo', Settings(0.5, 1.0, 4.5))
