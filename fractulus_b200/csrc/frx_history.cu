@@ -593,6 +593,8 @@ static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, c
         case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 4: return history_impl<MGeo<4, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        case 5: return history_impl<MGeo<4, 1024, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        case 6: return history_impl<MGeo<4, 512, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         default: return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
     }
 }

@@ -195,11 +195,12 @@ __global__ void __launch_bounds__(kSolveThreads) frx_k4_assemble_solve(const Sol
 // Retired U rows (2nb+1 entries) and the transformed right-hand side stream to a per-warp scratch in global memory
 // (L2) and are read back, prefetched four rows ahead, by the back substitution.  Needs nb <= 31.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kStreamWarps = 4;
+constexpr int kStreamWarps = 1;   // one-warp CTAs: shared memory (19 KB per system) is the occupancy limit, small CTAs pack it best
 constexpr int kStreamMaxNb = 31;
 constexpr int kStreamC = 2 * kStreamMaxNb + 1;
 constexpr int kStreamMaxN = 256;
-constexpr int kStreamWarpDoubles = 32 * kStreamC + kStreamC + 1 + kStreamMaxN;   // window + band coefficients (+1 pad) + rhs
+constexpr int kStreamRS = (kStreamC + 7) / 8 * 8 + 1;   // largest row stride: ring padded to a multiple of 8, +1 -> odd
+constexpr int kStreamWarpDoubles = 32 * kStreamRS + kStreamC + 1 + kStreamMaxN;   // window + band coefficients (+1 pad) + rhs
 
 struct StreamParams {
     int64_t n_sys;
@@ -218,8 +219,8 @@ struct StreamParams {
 __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const StreamParams p) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
-    double* W = sm + warp * kStreamWarpDoubles;          // W[slot * C + column slot]
-    double* a = W + 32 * kStreamC;                       // a[k + nb]
+    double* W = sm + warp * kStreamWarpDoubles;          // W[row slot * RS + column slot]
+    double* a = W + 32 * kStreamRS;                      // a[k + nb]
     double* bs = a + kStreamC + 1;                       // right-hand side, overwritten in place by the transformed one
     const int64_t gw = (int64_t)blockIdx.x * kStreamWarps + warp, nw = (int64_t)gridDim.x * kStreamWarps;
     double* U = p.uscratch + gw * (int64_t)n * kStreamC;
@@ -228,6 +229,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
         const int nb_a = res + 1;
         const int nb = nb_a > n - 1 ? n - 1 : nb_a;      // rows below k+nb are zero in column k
         const int C = 2 * nb + 1;
+        // the ring of C column slots is padded with always-zero slots to Cp (multiple of 8) so that the elimination
+        // runs over whole batches of 8 slots without predicates; row stride Cp + 1 is odd -> conflict-free lanes
+        const int Cp = (C + 7) & ~7, RS = Cp + 1;
         const double ih = 1.0 / p.h[s];
         const double* rc = p.rcw + p.wptr[s] + res;
         const double* rhs = p.rhs + s * p.ldb;
@@ -250,31 +254,31 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
         int logical = (lane <= nb && lane < n) ? lane : -1;
         double bval = logical >= 0 ? bs[lane] : 0.0;
         if (logical >= 0)
-            for (int j = 0; j < C; ++j) {
+            for (int j = 0; j < Cp; ++j) {
                 const int d = j - lane;
-                W[lane * C + j] = (d >= -nb && d <= nb && j < n) ? a[d + nb] : 0.0;
+                W[lane * RS + j] = (j < C && d >= -nb && d <= nb && j < n) ? a[d + nb] : 0.0;
             }
         int info = 0, kc = 0;                              // kc = k % C
         __syncwarp();
         for (int k = 0; k < n; ++k) {
             const bool active = logical >= 0;
-            const double v = active ? W[lane * C + kc] : 0.0;
-            double best = active ? fabs(v) : -1.0;
-            int blog = active ? logical : 0x7fffffff, bl = lane;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, d);
-                const int ol = __shfl_xor_sync(0xffffffffu, blog, d), oln = __shfl_xor_sync(0xffffffffu, bl, d);
-                if (ob > best || (ob == best && ol < blog)) { best = ob; blog = ol; bl = oln; }
-            }
-            const int P = bl;                              // pivot lane; blog = its row label
+            const double v = active ? W[lane * RS + kc] : 0.0;
+            // pivot = active lane with the largest |v|, ties -> lowest row label (LAPACK's first maximum).  |v| >= 0, so
+            // its bit pattern orders like an unsigned integer: two 32-bit warp reductions instead of a shuffle tree
+            const unsigned long long bits = active ? (unsigned long long)__double_as_longlong(fabs(v)) : 0ull;
+            const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+            const bool cand = active && hi == mh && lo == ml;
+            const int blog = __reduce_min_sync(0xffffffffu, cand ? logical : 0x7fffffff);
+            const int P = __ffs(__ballot_sync(0xffffffffu, cand && logical == blog)) - 1;   // pivot lane; blog = its label
             const double pval = __shfl_sync(0xffffffffu, v, P), bt = __shfl_sync(0xffffffffu, bval, P);
             if (pval == 0.0 && info == 0) info = k + 1;
             const bool worker = active && lane != P;
             const double l = worker ? v * (1.0 / pval) : 0.0;
             if (worker && logical == k) logical = blog;    // the interchange, on labels only
             const int cmax = min(n - 1, k + 2 * nb), len = cmax - k;   // U row k: columns k..cmax
-            const double* prow = W + P * C;
+            const double* prow = W + P * RS;
             // retire the pivot row: U[k][0..len] and the transformed right-hand side
             for (int c = lane; c <= len; c += 32) {
                 int cs = kc + c; if (cs >= C) cs -= C;
@@ -283,36 +287,19 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
             if (lane == 0) bs[k] = bt;                     // slot k is free: rhs[k] entered the window long ago
             // eliminate
             if (worker) {
-                // columns k+1..cmax occupy ring slots kc+1..kc+len, i.e. at most two straight runs; the pivot row is
-                // another lane's row, hence __restrict__ (lets the loads of later columns pass earlier stores)
-                double* __restrict__ myrow = W + lane * C;
+                // every slot of the padded ring, in batches of 8: slots beyond cmax and the pad slots hold zeros in both
+                // rows, slot kc (column k itself) is overwritten below.  A warp issues in order, so the 16 loads of a
+                // batch go out back to back, then the FMAs, then the stores; the pivot row is another lane's row, hence
+                // __restrict__.
+                double* __restrict__ myrow = W + lane * RS;
                 const double* __restrict__ pr = prow;
-                const int cend = kc + len, e1 = cend < C ? cend : C - 1;
-                // a warp issues in order: load 8 columns' operands back to back, then the FMAs, then the stores,
-                // so that one shared-memory latency is paid per 8 columns instead of per column
-                auto run = [&](int cs, int ce) {       // slots cs..ce inclusive
-                    for (; cs + 7 <= ce; cs += 8) {
-                        double pu[8], mv[8];
+                for (int cs = 0; cs < Cp; cs += 8) {
+                    double pu[8], mv[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) { pu[q] = pr[cs + q]; mv[q] = myrow[cs + q]; }
+                    for (int q = 0; q < 8; ++q) { pu[q] = pr[cs + q]; mv[q] = myrow[cs + q]; }
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) myrow[cs + q] = fma(-l, pu[q], mv[q]);
-                    }
-                    if (cs <= ce) {                    // tail of up to 7 columns, same shape with predicates
-                        double pu[7], mv[7];
-#pragma unroll
-                        for (int q = 0; q < 7; ++q) {
-                            const int c2 = cs + q <= ce ? cs + q : ce;
-                            pu[q] = pr[c2];
-                            mv[q] = myrow[c2];
-                        }
-#pragma unroll
-                        for (int q = 0; q < 7; ++q)
-                            if (cs + q <= ce) myrow[cs + q] = fma(-l, pu[q], mv[q]);
-                    }
-                };
-                run(kc + 1, e1);
-                run(0, cend - C);
+                    for (int q = 0; q < 8; ++q) myrow[cs + q] = fma(-l, pu[q], mv[q]);
+                }
                 bval = fma(-l, bt, bval);
                 myrow[kc] = 0.0;                           // column slot kc becomes column k + C
             }
@@ -320,12 +307,12 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
             // refill the retired slot with matrix row k+nb+1 (columns k+1 .. k+2nb+1 = the whole new window)
             const int inew = k + nb + 1;
             if (inew < n) {
-                double* nrow = W + P * C;
+                double* nrow = W + P * RS;
                 for (int c = lane; c < C; c += 32) {
                     const int j = k + 1 + c;
                     int cs = kc + 1 + c; if (cs >= C) cs -= C;
                     nrow[cs] = j < n ? a[j - inew + nb] : 0.0;
-                }
+                }   // (the pad slots C..Cp-1 of this row slot are still zero: nothing ever writes a non-zero there)
                 if (lane == P) { logical = inew; bval = bs[inew]; }
             } else if (lane == P) {
                 logical = -1;
