@@ -409,6 +409,9 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     const size_t o_par = carve(sizeof(double) * 4 * (size_t)n_sys);
     const size_t o_wptr = carve(sizeof(int64_t) * (size_t)(n_sys + 1) * 2);
     const size_t o_w = carve(sizeof(double) * (size_t)wptr[n_sys]);
+    extern size_t frx_k5_scratch_bytes(int64_t);
+    const size_t o_k5 = carve(frx_k5_scratch_bytes(n_sys));
+    const int64_t total_w = wptr[n_sys];
     rc = frx_ws_reserve(ctx, off);
     if (rc) { free(wptr); free(lf); return rc; }
     char* ws = (char*)ctx->ws;
@@ -427,9 +430,9 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     }
     // K5 for the whole batch (row pointer already on the device)
     extern int frx_launch_stencil_weights(frx_ctx*, int, int, int64_t, const double*, const double*, const double*,
-                                          const int64_t*, int32_t*, double*);
+                                          const int64_t*, int64_t, void*, int32_t*, double*);
     rc = frx_launch_stencil_weights(ctx, rule, FRX_SIDE_RIESZ_CAPUTO, n_sys, d_par, d_par + n_sys, d_par + 2 * n_sys,
-                                    (const int64_t*)(ws + o_wptr), nullptr, (double*)(ws + o_w));
+                                    (const int64_t*)(ws + o_wptr), total_w, ws + o_k5, nullptr, (double*)(ws + o_w));
     free(wptr); free(lf);
     if (rc) return rc;
     // every band narrow enough: one warp per system, window in shared memory, U streamed through L2

@@ -78,13 +78,92 @@ __global__ void __launch_bounds__(128) frx_k5_stencil_weights(int rule, int side
     }
 }
 
-// K5 launch with the row pointer already on the device (used by frx_assemble_solve)
+// Batched form of K5 for the four reference rules: (a) one THREAD per Settings evaluates its scalars (gammas,
+// multiplier, Riesz-Caputo constant) -- every thread runs the same chain, so the warp stays converged; (b) one
+// thread per stencil NODE of the whole batch (the stencil is found by bisection in row_ptr) evaluates its weight.
+struct frx_k5_scalars {
+    frx_par P;
+    double mult, K, sgn;
+};
+
+__global__ void __launch_bounds__(128) frx_k5a_settings_scalars(int rule, int64_t n, const double* __restrict__ alpha,
+                                                                const double* __restrict__ lf,
+                                                                const double* __restrict__ resolution,
+                                                                frx_k5_scalars* __restrict__ out) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    frx_k5_scalars S;
+    S.P = frx_par_init(rule, alpha[s]);
+    S.mult = frx_multiplier(S.P, lf[s], resolution[s]);
+    S.K = FRX_DIV(FRX_MUL(0.5, frx_gamma_py(FRX_SUB(2.0, alpha[s]))), 1.0);   // 1./2.*gamma(2.-alpha)/gamma(2.)   equation.py:23
+    S.sgn = (((long long)S.P.n) & 1) ? -1.0 : 1.0;                             // (-1.) ** n                       equation.py:24
+    out[s] = S;
+}
+
+__global__ void __launch_bounds__(128) frx_k5b_stencil_nodes(int rule, int side, int64_t n, int64_t total,
+                                                             const double* __restrict__ resolution,
+                                                             const int64_t* __restrict__ row_ptr,
+                                                             const frx_k5_scalars* __restrict__ scal,
+                                                             int32_t* __restrict__ offsets, double* __restrict__ weights) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    int64_t lo = 0, hi = n;                   // row_ptr[lo] <= e < row_ptr[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (row_ptr[mid] <= e) lo = mid; else hi = mid;
+    }
+    const int64_t s = lo, k = e - row_ptr[s];
+    const frx_k5_scalars& S = scal[s];
+    const frx_par P = S.P;
+    const long long p = (long long)resolution[s];
+    long long lfirst, lcount;
+    frx_left_layout(rule, p, &lfirst, &lcount);
+    const long long llast = lfirst + lcount - 1;
+    long long first = lfirst;
+    if (side == FRX_SIDE_RIGHT) first = -llast;
+    else if (side == FRX_SIDE_RIESZ_CAPUTO) first = lfirst < -llast ? lfirst : -llast;
+    const long long o = first + k;
+    const double mult = S.mult;
+    double w;
+    if (side == FRX_SIDE_LEFT) {
+        w = FRX_MUL(mult, frx_raw_at_offset(P, p, o));                 // multiplier * weight(node)   :78-79
+    } else if (side == FRX_SIDE_RIGHT) {
+        w = FRX_MUL(FRX_MUL(mult, frx_raw_at_offset(P, p, -o)), -1.0);  // symmetry + multiply(-1.)    :38-39
+    } else {
+        const bool in_left = (o >= lfirst && o <= llast), in_mirror = (-o >= lfirst && -o <= llast);
+        double acc = 0.0;
+        if (in_left) acc = FRX_MUL(mult, frx_raw_at_offset(P, p, o));
+        if (in_mirror) {
+            double r = FRX_MUL(S.sgn, FRX_MUL(FRX_MUL(mult, frx_raw_at_offset(P, p, -o)), -1.0));
+            acc = in_left ? FRX_ADD(acc, r) : r;
+        }
+        w = FRX_MUL(S.K, acc);
+    }
+    weights[e] = w;
+    if (offsets) offsets[e] = (int32_t)o;
+}
+
+size_t frx_k5_scratch_bytes(int64_t n_settings) { return sizeof(frx_k5_scalars) * (size_t)n_settings; }
+
+// K5 launch with the row pointer already on the device (also used by frx_assemble_solve).  d_scratch:
+// frx_k5_scratch_bytes(n_settings) bytes of device memory; total = row_ptr[n_settings].
 int frx_launch_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_settings, const double* d_alpha,
-                               const double* d_lf, const double* d_resolution, const int64_t* d_row_ptr,
-                               int32_t* d_offsets, double* d_weights) {
+                               const double* d_lf, const double* d_resolution, const int64_t* d_row_ptr, int64_t total,
+                               void* d_scratch, int32_t* d_offsets, double* d_weights) {
+    if (rule == FRX_RULE_GRUNWALD_LETNIKOV || total > (int64_t)64 * n_settings + 4096) {
+        // the GL scan is CTA-cooperative; very long stencils keep one CTA each (one pass over row_ptr is cheaper)
+        FRX_LAUNCH(ctx, FRX_K_STENCIL,
+                   frx_k5_stencil_weights<<<(unsigned)n_settings, 128, 0, ctx->stream>>>(
+                       rule, side, d_alpha, d_lf, d_resolution, d_row_ptr, d_offsets, d_weights));
+        return FRX_OK;
+    }
     FRX_LAUNCH(ctx, FRX_K_STENCIL,
-               frx_k5_stencil_weights<<<(unsigned)n_settings, 128, 0, ctx->stream>>>(
-                   rule, side, d_alpha, d_lf, d_resolution, d_row_ptr, d_offsets, d_weights));
+               frx_k5a_settings_scalars<<<(unsigned)((n_settings + 127) / 128), 128, 0, ctx->stream>>>(
+                   rule, n_settings, d_alpha, d_lf, d_resolution, (frx_k5_scalars*)d_scratch));
+    FRX_LAUNCH(ctx, FRX_K_STENCIL,
+               frx_k5b_stencil_nodes<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
+                   rule, side, n_settings, total, d_resolution, d_row_ptr, (const frx_k5_scalars*)d_scratch, d_offsets,
+                   d_weights));
     return FRX_OK;
 }
 
@@ -98,13 +177,14 @@ extern "C" int frx_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_s
     if (n_settings == 0) return FRX_OK;
     FRX_REQUIRE(d_alpha && d_lf && d_resolution && h_row_ptr && d_weights, FRX_ERR_INVALID_ARG, "NULL buffer");
     FRX_CUDA(cudaSetDevice(ctx->device));
-    // row_ptr travels through the workspace (it is host data describing the caller's layout)
-    size_t bytes = sizeof(int64_t) * (size_t)(n_settings + 1);
-    int rc = frx_ws_reserve(ctx, bytes);
+    // row_ptr travels through the workspace (it is host data describing the caller's layout): [row_ptr][scalars]
+    const size_t bytes = frx_align_up(sizeof(int64_t) * (size_t)(n_settings + 1), 256);
+    int rc = frx_ws_reserve(ctx, bytes + frx_k5_scratch_bytes(n_settings));
     if (rc) return rc;
-    FRX_CUDA(cudaMemcpyAsync(ctx->ws, h_row_ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FRX_CUDA(cudaMemcpyAsync(ctx->ws, h_row_ptr, sizeof(int64_t) * (size_t)(n_settings + 1), cudaMemcpyHostToDevice,
+                             ctx->stream));
     return frx_launch_stencil_weights(ctx, rule, side, n_settings, d_alpha, d_lf, d_resolution, (const int64_t*)ctx->ws,
-                                      d_offsets, d_weights);
+                                      h_row_ptr[n_settings], (char*)ctx->ws + bytes, d_offsets, d_weights);
 }
 
 extern "C" int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double alpha, double lf, double resolution,
@@ -116,8 +196,9 @@ extern "C" int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double
     *count = cnt;
     FRX_REQUIRE(capacity >= cnt, FRX_ERR_INVALID_ARG, "capacity smaller than the stencil length");
     FRX_CUDA(cudaSetDevice(ctx->device));
-    // workspace: [row_ptr (2 x i64, written by frx_stencil_weights)] [3 doubles] [weights] [offsets]
-    size_t off_par = 64, off_w = 128, off_o = off_w + frx_align_up(sizeof(double) * cnt, 64);
+    // workspace: [row_ptr (2 x i64) + scalars, written by frx_stencil_weights] [3 doubles] [weights] [offsets]
+    size_t off_par = 256 + frx_align_up(frx_k5_scratch_bytes(1), 256), off_w = off_par + 64,
+           off_o = off_w + frx_align_up(sizeof(double) * cnt, 64);
     size_t total = off_o + sizeof(int32_t) * (size_t)cnt;
     rc = frx_ws_reserve(ctx, total);
     if (rc) return rc;
