@@ -179,3 +179,19 @@ def weight_tolerance(rule, alpha, lf, res):
     emax = {'caputo': n - alpha + 1., 'trapezoidal': 2. - alpha, 'rectangle': 1. - alpha, 'simpson': 3. - alpha}[rule]
     mult = (lf / res) ** ({'caputo': n - alpha}.get(rule, 1. - alpha))
     return 8 * np.finfo(float).eps * mult * (res + 2.) ** emax
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under fractulus_b200/ (Python or CUDA) may import, include or
+    load anything from oracle/, and the shared library must not link it."""
+    pkg = os.path.join(REPO, 'fractulus_b200')
+    for root, _, files in os.walk(pkg):
+        if '_build' in root or '__pycache__' in root:
+            continue
+        for name in files:
+            if name.endswith(('.py', '.cu', '.cuh', '.h', '.inc')):
+                for line in open(os.path.join(root, name)):
+                    code = line.split('//')[0] if name.endswith(('.cu', '.cuh', '.h', '.inc')) else line.split('#')[0]
+                    assert not re.search(r'\b(import|from|include|CDLL)\b.*oracle', code), (name, line)
+    out = subprocess.run(['ldd', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'oracle' not in out
