@@ -159,6 +159,25 @@ def history_gather(approximation, alpha, h, g, peer_ptrs, row0, N, validate=Fals
                                              _ptr(g2), n_g, n_g, len(peer_ptrs), ptrs, int(row0), N + 1))
 
 
+def history_solve(approximation, alpha, h, f, u0):
+    """Inverse of history(side='left'): u[a, :] with u[a, 0] = u0[a] and history(approximation, alpha_a, h, u[a])[i] = f[a, i]
+    for i = 1..N (f[:, 0] is ignored).  alpha: 1-D (host); f: cuda float64 [n_alpha, N+1]; u0: scalar or [n_alpha].
+    'caputo' / 'trapezoidal'.  Extension: the reference has no solver."""
+    rule = _lib.RULES[approximation]
+    a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha)
+    if not torch.is_tensor(f) or not f.is_cuda or f.dim() != 2 or f.shape[0] != len(a_h):
+        raise TypeError('f must be a CUDA tensor [n_alpha, N+1]')
+    f = f.to(torch.float64).contiguous()
+    n_alpha, n1 = f.shape
+    ctx, idx = _ctx_for(f.device)
+    d_alpha = _as_f64(a_h, f.device)
+    d_u0 = _as_f64(np.broadcast_to(np.asarray(u0.cpu().numpy() if torch.is_tensor(u0) else u0, dtype=np.float64), (n_alpha,)).copy(), f.device)
+    u = torch.empty_like(f)
+    _lib.check(_lib.lib().frx_history_solve(ctx.handle, rule, n_alpha, _ptr(d_alpha), float(h), n1 - 1, _ptr(f), n1, _ptr(d_u0),
+                                            _ptr(u), n1))
+    return u
+
+
 def toeplitz_apply(approximation, alpha, h, G, N=None, out=None):
     """K3: Y[f, i] = sum_j T[i, j] G[f, j] for ONE alpha and many fields (BASELINE cfg 3), T the lower-triangular
     growing-history operator.  G: cuda float64 [n_fields, n_g], field-major; T is never materialised."""

@@ -147,6 +147,14 @@ int frx_history_gather(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_
 int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_alpha, double h, int64_t N,
                      int64_t n_fields, const double* h_g, int64_t ldg, int64_t n_g, double* h_y, int64_t ldy);
 
+/* ---- inverse of the growing-history operator (EXTENSION: the reference has no solver) -------------
+ * For every alpha: given f_1..f_N (d_f[a*ldf + i]) and the initial value u0[a], find u with
+ *   frx_history(rule, alpha, h, u)[i] = f_i, i = 1..N     (u_0 = u0; rows = Settings(alpha, i*h, i) stencils),
+ * by blocked forward substitution on the lower-triangular Toeplitz system (csrc/frx_ode.cu).  One implicit step of a
+ * fractional ODE / Volterra equation; 'caputo' and 'trapezoidal' only.  d_u[a*ldu + i], i = 0..N. */
+int frx_history_solve(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
+                      const double* d_f, int64_t ldf, const double* d_u0, double* d_u, int64_t ldu);
+
 /* ---- K3: batched Toeplitz application (one alpha, many fields) ----------------------------------
  * Y[f*ldy + i] = sum_j T[i][j] * G[f*ldg + j], T the (N+1)x(N+1) lower-triangular growing-history operator of
  * (rule, alpha, h) -- the dense contraction of BASELINE cfg 3 (N = 16384 x 4096 fields).  Fields are stored

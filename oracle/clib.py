@@ -36,6 +36,7 @@ def lib():
                                              lp, ctypes.c_long, dp, ctypes.c_int]
         L.orc_history_full.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long, dp,
                                        ctypes.c_long, ctypes.c_long, ctypes.c_long, dp, ctypes.c_long, ctypes.c_int]
+        L.orc_history_solve.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long, dp, ctypes.c_double, dp]
         _lib = L
     return _lib
 
@@ -123,3 +124,11 @@ def history_full(rule, alpha, h, N, g, n_threads=0):
     _raise(lib().orc_history_full(RULE_CODE[rule], float(alpha), float(h), N, _dp(g2), g2.shape[1], g2.shape[0],
                                   g2.shape[1], _dp(y), N + 1, n_threads))
     return y.reshape(g.shape[:-1] + (N + 1,))
+
+
+def history_solve(rule, alpha, h, f, u0):
+    """u with history(u)[i] = f[i], i = 1..N, u[0] = u0: forward substitution with the reference's weights."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    u = np.empty_like(f)
+    _raise(lib().orc_history_solve(RULE_CODE[rule], float(alpha), float(h), len(f) - 1, _dp(f), float(u0), _dp(u)))
+    return u

@@ -289,6 +289,27 @@ int orc_history_full(int rule, double alpha, double h, long N, const double* g, 
     return ORC_OK;
 }
 
+/* Inverse of the growing-history operator by forward substitution with the reference's own weights
+ * w_ij = mult_i * raw (every weight rounded like the reference's): given f_1..f_N and u_0 find u_1..u_N with
+ * sum_j w_ij u_j = f_i.  The reference has no solver; this is the definition the GPU extension
+ * frx_history_solve is checked against.  'caputo' (0) and 'trapezoidal' (2). */
+int orc_history_solve(int rule, double alpha, double h, long N, const double* f, double u0, double* u) {
+    if (rule != 0 && rule != 2) return ORC_ERR_RULE;
+    double* cA = (double*)malloc(sizeof(double) * (size_t)(N + 1) * 4);
+    double *cB = cA + (N + 1), *w0 = cB + (N + 1), *mult = w0 + (N + 1), cm1;
+    orc_tables(rule, alpha, h, N, cA, cB, w0, mult, &cm1);
+    u[0] = u0;
+    for (long i = 1; i <= N; ++i) {
+        const double m = mult[i];
+        nsum s = {0., 0.};
+        nsum_add(&s, u[0] * (m * w0[i]));
+        for (long d = i - 1; d >= 1; --d) nsum_add(&s, u[i - d] * (m * cA[d]));
+        u[i] = (f[i] - nsum_get(&s)) / (m * cA[0]);
+    }
+    free(cA);
+    return ORC_OK;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

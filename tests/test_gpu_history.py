@@ -342,3 +342,23 @@ def test_beyond_baseline_size_sampled_rows():
     rows = np.array([1, 2, 1023, 1024, 1025, 65536, 131071, 131072, 200001, N - 1, N])
     want = clib.history_rows_naive('caputo', 0.35, h, g, rows)
     assert_history_close('caputo', 0.35, h, rows, y[rows], want, g, 0.8)
+
+
+def test_history_solve_inverts_the_operator():
+    """EXTENSION frx_history_solve: blocked forward substitution on the lower-triangular Toeplitz system, against the
+    oracle's sequential forward substitution with the reference's weights, and as a round trip through K2."""
+    for N in (5, 1000, 1024, 1025, 5000):
+        h = 1. / N
+        x = np.arange(N + 1) * h
+        u_true = np.sin(3 * x) + x * x + 0.5
+        for rule, alphas in (('caputo', [0.3, 0.7]), ('trapezoidal', [0.5])):
+            f = batched.history(rule, alphas, h, dev(u_true), N=N)                  # [n_alpha, N+1]
+            u = batched.history_solve(rule, alphas, h, f, u_true[0]).cpu().numpy()
+            for ai, a in enumerate(alphas):
+                want = clib.history_solve(rule, a, h, f[ai].cpu().numpy(), u_true[0])
+                scale = np.abs(want).max()
+                assert np.abs(u[ai] - want).max() <= 1e-10 * scale, (rule, a, N, np.abs(u[ai] - want).max())
+                assert np.abs(u[ai] - u_true).max() <= 1e-9 * scale                  # round trip
+                assert u[ai, 0] == u_true[0]
+    with pytest.raises(ValueError):
+        batched.history_solve('simpson', [0.5], 0.1, torch.zeros((1, 12), dtype=torch.float64, device='cuda'), 0.)
