@@ -98,8 +98,11 @@ struct MGeo {
 
 struct HistParams {
     int rule, n_pass;
-    int64_t N, n_alpha, n_fields, n_tiles, units_per_prob, total_units;
-    const double *cA, *cB;
+    // n_sub sub-problems per (alpha, field): 1, or 2 for 'simpson' (rows of even / odd shifted index i' = 2r + q, each a
+    // half-size Toeplitz problem in r with two passes over the even / odd columns); NR = rows per sub-problem
+    int n_sub;
+    int64_t N, NR, n_alpha, n_fields, n_tiles, units_per_prob, total_units;
+    const double* tabs;   // Toeplitz tables [n_alpha][n_sub * n_pass][ldc]
     int64_t ldc;
     const double *w0, *mult;
     int64_t ldw;
@@ -151,7 +154,7 @@ __device__ inline Cursor cursor_at(const HistParams& p, int64_t u) {
     while (I + 1 < p.n_tiles && tile_prefix<G>(I + 1, p.n_pass) <= w) ++I;
     c.I = I;
     c.v = w - tile_prefix<G>(I, p.n_pass);
-    c.chunks = tile_chunks<G>(I, p.n_tiles, p.N);
+    c.chunks = tile_chunks<G>(I, p.n_tiles, p.NR);
     c.units = c.chunks * p.n_pass;
     return c;
 }
@@ -164,7 +167,7 @@ __device__ inline void cursor_advance(const HistParams& p, Cursor& c) {
             c.I = 0;
             ++c.prob;
         }
-        c.chunks = tile_chunks<G>(c.I, p.n_tiles, p.N);
+        c.chunks = tile_chunks<G>(c.I, p.n_tiles, p.NR);
         c.units = c.chunks * p.n_pass;
     }
 }
@@ -185,10 +188,10 @@ template <class G>
 __device__ inline void stage_unit_mma(const HistParams& p, const Cursor& c, char* stage) {
     const int64_t pass = c.v / c.chunks;
     const int64_t j0 = (c.v - pass * c.chunks) * G::TD;
-    const int64_t a = c.prob / p.n_fields, f = c.prob - a * p.n_fields;
+    const int64_t pf = c.prob / p.n_sub, q = c.prob - pf * p.n_sub, a = pf / p.n_fields, f = pf - a * p.n_fields;
     // row u of the window holds distances 8e..8e+7, e = e_base + u, e_base = p0 - m0 - MC
     const int64_t d_base = c.I * G::TI - j0 - G::TD;
-    const double* csrc = (pass ? p.cB : p.cA) + a * p.ldc + G::C_PAD + d_base;
+    const double* csrc = p.tabs + ((a * p.n_sub + q) * p.n_pass + pass) * p.ldc + G::C_PAD + d_base;
     const double* gsrc = p.gp + (f * p.n_pass + pass) * p.ldgp + G::PADF + j0 - 8;
     const int t = threadIdx.x;
 #pragma unroll
@@ -248,8 +251,8 @@ __device__ inline void stage_unit(const HistParams& p, const Cursor& c, char* st
     } else {
     const int64_t pass = c.v / c.chunks;
     const int64_t d0 = (c.v - pass * c.chunks) * G::TD;
-    const int64_t a = c.prob / p.n_fields, f = c.prob - a * p.n_fields;
-    const double* ctab = (pass ? p.cB : p.cA) + a * p.ldc + d0;
+    const int64_t pf = c.prob / p.n_sub, q = c.prob - pf * p.n_sub, a = pf / p.n_fields, f = pf - a * p.n_fields;
+    const double* ctab = p.tabs + ((a * p.n_sub + q) * p.n_pass + pass) * p.ldc + d0;
     const double* gsrc = p.gp + (f * p.n_pass + pass) * p.ldgp + G::PADF + c.I * G::TI - d0 - G::TD;
     const int t = threadIdx.x;
     for (int q = t; q < G::TD / 2; q += kNT) cp_async16(stage + 16 * q, ctab + 2 * q);
@@ -325,7 +328,9 @@ __device__ inline int acc_pair_row(int q) {
 // scale, add the first column / right-of-point terms and store the R rows of this thread
 template <class G>
 __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I, const double (&acc)[G::R]) {
-    const int64_t a = prob / p.n_fields, f = prob - a * p.n_fields;
+    // prob counts sub-problems: ((alpha * n_fields + field) * n_sub + q)
+    const int64_t pf = prob / p.n_sub, q = prob - pf * p.n_sub, a = pf / p.n_fields, f = pf - a * p.n_fields;
+    prob = pf;   // from here on: the (alpha, field) pair that owns the output row
     const double* gf = p.g + f * p.ldg;
     const bool rev = p.side != FRX_SIDE_LEFT;
     const double g0 = rev ? gf[p.N] : gf[0];
@@ -351,7 +356,7 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
     };
 #pragma unroll
     for (int r = 0; r < G::R; ++r) {
-        const int64_t ip = I * G::TI + acc_pair_row<G>(r >> 1) + (r & 1);   // shifted row i' = i - 1
+        const int64_t ip = (I * G::TI + acc_pair_row<G>(r >> 1) + (r & 1)) * p.n_sub + q;   // shifted row i' = i - 1
         const int64_t i = ip + 1;
         if (i > p.N) continue;
         if (ip == 0) store_row(0, 0.0);               // row 0 has no stencil: y_0 = 0 by convention
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
 // nodes of the pass's parity: pass 0 even, pass 1 odd) and 0 elsewhere, and clear the tickets.
 __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, const double* __restrict__ alpha, double h, int64_t N,
                                                           const frx_alpha_scalars* __restrict__ sc,
-                                                       double* __restrict__ cA, double* __restrict__ cB, int64_t ldc,
+                                                       double* __restrict__ tabs, int64_t ldc, int n_tab_per_alpha, int dec,
                                                        double* __restrict__ w0, double* __restrict__ mult, int64_t ldw,
                                                        double* __restrict__ cm1, int c_pad, int c_perm, int64_t n_tab,
                                                        int64_t tab_per_alpha,
@@ -463,8 +468,9 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
     frx_grid_launch_dependents();   // the history kernel may be scheduled as this grid drains; it waits before reading
     if (bx < n_tab) {
         const int64_t a = bx / tab_per_alpha;
-        frx_table_block(S, sc + a, rule, alpha[a], h, N, (bx - a * tab_per_alpha) * FRX_TAB_ENTRIES, c_pad, c_perm, cA + a * ldc,
-                        cB ? cB + a * ldc : nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 + a);
+        // tables of alpha a: n_tab_per_alpha consecutive tables of ldc entries (1; 'simpson': the 4 decimated ones)
+        frx_table_block(S, sc + a, rule, alpha[a], h, N, (bx - a * tab_per_alpha) * FRX_TAB_ENTRIES, c_pad, c_perm, dec,
+                        tabs + a * n_tab_per_alpha * ldc, nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 + a);
         return;
     }
     const int64_t n_pad_blocks = gridDim.x - n_tab, pb = bx - n_tab;
@@ -473,9 +479,10 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
         const int64_t fp = e / ldgp, x = e - fp * ldgp;
         const int64_t f = fp / n_pass, pass = fp - f * n_pass, j = x - padf;
         double v = 0.0;
-        // slot padf + j' holds column j = j' + 1 (shifted coordinates, see tile_chunks)
-        const int64_t jj = j + 1;
-        if (jj >= 1 && jj <= N && (n_pass == 1 || (jj & 1) == pass)) v = g[f * ldg + (reverse ? N - jj : jj)];
+        // slot padf + j' holds column j = j' + 1 (shifted coordinates, see tile_chunks); 'simpson' (n_pass = 2): pass e
+        // holds every second column, slot padf + k <-> j' = 2k + e
+        const int64_t jj = (n_pass == 1 ? j : 2 * j + pass) + 1;
+        if (j >= 0 && jj <= N) v = g[f * ldg + (reverse ? N - jj : jj)];
         gp[e] = v;
     }
     for (int64_t e = pb * blockDim.x + threadIdx.x; e < n_tickets; e += stride) tickets[e] = 0;
@@ -496,20 +503,24 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     p.n_peers = peers ? peers->n_peers : 0;
     p.y_row0 = peers ? peers->row0 : 0;
     for (int q = 0; q < FRX_MAX_PEERS; ++q) p.peer_y[q] = (peers && q < peers->n_peers) ? peers->y[q] : nullptr;
-    p.n_pass = rule == FRX_RULE_SIMPSON ? 2 : 1;
+    const bool simpson = rule == FRX_RULE_SIMPSON;
+    p.n_pass = simpson ? 2 : 1;
+    p.n_sub = simpson ? 2 : 1;
     p.N = N;
+    p.NR = simpson ? (N + 1) / 2 : N;       // rows i' = 2r + q, q = 0, 1: at most ceil(N/2) per sub-problem
     p.n_alpha = n_alpha;
     p.n_fields = n_fields;
-    p.n_tiles = (N + G::TI - 1) / G::TI;
-    p.units_per_prob = tile_prefix<G>(p.n_tiles - 1, p.n_pass) + p.n_pass * tile_chunks<G>(p.n_tiles - 1, p.n_tiles, N);
-    p.total_units = p.units_per_prob * n_alpha * n_fields;
-    // tables are zero beyond d = N-1 up to the end of the last tile: whole-tile reads stay in bounds and finite
-    p.ldc = G::C_PAD + (frx_table_ldc(N) > p.n_tiles * G::TI ? frx_table_ldc(N) : p.n_tiles * G::TI);
+    p.n_tiles = (p.NR + G::TI - 1) / G::TI;
+    p.units_per_prob = tile_prefix<G>(p.n_tiles - 1, p.n_pass) + p.n_pass * tile_chunks<G>(p.n_tiles - 1, p.n_tiles, p.NR);
+    p.total_units = p.units_per_prob * n_alpha * n_fields * p.n_sub;
+    // tables are zero beyond the last distance up to the end of the last tile: whole-tile reads stay in bounds and finite
+    p.ldc = G::C_PAD + (frx_table_ldc(p.NR) > p.n_tiles * G::TI ? frx_table_ldc(p.NR) : p.n_tiles * G::TI);
+    const int n_tabs = p.n_sub * p.n_pass;  // tables per alpha
     p.ldw = (N + 1 + 1) / 2 * 2;
     p.ldgp = G::PADF + p.n_tiles * G::TI;
     int64_t NG = (int64_t)ctx->sm_count * G::CTAS_PER_SM;
     if (NG > p.total_units * G::SUBS) NG = p.total_units * G::SUBS;
-    const int64_t n_tickets = n_alpha * n_fields * p.n_tiles;
+    const int64_t n_tickets = n_alpha * n_fields * p.n_sub * p.n_tiles;
 
     // workspace carve-up (all offsets multiples of 256 bytes)
     size_t off = 0;
@@ -518,8 +529,7 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
         off += frx_align_up(bytes, 256);
         return o;
     };
-    const size_t o_cA = carve(sizeof(double) * (size_t)n_alpha * p.ldc);
-    const size_t o_cB = carve(p.n_pass == 2 ? sizeof(double) * (size_t)n_alpha * p.ldc : 0);
+    const size_t o_cA = carve(sizeof(double) * (size_t)n_alpha * n_tabs * p.ldc);
     const size_t o_w0 = carve(sizeof(double) * (size_t)n_alpha * p.ldw);
     const size_t o_mult = carve(sizeof(double) * (size_t)n_alpha * p.ldw);
     const size_t o_cm1 = carve(sizeof(double) * (size_t)n_alpha);
@@ -531,13 +541,11 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     if (rc) return rc;
     char* ws = (char*)ctx->ws;
     double* cA = (double*)(ws + o_cA);
-    double* cB = p.n_pass == 2 ? (double*)(ws + o_cB) : nullptr;
     double* w0 = (double*)(ws + o_w0);
     double* mult = (double*)(ws + o_mult);
     double* cm1 = (double*)(ws + o_cm1);
     double* gp = (double*)(ws + o_gp);
-    p.cA = cA;
-    p.cB = cB;
+    p.tabs = cA;
     p.w0 = w0;
     p.mult = mult;
     p.cm1 = cm1;
@@ -552,7 +560,11 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
 
     {
         const bool gl = rule == FRX_RULE_GRUNWALD_LETNIKOV;   // extension: its tables come from their own scan kernel
-        const int64_t tab_per_alpha = (p.ldc + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES, n_tab = gl ? 0 : tab_per_alpha * n_alpha;
+        // table CTAs cover the storage slots of one table (the base sequences d = 0..N for 'simpson')
+        const int64_t cover = simpson ? G::C_PAD + N + 1 : p.ldc;
+        const int64_t tab_per_alpha = (cover + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES, n_tab = gl ? 0 : tab_per_alpha * n_alpha;
+        if (simpson)   // the four decimated tables are scattered into: padding, tails and T(0,1)[0] must be zero
+            FRX_CUDA(cudaMemsetAsync(cA, 0, sizeof(double) * (size_t)n_alpha * n_tabs * p.ldc, ctx->stream));
         const int64_t n_fp = n_fields * p.n_pass;
         int64_t n_pad = (n_fp * p.ldgp + 8 * kNT - 1) / (8 * kNT);
         if (n_pad > 4096) n_pad = 4096;
@@ -565,7 +577,7 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
         }
         FRX_LAUNCH(ctx, FRX_K_WEIGHTS_TABLE,
                    FRX_CUDA(frx_launch_dependent(frx_k12_prepare, dim3((unsigned)(n_tab + n_pad)), dim3(FRX_TAB_BLOCK), 0,
-                                                 ctx->stream, rule, d_alpha, h, N, (const frx_alpha_scalars*)(ws + o_scal), cA, cB, p.ldc, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
+                                                 ctx->stream, rule, d_alpha, h, N, (const frx_alpha_scalars*)(ws + o_scal), cA, p.ldc, n_tabs, (int)simpson, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
                                                  n_fp, p.ldgp, (int)G::PADF, gp, p.tickets, n_tickets,
                                                  (int)(side != FRX_SIDE_LEFT))));
     }

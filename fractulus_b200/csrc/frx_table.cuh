@@ -93,7 +93,7 @@ struct frx_pow_shared {
 // is written by the preceding kernel K0: it is read only after the grid-dependency wait, so under programmatic
 // dependent launch the power evaluation overlaps K0.
 __device__ __forceinline__ void frx_table_block(frx_table_smem& S, const frx_alpha_scalars* __restrict__ sc, int rule,
-                                                double alpha, double h, int64_t N, int64_t X0, int c_pad, int c_perm,
+                                                double alpha, double h, int64_t N, int64_t X0, int c_pad, int c_perm, int dec,
                                                 double* __restrict__ cA, double* __restrict__ cB, int64_t ldc,
                                                 double* __restrict__ w0, double* __restrict__ mult,
                                                 double* __restrict__ cm1) {
@@ -130,11 +130,15 @@ __device__ __forceinline__ void frx_table_block(frx_table_smem& S, const frx_alp
     __syncthreads();
     if (t < FRX_TAB_HALO || t >= FRX_TAB_THREADS - FRX_TAB_HALO) return;  // halo threads and the scalar warps
     const int64_t X = X0 + (t - FRX_TAB_HALO);
-    if (X >= ldc) return;
+    // dec (Simpson inside frx_history): the two base sequences are scattered into four half-length tables, see below;
+    // the caller has zeroed them, entries 0 <= x <= N are all this CTA writes
+    if (dec ? X > c_pad + N : X >= ldc) return;
     const int64_t x = X - c_pad;
     if (x < 0) {
-        cA[X] = 0.0;
-        if (cB) cB[X] = 0.0;
+        if (!dec) {
+            cA[X] = 0.0;
+            if (cB) cB[X] = 0.0;
+        }
         return;
     }
     const frx_par& P = S.sc.P;
@@ -146,9 +150,24 @@ __device__ __forceinline__ void frx_table_block(frx_table_smem& S, const frx_alp
         if (rule == FRX_R_SIMPSON) cb = frx_raw_toeplitz_pw(P, xd, false, pw);
     }
     // the DMMA history kernel wants every aligned group of 8 distances stored as [0 4 1 5 2 6 3 7]
-    const int64_t slot = c_perm ? c_pad + (x & ~(int64_t)7) + ((x & 3) * 2 + ((x >> 2) & 1)) : X;
-    cA[slot] = ca;
-    if (cB) cB[slot] = cb;
+    auto slot_of = [&](int64_t d) { return c_perm ? c_pad + (d & ~(int64_t)7) + ((d & 3) * 2 + ((d >> 2) & 1)) : c_pad + d; };
+    if (!dec) {
+        cA[slot_of(x)] = ca;
+        if (cB) cB[slot_of(x)] = cb;
+    } else if (x < N) {
+        // Simpson as four half-size Toeplitz problems (shifted coordinates i' = i-1 = 2r + q, j' = j-1 = 2k + e):
+        // the coefficient of (i', j') is cE[d] for odd j' (even node j) and cO[d] for even j', d = i' - j' = 2(r-k) + q - e,
+        // so table T(q,e)[r-k] takes every second entry of the base sequence:  T(q,e) = cA + (2q+e)*ldc
+        //   cE (e=1): d even -> T(1,1)[d/2],   d odd -> T(0,1)[(d+1)/2]  (T(0,1)[0] = 0: column k = r lies right of row r)
+        //   cO (e=0): d even -> T(0,0)[d/2],   d odd -> T(1,0)[(d-1)/2]
+        if ((x & 1) == 0) {
+            cA[3 * ldc + slot_of(x >> 1)] = ca;
+            cA[0 * ldc + slot_of(x >> 1)] = cb;
+        } else {
+            cA[1 * ldc + slot_of((x + 1) >> 1)] = ca;
+            cA[2 * ldc + slot_of((x - 1) >> 1)] = cb;
+        }
+    }
     if (x <= N) {
         double w = 0.0, m = 0.0;
         if (x >= 1) {

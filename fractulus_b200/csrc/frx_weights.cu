@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k1_weights_table(int rul
                                                                            double* __restrict__ cm1) {
     __shared__ frx_table_smem S;
     const int64_t a = blockIdx.y;
-    frx_table_block(S, sc + a, rule, alpha[a], h, N, (int64_t)blockIdx.x * FRX_TAB_ENTRIES, 0, 0, cA + a * ldc,
+    frx_table_block(S, sc + a, rule, alpha[a], h, N, (int64_t)blockIdx.x * FRX_TAB_ENTRIES, 0, 0, 0, cA + a * ldc,
                     cB ? cB + a * ldc : nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 ? cm1 + a : nullptr);
 }
 
