@@ -1,31 +1,32 @@
-// frx_history.cu -- K2: the "history sum" of the growing-history fractional operator,
-//     S_i = sum_{d=0}^{i-1} c[d] * g_{i-d},   i = 0..N         (lower-triangular Toeplitz mat-vec)
-//     y_i = mult[i] * (S_i + w0[i]*g_0 [+ cm1*g_{i+1}]),
-// the O(N^2) loop that the reference performs in Python by rebuilding the stencil of
-// Settings(alpha, i*h, i) for every node i and summing weight*value over its nodes
-// (reference fractulus/test/integration/test_equation.py:48-57; weights equation.py:42-176).
+// frx_history.cu -- K2 / K3: the "history sum" of the growing-history fractional operator,
+//     S_i = sum_{j=1}^{i} c[i-j] * g_j,                       i = 1..N   (lower-triangular Toeplitz mat-vec)
+//     y_i = mult[i] * (S_i + w0[i]*g_0 [+ cm1*g_{i+1}]),      y_0 = 0,
+// the O(N^2) loop that the reference performs in Python by rebuilding the stencil of Settings(alpha, i*h, i) for every
+// node i and summing weight*value over its nodes (reference fractulus/test/integration/test_equation.py:48-57; weights
+// equation.py:42-176).  FP64-compute bound (N = 1e5: 5e9 FMA over 1.6 MB of input).
 //
-// FP64 DFMA-pipe bound (N = 1e5: 5e9 FMA over 1.6 MB of input), so the design goal is one DFMA per
-// (i, d) pair with as few other instructions as possible:
-//   * work unit  = TI rows x TD distances.  Units are laid out in a 1-D sequence (alpha, field, row
-//     tile, pass, distance chunk) and dealt in equal contiguous spans to a grid of exactly
-//     sm_count * CTAS_PER_SM persistent CTAs (stream-K), which balances the triangle; dynamic shared
-//     memory is sized so that exactly CTAS_PER_SM CTAs fit on an SM (all CTAs resident, evenly spread).
-//   * inside a unit each thread owns R consecutive rows (R accumulators) and slides a register window
-//     of 2R field values: per R distances it issues R*R DFMAs for R/2 LDS.128 of field values and
-//     R/2 broadcast LDS.128 of weights.
-//   * weights c[] and the field window are staged global -> shared with 16-byte cp.async into a double
-//     buffer; each thread's 8R-byte chunk of the window is stored at a stride of 8R+16 bytes, which
-//     makes the per-thread LDS.128 bank-conflict free (consecutive lanes land on distinct 16-byte bank
-//     groups: stride/16 is odd).
-//   * the triangular edge and the first column are handled by zero padding (a padded copy of the field
-//     with zeros in front is made by the prepare kernel; rows/columns are shifted by one so that the operator is
-//     exactly N x N), so the inner loop has no predicates.
-//   * a row tile finished inside one CTA is scaled and written directly; a tile split between CTAs
-//     goes through per-CTA partial slots, and the LAST CTA to arrive (atomic ticket per tile) adds
-//     the slots in CTA order -> bitwise deterministic results, no floating-point atomics.
-//   * one prepare kernel per call generates the weight tables (K1), pads the fields and clears the
-//     tickets; one main kernel does everything else: 2 launches per call.
+// Common machinery (both kernel variants)
+//   * rows and columns are tiled in shifted coordinates i' = i-1, j' = j-1: exactly N x N, lower triangular.
+//   * work unit = TI rows x TD columns (tensor variant) / distances (DFMA variant).  Units are laid out in a 1-D sequence
+//     (alpha, field, [row parity], row tile, pass, chunk) and dealt in contiguous spans, cut at sub-unit granularity, to
+//     a grid of exactly sm_count * CTAS_PER_SM persistent CTAs (stream-K); dynamic shared memory is sized so that
+//     exactly CTAS_PER_SM CTAs fit on an SM (all CTAs resident, evenly spread).
+//   * tables and field chunks are staged global -> shared with 16-byte cp.async into a double buffer.
+//   * the triangular edge is handled by zero padding (tables have zeros for negative distances, the prepare kernel makes
+//     a zero-padded copy of every field), so the inner loops have no predicates.
+//   * a row tile finished inside one CTA is scaled and written directly; a tile split between CTAs goes through per-CTA
+//     partial slots, and the LAST CTA to arrive (atomic ticket per tile) adds the slots in CTA order -> bitwise
+//     deterministic results, no floating-point atomics, no second kernel.
+//   * per call: K0 (per-alpha scalars) -> prepare (K1 weight tables + field padding + tickets) -> history kernel, chained
+//     by programmatic dependent launch.
+//   * epilogue options: right-sided / Riesz-Caputo combination (frx_history_sided), stores into every NVLink peer's copy
+//     of a gathered result array (frx_history_gather).
+//   * 'simpson': two interleaved weight sequences -> two half-size problems (row parity) of two passes each over
+//     decimated tables and fields (see frx_table_block), same N^2/2 FMA as the other rules.
+// Tensor variant MGeo (default): block-Toeplitz formulation on mma.m8n8k4.f64 (DMMA), see MGeo below.
+// DFMA variant Geo (FRX_K2_VARIANT=0/1, kept for comparison): each thread owns R consecutive rows and slides a register
+//   window of 2R field values: per R distances R*R DFMAs for R/2 LDS.128 of field values (chunk stride 8R+16 bytes ->
+//   conflict-free) and R/2 broadcast LDS.128 of weights.
 #include <math.h>
 #include <stdlib.h>
 
