@@ -141,6 +141,9 @@ __host__ __device__ inline int64_t tile_prefix(int64_t I, int n_pass) {  // unit
 
 struct Cursor {
     int64_t prob, I, v, chunks, units;  // v in [0, units), units = n_pass * chunks
+    // decoded once (cursor_at) and then kept up to date incrementally, so the per-unit code has no 64-bit divisions:
+    int64_t a, f, chunk;                // prob = ((a * n_fields + f) * n_sub + q),  v = pass * chunks + chunk
+    int q, pass;
 };
 
 template <class G>
@@ -157,16 +160,35 @@ __device__ inline Cursor cursor_at(const HistParams& p, int64_t u) {
     c.v = w - tile_prefix<G>(I, p.n_pass);
     c.chunks = tile_chunks<G>(I, p.n_tiles, p.NR);
     c.units = c.chunks * p.n_pass;
+    const int64_t pf = c.prob / p.n_sub;
+    c.q = (int)(c.prob - pf * p.n_sub);
+    c.a = pf / p.n_fields;
+    c.f = pf - c.a * p.n_fields;
+    c.pass = (int)(c.v / c.chunks);
+    c.chunk = c.v - c.pass * c.chunks;
     return c;
 }
 
 template <class G>
 __device__ inline void cursor_advance(const HistParams& p, Cursor& c) {
-    if (++c.v == c.units) {
+    ++c.v;
+    if (++c.chunk == c.chunks) {
+        c.chunk = 0;
+        ++c.pass;
+    }
+    if (c.v == c.units) {
         c.v = 0;
+        c.pass = 0;
         if (++c.I == p.n_tiles) {
             c.I = 0;
             ++c.prob;
+            if (++c.q == p.n_sub) {
+                c.q = 0;
+                if (++c.f == p.n_fields) {
+                    c.f = 0;
+                    ++c.a;
+                }
+            }
         }
         c.chunks = tile_chunks<G>(c.I, p.n_tiles, p.NR);
         c.units = c.chunks * p.n_pass;
@@ -187,9 +209,7 @@ __device__ inline void cp_async_wait() {
 // as NU rows of 8, in the table's permuted order) and the column chunk of the padded field (+8 halo).
 template <class G>
 __device__ inline void stage_unit_mma(const HistParams& p, const Cursor& c, char* stage) {
-    const int64_t pass = c.v / c.chunks;
-    const int64_t j0 = (c.v - pass * c.chunks) * G::TD;
-    const int64_t pf = c.prob / p.n_sub, q = c.prob - pf * p.n_sub, a = pf / p.n_fields, f = pf - a * p.n_fields;
+    const int64_t pass = c.pass, j0 = c.chunk * G::TD, q = c.q, a = c.a, f = c.f;
     // row u of the window holds distances 8e..8e+7, e = e_base + u, e_base = p0 - m0 - MC
     const int64_t d_base = c.I * G::TI - j0 - G::TD;
     const double* csrc = p.tabs + ((a * p.n_sub + q) * p.n_pass + pass) * p.ldc + G::C_PAD + d_base;
@@ -250,9 +270,7 @@ __device__ inline void stage_unit(const HistParams& p, const Cursor& c, char* st
         stage_unit_mma<G>(p, c, stage);
         return;
     } else {
-    const int64_t pass = c.v / c.chunks;
-    const int64_t d0 = (c.v - pass * c.chunks) * G::TD;
-    const int64_t pf = c.prob / p.n_sub, q = c.prob - pf * p.n_sub, a = pf / p.n_fields, f = pf - a * p.n_fields;
+    const int64_t pass = c.pass, d0 = c.chunk * G::TD, q = c.q, a = c.a, f = c.f;
     const double* ctab = p.tabs + ((a * p.n_sub + q) * p.n_pass + pass) * p.ldc + d0;
     const double* gsrc = p.gp + (f * p.n_pass + pass) * p.ldgp + G::PADF + c.I * G::TI - d0 - G::TD;
     const int t = threadIdx.x;
