@@ -196,6 +196,38 @@ def toeplitz_apply(approximation, alpha, h, G, N=None, out=None):
     return out
 
 
+def toeplitz_product(c, g, paired=False, scale=1.0, n_cols=0, out=None):
+    """Extension: plain lower-triangular Toeplitz products y[s, f, i] = scale * sum_{j<=i} c[s, i-j] g[., j] (0-based) with
+    caller-supplied sequences on the tensor-core history kernel.  c: cuda float64 [n_seq, N]; g: [n_fields, N]
+    (every sequence with every field -> [n_seq, n_fields, N]) or, paired, [n_seq, n_fields, N] (sequence s with its own
+    fields).  n_cols > 0: g is zero from column n_cols on and only rows >= n_cols are wanted."""
+    if not (torch.is_tensor(c) and c.is_cuda and torch.is_tensor(g) and g.is_cuda):
+        raise TypeError('c and g must be CUDA tensors')
+    c = c.to(torch.float64).contiguous()
+    g = g.to(torch.float64).contiguous()
+    if c.dim() == 1:
+        c = c[None]
+    n_seq, N = c.shape
+    if paired:
+        if g.dim() == 2:
+            g = g[:, None]
+        if g.shape[0] != n_seq or g.shape[-1] != N:
+            raise ValueError('paired: g must be [n_seq, n_fields, N]')
+        n_fields = g.shape[1]
+    else:
+        if g.dim() == 1:
+            g = g[None]
+        if g.shape[-1] != N:
+            raise ValueError('g must be [n_fields, N]')
+        n_fields = g.shape[0]
+    ctx, idx = _ctx_for(c.device)
+    if out is None:
+        out = torch.zeros((n_seq, n_fields, N), dtype=torch.float64, device=c.device)
+    _lib.check(_lib.lib().frx_toeplitz_product(ctx.handle, n_seq, _ptr(c), N, N, n_fields, 1 if paired else 0, _ptr(g), N,
+                                               float(scale), _ptr(out), N, int(n_cols)))
+    return out
+
+
 def _solve_params(alpha, h, res, n_sys=None):
     a = np.ascontiguousarray(np.atleast_1d(np.asarray(alpha, dtype=np.float64)))
     n_sys = len(a) if n_sys is None else n_sys

@@ -44,6 +44,10 @@ namespace {
 
 constexpr int kNT = 128;      // threads per CTA
 constexpr int kLdcQuantum = 256;
+#ifndef FRX_FIXUP_BATCH
+#define FRX_FIXUP_BATCH 2
+#endif
+constexpr int kFixupBatch = FRX_FIXUP_BATCH;   // partial slots loaded together in the split-tile fix-up
 
 template <int R_, int TD_, int CTAS_>
 struct Geo {
@@ -124,6 +128,14 @@ struct HistParams {
     double* peer_y[FRX_MAX_PEERS];
     double* partial;   // [2 * grid][TI]
     int* tickets;      // [n_alpha * n_fields * n_tiles], zero on entry, zero again on exit
+    // plain Toeplitz product with caller-supplied sequences (frx_toeplitz_raw): y_i = raw_scale * S_i, row 0 untouched,
+    // no first-column / multiplier terms.  paired: table a goes with fields [a*n_fields, (a+1)*n_fields) only
+    int raw, paired;
+    double raw_scale;
+    // rectangular restriction (raw products whose field is zero beyond column TD*rect_chunks): only row tiles
+    // I >= rect_I0 are computed, each over the first rect_chunks column chunks; requires (rect_I0+1)*TI/TD >= rect_chunks
+    // (no chunk beyond the tile's diagonal).  rect_chunks = 0: off
+    int64_t rect_I0, rect_chunks;
 };
 
 // Rows and columns are tiled in SHIFTED coordinates i' = i - 1, j' = j - 1 (row 0 is identically 0 and column 0 is
@@ -151,14 +163,21 @@ __device__ inline Cursor cursor_at(const HistParams& p, int64_t u) {
     Cursor c;
     c.prob = u / p.units_per_prob;
     int64_t w = u - c.prob * p.units_per_prob;
-    const double K = (double)p.n_pass * (G::TI / G::TD);
-    int64_t I = (int64_t)((sqrt(1.0 + 8.0 * (double)w / K) - 1.0) * 0.5);
-    if (I > p.n_tiles - 1) I = p.n_tiles - 1;
-    while (I > 0 && tile_prefix<G>(I, p.n_pass) > w) --I;
-    while (I + 1 < p.n_tiles && tile_prefix<G>(I + 1, p.n_pass) <= w) ++I;
-    c.I = I;
-    c.v = w - tile_prefix<G>(I, p.n_pass);
-    c.chunks = tile_chunks<G>(I, p.n_tiles, p.NR);
+    if (p.rect_chunks) {
+        const int64_t per_tile = p.rect_chunks * p.n_pass, t = w / per_tile;
+        c.I = p.rect_I0 + t;
+        c.v = w - t * per_tile;
+        c.chunks = p.rect_chunks;
+    } else {
+        const double K = (double)p.n_pass * (G::TI / G::TD);
+        int64_t I = (int64_t)((sqrt(1.0 + 8.0 * (double)w / K) - 1.0) * 0.5);
+        if (I > p.n_tiles - 1) I = p.n_tiles - 1;
+        while (I > 0 && tile_prefix<G>(I, p.n_pass) > w) --I;
+        while (I + 1 < p.n_tiles && tile_prefix<G>(I + 1, p.n_pass) <= w) ++I;
+        c.I = I;
+        c.v = w - tile_prefix<G>(I, p.n_pass);
+        c.chunks = tile_chunks<G>(I, p.n_tiles, p.NR);
+    }
     c.units = c.chunks * p.n_pass;
     const int64_t pf = c.prob / p.n_sub;
     c.q = (int)(c.prob - pf * p.n_sub);
@@ -180,7 +199,7 @@ __device__ inline void cursor_advance(const HistParams& p, Cursor& c) {
         c.v = 0;
         c.pass = 0;
         if (++c.I == p.n_tiles) {
-            c.I = 0;
+            c.I = p.rect_I0;
             ++c.prob;
             if (++c.q == p.n_sub) {
                 c.q = 0;
@@ -190,7 +209,7 @@ __device__ inline void cursor_advance(const HistParams& p, Cursor& c) {
                 }
             }
         }
-        c.chunks = tile_chunks<G>(c.I, p.n_tiles, p.NR);
+        c.chunks = p.rect_chunks ? p.rect_chunks : tile_chunks<G>(c.I, p.n_tiles, p.NR);
         c.units = c.chunks * p.n_pass;
     }
 }
@@ -213,7 +232,8 @@ __device__ inline void stage_unit_mma(const HistParams& p, const Cursor& c, char
     // row u of the window holds distances 8e..8e+7, e = e_base + u, e_base = p0 - m0 - MC
     const int64_t d_base = c.I * G::TI - j0 - G::TD;
     const double* csrc = p.tabs + ((a * p.n_sub + q) * p.n_pass + pass) * p.ldc + G::C_PAD + d_base;
-    const double* gsrc = p.gp + (f * p.n_pass + pass) * p.ldgp + G::PADF + j0 - 8;
+    const int64_t fg = p.paired ? a * p.n_fields + f : f;
+    const double* gsrc = p.gp + (fg * p.n_pass + pass) * p.ldgp + G::PADF + j0 - 8;
     const int t = threadIdx.x;
 #pragma unroll
     for (int q = t; q < G::NU * 4; q += kNT) cp_async16(stage + (q >> 2) * G::ROW_STRIDE + (q & 3) * 16, csrc + 2 * q);
@@ -272,7 +292,8 @@ __device__ inline void stage_unit(const HistParams& p, const Cursor& c, char* st
     } else {
     const int64_t pass = c.pass, d0 = c.chunk * G::TD, q = c.q, a = c.a, f = c.f;
     const double* ctab = p.tabs + ((a * p.n_sub + q) * p.n_pass + pass) * p.ldc + d0;
-    const double* gsrc = p.gp + (f * p.n_pass + pass) * p.ldgp + G::PADF + c.I * G::TI - d0 - G::TD;
+    const int64_t fg = p.paired ? a * p.n_fields + f : f;
+    const double* gsrc = p.gp + (fg * p.n_pass + pass) * p.ldgp + G::PADF + c.I * G::TI - d0 - G::TD;
     const int t = threadIdx.x;
     for (int q = t; q < G::TD / 2; q += kNT) cp_async16(stage + 16 * q, ctab + 2 * q);
     char* win = stage + G::TD * 8;
@@ -350,9 +371,9 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
     // prob counts sub-problems: ((alpha * n_fields + field) * n_sub + q)
     const int64_t pf = prob / p.n_sub, q = prob - pf * p.n_sub, a = pf / p.n_fields, f = pf - a * p.n_fields;
     prob = pf;   // from here on: the (alpha, field) pair that owns the output row
-    const double* gf = p.g + f * p.ldg;
+    const double* gf = p.g + (p.paired ? a * p.n_fields + f : f) * p.ldg;
     const bool rev = p.side != FRX_SIDE_LEFT;
-    const double g0 = rev ? gf[p.N] : gf[0];
+    const double g0 = p.raw ? 0.0 : (rev ? gf[p.N] : gf[0]);
     const double cm1 = p.rule == FRX_RULE_SIMPSON ? p.cm1[a] : 0.0;
     auto store_row = [&](int64_t i, double v) {   // v: value of row i of the (possibly mirrored) left operator
         if (!rev) {
@@ -378,6 +399,10 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
         const int64_t ip = (I * G::TI + acc_pair_row<G>(r >> 1) + (r & 1)) * p.n_sub + q;   // shifted row i' = i - 1
         const int64_t i = ip + 1;
         if (i > p.N) continue;
+        if (p.raw) {
+            store_row(i, p.raw_scale * acc[r]);
+            continue;
+        }
         if (ip == 0) store_row(0, 0.0);               // row 0 has no stencil: y_0 = 0 by convention
         double v;
         if (i == 1 && (p.rule == FRX_RULE_RECTANGLE || p.rule == FRX_RULE_SIMPSON)) {
@@ -454,10 +479,22 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
                     const double* src = p.partial + (2 * k0 + 1) * G::TI;
 #pragma unroll
                     for (int r = 0; r < R; ++r) acc[r] = __ldcg(src + acc_pair_row<G>(r >> 1) + (r & 1));
-                    for (int64_t kk = k0 + 1; kk <= k1; ++kk) {
-                        src = p.partial + (2 * kk) * G::TI;
+                    // slots are added in CTA order, the loads of kFixupBatch slots in flight together (a small problem can
+                    // split one tile over a hundred CTAs: one L2 round trip per slot would dominate it)
+                    for (int64_t kk = k0 + 1; kk <= k1; kk += kFixupBatch) {
+                        double part[kFixupBatch][R];
 #pragma unroll
-                        for (int r = 0; r < R; ++r) acc[r] += __ldcg(src + acc_pair_row<G>(r >> 1) + (r & 1));
+                        for (int j = 0; j < kFixupBatch; ++j) {
+                            src = p.partial + (2 * (kk + j <= k1 ? kk + j : k1)) * G::TI;
+#pragma unroll
+                            for (int r = 0; r < R; ++r) part[j][r] = __ldcg(src + acc_pair_row<G>(r >> 1) + (r & 1));
+                        }
+#pragma unroll
+                        for (int j = 0; j < kFixupBatch; ++j)
+                            if (kk + j <= k1) {
+#pragma unroll
+                                for (int r = 0; r < R; ++r) acc[r] += part[j][r];
+                            }
                     }
                     finish_rows<G>(p, cur.prob, cur.I, acc);
                 }
@@ -481,12 +518,27 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
                                                        int64_t tab_per_alpha,
                                                        const double* __restrict__ g, int64_t ldg, int n_pass, int64_t n_fp,
                                                        int64_t ldgp, int padf, double* __restrict__ gp, int* __restrict__ tickets,
-                                                       int64_t n_tickets, int reverse) {
+                                                       int64_t n_tickets, int reverse, const double* __restrict__ raw_c,
+                                                       int64_t raw_ldc) {
     __shared__ frx_table_smem S;
     const int64_t bx = blockIdx.x;
+    if (raw_c) frx_grid_dependency_wait();   // caller-supplied sequences may come from the previous kernel in the stream
     frx_grid_launch_dependents();   // the history kernel may be scheduled as this grid drains; it waits before reading
     if (bx < n_tab) {
         const int64_t a = bx / tab_per_alpha;
+        if (raw_c) {   // copy sequence a into the padded (and permuted) table layout
+            const int t = threadIdx.x;
+            if (t < FRX_TAB_HALO || t >= FRX_TAB_THREADS - FRX_TAB_HALO) return;
+            const int64_t X = (bx - a * tab_per_alpha) * FRX_TAB_ENTRIES + (t - FRX_TAB_HALO);
+            if (X >= ldc) return;
+            const int64_t x = X - c_pad;
+            double* cA = tabs + a * ldc;
+            if (x < 0) cA[X] = 0.0;
+            else
+                cA[c_perm ? c_pad + (x & ~(int64_t)7) + ((x & 3) * 2 + ((x >> 2) & 1)) : c_pad + x] =
+                    x < N ? raw_c[a * raw_ldc + x] : 0.0;
+            return;
+        }
         // tables of alpha a: n_tab_per_alpha consecutive tables of ldc entries (1; 'simpson': the 4 decimated ones)
         frx_table_block(S, sc + a, rule, alpha[a], h, N, (bx - a * tab_per_alpha) * FRX_TAB_ENTRIES, c_pad, c_perm, dec,
                         tabs + a * n_tab_per_alpha * ldc, nullptr, ldc, w0 + a * ldw, mult + a * ldw, cm1 + a);
@@ -512,11 +564,22 @@ struct PeerTargets {
     int64_t row0;
     double* y[FRX_MAX_PEERS];
 };
+struct RawSpec {
+    const double* c;   // sequences [n_alpha][ldc], natural order
+    int64_t ldc;
+    double scale;
+    int paired;
+    int64_t n_cols;    // > 0: the fields are zero from column n_cols on and only rows > n_cols are wanted
+};
 
 template <class G>
 int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
-                 int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy, const PeerTargets* peers) {
+                 int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy, const PeerTargets* peers,
+                 const RawSpec* raw = nullptr) {
     HistParams p;
+    p.raw = raw != nullptr;
+    p.paired = raw ? raw->paired : 0;
+    p.raw_scale = raw ? raw->scale : 1.0;
     p.rule = rule;
     p.side = side;
     p.n_peers = peers ? peers->n_peers : 0;
@@ -531,6 +594,15 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     p.n_fields = n_fields;
     p.n_tiles = (p.NR + G::TI - 1) / G::TI;
     p.units_per_prob = tile_prefix<G>(p.n_tiles - 1, p.n_pass) + p.n_pass * tile_chunks<G>(p.n_tiles - 1, p.n_tiles, p.NR);
+    p.rect_I0 = 0;
+    p.rect_chunks = 0;
+    if (raw && raw->n_cols > 0 && raw->n_cols % G::TI == 0 && raw->n_cols < N) {
+        p.rect_I0 = raw->n_cols / G::TI;
+        // + 1: column block m holds the columns j' = 8m + r - s, so the last columns below n_cols also belong to the
+        // first block of the next chunk
+        p.rect_chunks = raw->n_cols / G::TD + 1;
+        p.units_per_prob = (p.n_tiles - p.rect_I0) * p.rect_chunks * p.n_pass;
+    }
     p.total_units = p.units_per_prob * n_alpha * n_fields * p.n_sub;
     // tables are zero beyond the last distance up to the end of the last tile: whole-tile reads stay in bounds and finite
     p.ldc = G::C_PAD + (frx_table_ldc(p.NR) > p.n_tiles * G::TI ? frx_table_ldc(p.NR) : p.n_tiles * G::TI);
@@ -538,7 +610,8 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     p.ldw = (N + 1 + 1) / 2 * 2;
     p.ldgp = G::PADF + p.n_tiles * G::TI;
     int64_t NG = (int64_t)ctx->sm_count * G::CTAS_PER_SM;
-    if (NG > p.total_units * G::SUBS) NG = p.total_units * G::SUBS;
+    // small problems: at least 4 sub-steps per CTA (fewer participants in the split-tile fix-up)
+    if (NG > (p.total_units * G::SUBS + 3) / 4) NG = (p.total_units * G::SUBS + 3) / 4;
     const int64_t n_tickets = n_alpha * n_fields * p.n_sub * p.n_tiles;
 
     // workspace carve-up (all offsets multiples of 256 bytes)
@@ -552,7 +625,8 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     const size_t o_w0 = carve(sizeof(double) * (size_t)n_alpha * p.ldw);
     const size_t o_mult = carve(sizeof(double) * (size_t)n_alpha * p.ldw);
     const size_t o_cm1 = carve(sizeof(double) * (size_t)n_alpha);
-    const size_t o_gp = carve(sizeof(double) * (size_t)n_fields * p.n_pass * p.ldgp);
+    const int64_t n_fields_all = p.paired ? n_alpha * n_fields : n_fields;
+    const size_t o_gp = carve(sizeof(double) * (size_t)n_fields_all * p.n_pass * p.ldgp);
     const size_t o_part = carve(sizeof(double) * (size_t)2 * NG * G::TI);
     const size_t o_tick = carve(sizeof(int) * (size_t)n_tickets);
     const size_t o_scal = carve(frx_alpha_scalars_bytes() * (size_t)n_alpha);
@@ -584,12 +658,14 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
         const int64_t tab_per_alpha = (cover + FRX_TAB_ENTRIES - 1) / FRX_TAB_ENTRIES, n_tab = gl ? 0 : tab_per_alpha * n_alpha;
         if (simpson)   // the four decimated tables are scattered into: padding, tails and T(0,1)[0] must be zero
             FRX_CUDA(cudaMemsetAsync(cA, 0, sizeof(double) * (size_t)n_alpha * n_tabs * p.ldc, ctx->stream));
-        const int64_t n_fp = n_fields * p.n_pass;
+        const int64_t n_fp = n_fields_all * p.n_pass;
         int64_t n_pad = (n_fp * p.ldgp + 8 * kNT - 1) / (8 * kNT);
         if (n_pad > 4096) n_pad = 4096;
         FRX_REQUIRE(n_tab + n_pad < ((int64_t)1 << 31), FRX_ERR_INVALID_ARG, "problem too large for one launch");
-        rc = frx_launch_alpha_scalars(ctx, rule, n_alpha, d_alpha, h, ws + o_scal);
-        if (rc) return rc;
+        if (!raw) {
+            rc = frx_launch_alpha_scalars(ctx, rule, n_alpha, d_alpha, h, ws + o_scal);
+            if (rc) return rc;
+        }
         if (gl) {
             rc = frx_launch_gl_table(ctx, n_alpha, d_alpha, h, N, ws + o_scal, G::C_PAD, G::C_PERM, cA, p.ldc, w0, mult, p.ldw, cm1);
             if (rc) return rc;
@@ -598,7 +674,8 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
                    FRX_CUDA(frx_launch_dependent(frx_k12_prepare, dim3((unsigned)(n_tab + n_pad)), dim3(FRX_TAB_BLOCK), 0,
                                                  ctx->stream, rule, d_alpha, h, N, (const frx_alpha_scalars*)(ws + o_scal), cA, p.ldc, n_tabs, (int)simpson, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
                                                  n_fp, p.ldgp, (int)G::PADF, gp, p.tickets, n_tickets,
-                                                 (int)(side != FRX_SIDE_LEFT))));
+                                                 (int)(side != FRX_SIDE_LEFT), raw ? raw->c : (const double*)nullptr,
+                                                 raw ? raw->ldc : (int64_t)0)));
     }
     // dynamic shared memory: at least the double buffer, padded so that exactly CTAS_PER_SM CTAs fit per SM
     int smem_sm = 0;
@@ -617,7 +694,10 @@ extern "C" int64_t frx_table_ldc(int64_t N) { return (N + 1 + kLdcQuantum - 1) /
 
 static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                             int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy,
-                            const PeerTargets* peers = nullptr) {
+                            const PeerTargets* peers = nullptr, const void* raw_spec = nullptr) {
+    if (raw_spec)
+        return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, nullptr,
+                                             (const RawSpec*)raw_spec);
     // tile geometry: FRX_K2_VARIANT is a tuning/experiment switch, the default is the measured best
     static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 9;
     switch (variant) {
@@ -685,6 +765,32 @@ extern "C" int frx_history_gather(frx_ctx* ctx, int rule, int64_t n_alpha, const
 extern "C" int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                            int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy) {
     return frx_history_sided(ctx, rule, FRX_SIDE_LEFT, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, n_g, d_y, ldy);
+}
+
+// Plain lower-triangular Toeplitz products with caller-supplied sequences on the same kernel (used by frx_history_solve):
+//     y[a][f][i] = scale * sum_{j=1..i} c[a][i-j] * g[.][j],   i = 1..N        (y[..][0] is not written)
+// paired != 0: sequence a is applied to fields a*n_fields .. a*n_fields+n_fields-1 only (y has n_seq*n_fields rows);
+// otherwise every sequence is applied to every field.  n_cols > 0 promises g[.][j] = 0 for j > n_cols and asks for rows
+// i > n_cols only (the rows up to n_cols are left untouched when n_cols is a multiple of the row tile, else computed).
+int frx_toeplitz_raw(frx_ctx* ctx, int64_t n_seq, const double* d_c, int64_t ldc, int64_t N, int64_t n_fields, int paired,
+                     const double* d_g, int64_t ldg, double scale, double* d_y, int64_t ldy, int64_t n_cols) {
+    RawSpec rs{d_c, ldc, scale, paired, n_cols};
+    return history_dispatch(ctx, FRX_RULE_CAPUTO, FRX_SIDE_LEFT, n_seq, nullptr, 0.0, N, n_fields, d_g, ldg, d_y, ldy, nullptr, &rs);
+}
+
+extern "C" int frx_toeplitz_product(frx_ctx* ctx, int64_t n_seq, const double* d_c, int64_t ldc, int64_t N, int64_t n_fields,
+                                    int32_t paired, const double* d_g, int64_t ldg, double scale, double* d_y, int64_t ldy,
+                                    int64_t n_cols) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    FRX_REQUIRE(N >= 1 && N < ((int64_t)1 << 30) && n_cols >= 0, FRX_ERR_INVALID_ARG, "N / n_cols out of range");
+    FRX_REQUIRE(n_seq >= 0 && n_seq <= 65535 && n_fields >= 0 && n_fields <= 32767, FRX_ERR_INVALID_ARG,
+                "n_seq (<= 65535) / n_fields (<= 32767) out of range");
+    FRX_REQUIRE(ldc >= N && ldg >= N && ldy >= N, FRX_ERR_INVALID_ARG, "leading dimension too small");
+    if (n_seq == 0 || n_fields == 0) return FRX_OK;
+    FRX_REQUIRE(d_c && d_g && d_y, FRX_ERR_INVALID_ARG, "NULL buffer");
+    FRX_CUDA(cudaSetDevice(ctx->device));
+    // the kernel's rows and columns are numbered from 1 (node 0 is the first-column term, absent here)
+    return frx_toeplitz_raw(ctx, n_seq, d_c, ldc, N, n_fields, paired, d_g - 1, ldg, scale, d_y - 1, ldy, n_cols);
 }
 
 // K3: one alpha, many fields -- the same tensor-core kernel with the fields as independent problems (the c window

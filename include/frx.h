@@ -150,7 +150,7 @@ int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_al
 /* ---- inverse of the growing-history operator (EXTENSION: the reference has no solver) -------------
  * For every alpha: given f_1..f_N (d_f[a*ldf + i]) and the initial value u0[a], find u with
  *   frx_history(rule, alpha, h, u)[i] = f_i, i = 1..N     (u_0 = u0; rows = Settings(alpha, i*h, i) stencils),
- * by blocked forward substitution on the lower-triangular Toeplitz system (csrc/frx_ode.cu).  One implicit step of a
+ * by Newton iteration for the inverse series on the tensor-core Toeplitz kernel (csrc/frx_ode.cu).  One implicit step of a
  * fractional ODE / Volterra equation; 'caputo' and 'trapezoidal' only.  d_u[a*ldu + i], i = 0..N. */
 int frx_history_solve(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                       const double* d_f, int64_t ldf, const double* d_u0, double* d_u, int64_t ldu);
@@ -163,6 +163,18 @@ int frx_history_solve(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_a
  * Same call pattern as above: row i of T is the reference stencil of Settings(alpha, i*h, i). */
 int frx_toeplitz_apply(frx_ctx* ctx, int rule, double alpha, double h, int64_t N, int64_t n_fields,
                        const double* d_G, int64_t ldg, int64_t n_g, double* d_Y, int64_t ldy);
+
+/* ---- plain lower-triangular Toeplitz products with caller-supplied sequences (extension) --------
+ * y[(s, f)][i] = scale * sum_{j=0..i} c[s*ldc + i-j] * g[.][j],   i = 0..N-1      (0-based: a truncated product of series)
+ * on the same FP64 tensor-core kernel as frx_history -- for weight sequences the four rules do not cover, and the
+ * building block of frx_history_solve.  paired == 0: every sequence s < n_seq is applied to every field f < n_fields
+ * (output row s*n_fields + f, field f); paired != 0: sequence s is applied to fields s*n_fields .. s*n_fields+n_fields-1
+ * (g holds n_seq*n_fields fields).  n_cols > 0 promises g[.][j] == 0 for j >= n_cols and asks for rows i >= n_cols only
+ * (rows below may be left untouched): the rectangular block of the product, as Newton's iteration on series needs it.
+ * No counterpart in the reference. */
+int frx_toeplitz_product(frx_ctx* ctx, int64_t n_seq, const double* d_c, int64_t ldc, int64_t N, int64_t n_fields,
+                         int32_t paired, const double* d_g, int64_t ldg, double scale, double* d_y, int64_t ldy,
+                         int64_t n_cols);
 
 /* ---- K4: assemble + batch-solve small fractional boundary-value systems -------------------------
  * No counterpart in the reference (upstream `fdm` would do it): PARITY UNPINNED, see DESIGN.md section 6.

@@ -345,9 +345,9 @@ def test_beyond_baseline_size_sampled_rows():
 
 
 def test_history_solve_inverts_the_operator():
-    """EXTENSION frx_history_solve: blocked forward substitution on the lower-triangular Toeplitz system, against the
+    """EXTENSION frx_history_solve: Newton iteration for the inverse series on the tensor-core Toeplitz kernel, against the
     oracle's sequential forward substitution with the reference's weights, and as a round trip through K2."""
-    for N in (5, 1000, 1024, 1025, 5000):
+    for N in (5, 1000, 1024, 1025, 2048, 5000, 20000):
         h = 1. / N
         x = np.arange(N + 1) * h
         u_true = np.sin(3 * x) + x * x + 0.5
@@ -357,8 +357,42 @@ def test_history_solve_inverts_the_operator():
             for ai, a in enumerate(alphas):
                 want = clib.history_solve(rule, a, h, f[ai].cpu().numpy(), u_true[0])
                 scale = np.abs(want).max()
-                assert np.abs(u[ai] - want).max() <= 1e-10 * scale, (rule, a, N, np.abs(u[ai] - want).max())
-                assert np.abs(u[ai] - u_true).max() <= 1e-9 * scale                  # round trip
+                # The oracle inverts with glibc-pow tables a right-hand side that K2 produced with correctly rounded ones
+                # (DESIGN.md section 3); the inverse amplifies that table difference ~N^2 (measured 1.5e-10 at N=5000,
+                # 2.3e-9 at N=20000, where the oracle itself is 2.3e-9 away from u_true and the GPU result 3e-12).
+                assert np.abs(u[ai] - want).max() <= 1e-10 * scale * max(1., (N / 5000.) ** 2), (rule, a, N)
+                assert np.abs(u[ai] - u_true).max() <= 1e-10 * scale, (rule, a, N)   # round trip
                 assert u[ai, 0] == u_true[0]
+    # BASELINE size: round trip only (size-independent property)
+    N = 100000
+    h = 1. / N
+    x = np.arange(N + 1) * h
+    u_true = np.sin(3 * x) + x * x + 0.5
+    f = batched.history('caputo', [0.5], h, dev(u_true), N=N)
+    u = batched.history_solve('caputo', [0.5], h, f, u_true[0]).cpu().numpy()
+    assert np.abs(u[0] - u_true).max() <= 1e-10 * np.abs(u_true).max()
     with pytest.raises(ValueError):
         batched.history_solve('simpson', [0.5], 0.1, torch.zeros((1, 12), dtype=torch.float64, device='cuda'), 0.)
+
+
+def test_toeplitz_product_matches_dense():
+    """EXTENSION frx_toeplitz_product: caller-supplied sequences on the history kernel (all-pairs and paired), incl. the
+    rectangular mode (field zero from n_cols on, rows >= n_cols wanted) that the Newton iteration of the solve uses."""
+    from scipy.linalg import toeplitz
+    rng = np.random.default_rng(3)
+    for N, n_cols in ((1, 0), (7, 0), (700, 0), (2048, 0), (2048, 1024), (3000, 1024), (5000, 4096), (5000, 1000)):
+        for n_seq, paired in ((1, False), (3, True), (2, False)):
+            c = rng.standard_normal((n_seq, N)) / (1 + np.arange(N))
+            g = rng.standard_normal((n_seq, 2, N) if paired else (2, N))
+            if n_cols:
+                g[..., n_cols:] = 0.0
+            y = batched.toeplitz_product(dev(c), dev(g), paired=paired, scale=-1.0, n_cols=n_cols).cpu().numpy()
+            assert y.shape == (n_seq, 2, N)
+            for s in range(n_seq):
+                T = np.tril(toeplitz(c[s]))
+                fields = g[s] if paired else g
+                for f in range(2):
+                    ref = -(T @ fields[f])
+                    assert np.abs(y[s, f] - ref)[n_cols:].max() <= 1e-13 * np.abs(ref).max(), (N, n_cols, n_seq, paired)
+    with pytest.raises(ValueError):
+        batched.toeplitz_product(dev(np.ones((2, 8))), dev(np.ones((3, 1, 8))), paired=True)
