@@ -313,8 +313,10 @@ def run_b200(args):
     # ---- e2e: host buffers in, host buffers out, through the public host-buffer API ---------------
     g_np = g_host.numpy()
     if world == 1:
+        y_pinned = batched.pinned_empty((A, 1, N_NODES + 1))      # pinned input AND output: the kernels use them in place
+
         def e2e_step():
-            return batched.history_host(RULE, alphas[b:e], h, g_np, N=N_NODES, device=local_rank)
+            return batched.history_host(RULE, alphas[b:e], h, g_np, N=N_NODES, device=local_rank, out=y_pinned)
         h2d = 8 * (N_NODES + 2) + 8 * A
         d2h = 8 * (N_NODES + 1) * A
     else:
@@ -385,7 +387,7 @@ def run_b200(args):
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic', 'config': dict(workload_config(world, A), gather=gather_mode),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': e2e_s * 1e3, 'api': 'frx_history_host (C ABI, host buffers)' if world == 1 else
+                    'ms_per_step': e2e_s * 1e3, 'api': 'frx_history_host (C ABI, pinned host buffers in and out; the prepare kernel reads the field and the history kernel stores the rows over PCIe in place)' if world == 1 else
                     'fractulus_b200.sweep.history_sweep (host field in on every rank, gathered host result out on rank 0)',
                     'bitwise_equal_to_device_path': same},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,

@@ -269,9 +269,16 @@ def assemble_dense(approximation, alpha, h, res, n, device=None):
     return A
 
 
-def history_host(approximation, alpha, h, g, N=None, device=None):
+def pinned_empty(shape):
+    """Page-locked float64 host array (NumPy view of a pinned torch tensor): frx_history_host reads / writes such
+    buffers in place from the kernels instead of staging them through copies."""
+    return torch.empty(tuple(shape), dtype=torch.float64).pin_memory().numpy()
+
+
+def history_host(approximation, alpha, h, g, N=None, device=None, out=None):
     """Same operator through the host-buffer entry point frx_history_host: NumPy in, NumPy out, the
-    host<->device copies happen inside the call."""
+    host<->device transfers happen inside the call.  `out`: optional C-contiguous float64 array [n_alpha, n_fields, N+1]
+    to receive the result (a pinned one, see pinned_empty, is written directly by the kernel)."""
     rule = _lib.RULES[approximation]
     a_h = np.ascontiguousarray(np.atleast_1d(np.asarray(alpha, dtype=np.float64)))
     g_h = np.ascontiguousarray(g, dtype=np.float64)
@@ -280,7 +287,14 @@ def history_host(approximation, alpha, h, g, N=None, device=None):
     if N is None:
         N = n_g - 1 - (1 if approximation == 'simpson' else 0)
     ctx = _lib.context(device)
-    y = np.empty((len(a_h), n_fields, N + 1), dtype=np.float64)
+    if out is None:
+        y = np.empty((len(a_h), n_fields, N + 1), dtype=np.float64)
+    else:
+        y = out
+        if not (isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous and y.flags.writeable
+                and y.size == len(a_h) * n_fields * (N + 1)):
+            raise ValueError('out must be a writeable C-contiguous float64 array with n_alpha*n_fields*(N+1) elements')
+        y = y.reshape(len(a_h), n_fields, N + 1)
     _lib.check(_lib.lib().frx_history_host(ctx.handle, rule, len(a_h), a_h.ctypes.data_as(_lib.c_double_p), float(h),
                                            int(N), n_fields, g2.ctypes.data_as(_lib.c_double_p), n_g, n_g,
                                            y.ctypes.data_as(_lib.c_double_p), N + 1))

@@ -67,6 +67,7 @@ struct Geo {
     static constexpr int C_PERM = 0;
     static constexpr bool TENSOR = false;
     static_assert(TI % TD == 0, "tile rows must be a multiple of the distance chunk");
+    static_assert(STAGE_BYTES >= TI * 8, "the epilogue stages one tile of rows in a stage buffer");
     static_assert((TD / R) % 2 == 0, "inner loop is unrolled by two blocks");
     static_assert(kNT == FRX_TAB_THREADS && kLdcQuantum % TD == 0, "table padding quantum must cover a chunk");
 };
@@ -98,6 +99,7 @@ struct MGeo {
     static constexpr int C_PERM = 1;
     static constexpr bool TENSOR = true;
     static_assert(TI % TD == 0 && TD % 8 == 0 && MC % T == 0, "bad tile geometry");
+    static_assert(STAGE_BYTES >= TI * 8, "the epilogue stages one tile of rows in a stage buffer");
     static_assert(T == 4, "ROW_STRIDE = 80 is conflict free for T = 4 only");
 };
 
@@ -114,8 +116,9 @@ struct HistParams {
     const double* cm1;
     const double* gp;  // padded fields [n_fields][n_pass][ldgp]
     int64_t ldgp;
-    const double* g;   // original fields
+    const double* g;   // original fields (the kernels after the prepare kernel do not read them: they may be host memory)
     int64_t ldg;
+    const double* g0;  // node 0 (node N of a mirrored field) of every field, copied by the prepare kernel
     double* y;
     int64_t ldy;
     int side;          // FRX_SIDE_LEFT; FRX_SIDE_RIGHT: field read reversed, y[N-i] = -value; FRX_SIDE_RIESZ_CAPUTO: second
@@ -367,13 +370,15 @@ __device__ inline int acc_pair_row(int q) {
 
 // scale, add the first column / right-of-point terms and store the R rows of this thread
 template <class G>
-__device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I, const double (&acc)[G::R]) {
+__device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I, const double (&acc)[G::R], double* srow) {
     // prob counts sub-problems: ((alpha * n_fields + field) * n_sub + q)
     const int64_t pf = prob / p.n_sub, q = prob - pf * p.n_sub, a = pf / p.n_fields, f = pf - a * p.n_fields;
     prob = pf;   // from here on: the (alpha, field) pair that owns the output row
-    const double* gf = p.g + (p.paired ? a * p.n_fields + f : f) * p.ldg;
+    const int64_t fg = p.paired ? a * p.n_fields + f : f;
     const bool rev = p.side != FRX_SIDE_LEFT;
-    const double g0 = p.raw ? 0.0 : (rev ? gf[p.N] : gf[0]);
+    const double g0 = p.raw ? 0.0 : p.g0[fg];
+    // 'simpson', odd row i: node i+1 = shifted column j' = i (odd: pass 1, slot (i-1)/2 of the padded copy)
+    const double* g_odd = p.gp + (fg * p.n_pass + 1) * p.ldgp + G::PADF;
     const double cm1 = p.rule == FRX_RULE_SIMPSON ? p.cm1[a] : 0.0;
     auto store_row = [&](int64_t i, double v) {   // v: value of row i of the (possibly mirrored) left operator
         if (!rev) {
@@ -394,13 +399,19 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
             }
         }
     };
+    // the accumulators go through shared memory (the stage buffer that was just consumed) so that consecutive threads
+    // finish consecutive rows: coalesced loads of w0 / mult and full-line stores of y, which matters when y is a
+    // peer's or the host's memory
 #pragma unroll
-    for (int r = 0; r < G::R; ++r) {
-        const int64_t ip = (I * G::TI + acc_pair_row<G>(r >> 1) + (r & 1)) * p.n_sub + q;   // shifted row i' = i - 1
+    for (int r = 0; r < G::R; ++r) srow[acc_pair_row<G>(r >> 1) + (r & 1)] = acc[r];
+    __syncthreads();
+    for (int local = threadIdx.x; local < G::TI; local += kNT) {
+        const int64_t ip = (I * G::TI + local) * p.n_sub + q;   // shifted row i' = i - 1
         const int64_t i = ip + 1;
-        if (i > p.N) continue;
+        if (i > p.N) break;
+        const double sum = srow[local];
         if (p.raw) {
-            store_row(i, p.raw_scale * acc[r]);
+            store_row(i, p.raw_scale * sum);
             continue;
         }
         if (ip == 0) store_row(0, 0.0);               // row 0 has no stencil: y_0 = 0 by convention
@@ -408,12 +419,13 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
         if (i == 1 && (p.rule == FRX_RULE_RECTANGLE || p.rule == FRX_RULE_SIMPSON)) {
             v = nan("");  // the reference cannot build this stencil
         } else {
-            double s = fma(p.w0[a * p.ldw + i], g0, acc[r]);
-            if (p.rule == FRX_RULE_SIMPSON && (i & 1)) s = fma(cm1, gf[i + 1], s);
+            double s = fma(p.w0[a * p.ldw + i], g0, sum);
+            if (p.rule == FRX_RULE_SIMPSON && (i & 1)) s = fma(cm1, g_odd[(i - 1) >> 1], s);
             v = p.mult[a * p.ldw + i] * s;
         }
         store_row(i, v);
     }
+    __syncthreads();   // the buffer is the target of the next prefetch
 }
 
 // CTA that owns unit u when `total` units are dealt to `G` CTAs as [k*total/G, (k+1)*total/G)
@@ -455,7 +467,7 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
         const bool tile_done = (cur.v + 1 == cur.units && s1 == G::SUBS), span_done = (u + 1 == uend);
         if (tile_done || span_done) {
             if (tile_done && from_start) {
-                finish_rows<G>(p, cur.prob, cur.I, acc);
+                finish_rows<G>(p, cur.prob, cur.I, acc, reinterpret_cast<double*>(stage));
             } else {
                 // tile shared with other CTAs.  Slot 2k: continuation of a tile begun by an earlier CTA;
                 // slot 2k+1: tile begun here but not finished here.
@@ -496,7 +508,7 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
                                 for (int r = 0; r < R; ++r) acc[r] += part[j][r];
                             }
                     }
-                    finish_rows<G>(p, cur.prob, cur.I, acc);
+                    finish_rows<G>(p, cur.prob, cur.I, acc, reinterpret_cast<double*>(stage));
                 }
             }
 #pragma unroll
@@ -519,7 +531,7 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
                                                        const double* __restrict__ g, int64_t ldg, int n_pass, int64_t n_fp,
                                                        int64_t ldgp, int padf, double* __restrict__ gp, int* __restrict__ tickets,
                                                        int64_t n_tickets, int reverse, const double* __restrict__ raw_c,
-                                                       int64_t raw_ldc) {
+                                                       int64_t raw_ldc, double* __restrict__ g0) {
     __shared__ frx_table_smem S;
     const int64_t bx = blockIdx.x;
     if (raw_c) frx_grid_dependency_wait();   // caller-supplied sequences may come from the previous kernel in the stream
@@ -552,9 +564,11 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
         double v = 0.0;
         // slot padf + j' holds column j = j' + 1 (shifted coordinates, see tile_chunks); 'simpson' (n_pass = 2): pass e
         // holds every second column, slot padf + k <-> j' = 2k + e
+        // ('simpson' also keeps node N+1, column j' = N: no row reaches it, the epilogue of the last odd row reads it)
         const int64_t jj = (n_pass == 1 ? j : 2 * j + pass) + 1;
-        if (j >= 0 && jj <= N) v = g[f * ldg + (reverse ? N - jj : jj)];
+        if (j >= 0 && jj <= N + (n_pass == 2 ? 1 : 0)) v = g[f * ldg + (reverse ? N - jj : jj)];
         gp[e] = v;
+        if (j == 0 && pass == 0 && !raw_c) g0[f] = g[f * ldg + (reverse ? N : 0)];
     }
     for (int64_t e = pb * blockDim.x + threadIdx.x; e < n_tickets; e += stride) tickets[e] = 0;
 }
@@ -630,6 +644,7 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     const size_t o_part = carve(sizeof(double) * (size_t)2 * NG * G::TI);
     const size_t o_tick = carve(sizeof(int) * (size_t)n_tickets);
     const size_t o_scal = carve(frx_alpha_scalars_bytes() * (size_t)n_alpha);
+    const size_t o_g0 = carve(sizeof(double) * (size_t)n_fields_all);
     int rc = frx_ws_reserve(ctx, off);
     if (rc) return rc;
     char* ws = (char*)ctx->ws;
@@ -645,6 +660,7 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     p.gp = gp;
     p.g = d_g;
     p.ldg = ldg;
+    p.g0 = (const double*)(ws + o_g0);
     p.y = d_y;
     p.ldy = ldy;
     p.sc = (const frx_alpha_scalars*)(ws + o_scal);
@@ -675,7 +691,7 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
                                                  ctx->stream, rule, d_alpha, h, N, (const frx_alpha_scalars*)(ws + o_scal), cA, p.ldc, n_tabs, (int)simpson, w0, mult, p.ldw, cm1, G::C_PAD, G::C_PERM, n_tab, tab_per_alpha, d_g, ldg, p.n_pass,
                                                  n_fp, p.ldgp, (int)G::PADF, gp, p.tickets, n_tickets,
                                                  (int)(side != FRX_SIDE_LEFT), raw ? raw->c : (const double*)nullptr,
-                                                 raw ? raw->ldc : (int64_t)0)));
+                                                 raw ? raw->ldc : (int64_t)0, (double*)(ws + o_g0))));
     }
     // dynamic shared memory: at least the double buffer, padded so that exactly CTAS_PER_SM CTAs fit per SM
     int smem_sm = 0;
@@ -805,6 +821,19 @@ extern "C" int frx_toeplitz_apply(frx_ctx* ctx, int rule, double alpha, double h
     return frx_history(ctx, rule, 1, (const double*)ctx->scalars, h, N, n_fields, d_G, ldg, n_g, d_Y, ldy);
 }
 
+// Host-buffer entry point.  Pinned (page-locked, device-mapped) host buffers are used in place: the prepare kernel
+// reads the field straight from host memory while its other CTAs build the weight tables, and the history kernel's
+// epilogue stores every finished row straight into the host result as the tiles complete, so neither transfer is a
+// separate step on the critical path.  Pageable buffers go through copies to a context-owned device buffer.
+static const void* mapped_device_pointer(const void* h) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_alpha, double h, int64_t N,
                                 int64_t n_fields, const double* h_g, int64_t ldg, int64_t n_g, double* h_y, int64_t ldy) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
@@ -817,22 +846,27 @@ extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const d
     if (n_alpha == 0 || n_fields == 0) return FRX_OK;
     FRX_REQUIRE(ldg >= n_g && ldy >= N + 1, FRX_ERR_INVALID_ARG, "leading dimension too small");
     FRX_CUDA(cudaSetDevice(ctx->device));
+    // FRX_HOST_ZERO_COPY: bit 0 = read the field in place, bit 1 = store the result in place
+    static const int zero_copy = getenv("FRX_HOST_ZERO_COPY") ? atoi(getenv("FRX_HOST_ZERO_COPY")) : 3;
+    const double* map_g = (zero_copy & 1) ? (const double*)mapped_device_pointer(h_g) : nullptr;
+    double* map_y = (zero_copy & 2) ? (double*)mapped_device_pointer(h_y) : nullptr;
     // caller-facing device buffers: a grow-only allocation owned by the context (separate from the
     // workspace, which frx_history re-carves)
     const size_t b_alpha = frx_align_up(sizeof(double) * n_alpha, 256);
-    const size_t b_g = frx_align_up(sizeof(double) * (size_t)n_fields * ldg, 256);
+    const size_t b_g = map_g ? 0 : frx_align_up(sizeof(double) * (size_t)n_fields * ldg, 256);
     const size_t b_y = sizeof(double) * (size_t)n_alpha * n_fields * ldy;
-    int rc = frx_io_reserve(ctx, b_alpha + b_g + b_y);
+    int rc = frx_io_reserve(ctx, b_alpha + b_g + (map_y ? 0 : b_y));
     if (rc) return rc;
     char* io = (char*)ctx->io;
     double* d_alpha = (double*)io;
-    double* d_g = (double*)(io + b_alpha);
-    double* d_y = (double*)(io + b_alpha + b_g);
+    const double* d_g = map_g ? map_g : (const double*)(io + b_alpha);
+    double* d_y = map_y ? map_y : (double*)(io + b_alpha + b_g);
     FRX_CUDA(cudaMemcpyAsync(d_alpha, h_alpha, sizeof(double) * n_alpha, cudaMemcpyHostToDevice, ctx->stream));
-    FRX_CUDA(cudaMemcpyAsync(d_g, h_g, sizeof(double) * (size_t)n_fields * ldg, cudaMemcpyHostToDevice, ctx->stream));
+    if (!map_g)
+        FRX_CUDA(cudaMemcpyAsync(io + b_alpha, h_g, sizeof(double) * (size_t)n_fields * ldg, cudaMemcpyHostToDevice, ctx->stream));
     rc = frx_history(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, n_g, d_y, ldy);
     if (rc) return rc;
-    FRX_CUDA(cudaMemcpyAsync(h_y, d_y, b_y, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!map_y) FRX_CUDA(cudaMemcpyAsync(h_y, d_y, b_y, cudaMemcpyDeviceToHost, ctx->stream));
     FRX_CUDA(cudaStreamSynchronize(ctx->stream));
     return FRX_OK;
 }

@@ -177,8 +177,19 @@ def test_history_host_entry_point_equals_device_entry_point():
     g = np.array(smooth_field(N + 2, h))
     for rule in RULES:
         a = batched.history(rule, [0.3, 0.6], h, dev(g), N=N).cpu().numpy()
-        b = batched.history_host(rule, [0.3, 0.6], h, g, N=N)
+        b = batched.history_host(rule, [0.3, 0.6], h, g, N=N)                       # pageable buffers: staged copies
         assert np.array_equal(a, b, equal_nan=True)
+        # pinned buffers are used in place by the kernels (field read and result rows stored over PCIe)
+        g_pin = batched.pinned_empty(g.shape)
+        g_pin[:] = g
+        out = batched.pinned_empty((2, 1, N + 1))
+        out[:] = -7.0
+        c = batched.history_host(rule, [0.3, 0.6], h, g_pin, N=N, out=out)
+        assert np.shares_memory(c, out) and np.array_equal(a, c, equal_nan=True)
+        d = batched.history_host(rule, [0.3, 0.6], h, g_pin, N=N)                   # pinned in, pageable out
+        assert np.array_equal(a, d, equal_nan=True)
+    with pytest.raises(ValueError):
+        batched.history_host('caputo', [0.3], h, g, N=N, out=np.empty(5))
 
 
 def test_full_size_properties_cfg2():
