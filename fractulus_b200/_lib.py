@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_build', 'libfrx_b200.so')
+# FRX_B200_LIB: alternative build of the same library (tuning aids such as tools/build_trace_lib.sh)
+LIB_PATH = os.environ.get('FRX_B200_LIB') or os.path.join(_HERE, '_build', 'libfrx_b200.so')
 
 FRX_OK = 0
 RULES = {'caputo': 0, 'rectangle': 1, 'trapezoidal': 2, 'simpson': 3,   # reference equation.py:179-184

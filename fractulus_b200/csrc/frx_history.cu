@@ -94,7 +94,7 @@ struct MGeo {
     static constexpr int ROW_STRIDE = 80;        // 64 B of data + 16 B: LDS.128 of 8 lanes x (k, k+1) conflict free for T = 4
     static constexpr int CWIN_BYTES = NU * ROW_STRIDE;
     static constexpr int GCH_ELEMS = TD + 8;     // 8-element halo in front (B fragments reach back 7)
-    static constexpr int STAGE_BYTES = (CWIN_BYTES + GCH_ELEMS * 8 + 127) / 128 * 128;
+    static constexpr int STAGE_BYTES = (CWIN_BYTES + GCH_ELEMS * 8 + 64 + 127) / 128 * 128;   // + 64: see compute_unit_mma
     static constexpr int C_PAD = PADF;
     static constexpr int C_PERM = 1;
     static constexpr bool TENSOR = true;
@@ -250,7 +250,9 @@ __device__ inline void dmma884(double& d0, double& d1, double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-// tensor variant: acc[2t], acc[2t+1] = D fragment of tile t (rows 8(P0w + t + T k) + 2 s' + {0,1})
+// tensor variant: acc[2t], acc[2t+1] = D fragment of tile t (rows 8(P0w + t + T k) + 2 s' + {0,1}).
+// The operands of column block mi+1 are loaded before the DMMAs of block mi are issued (register double buffer), so no
+// load sits between a warp and its next DMMA -- matters when few warps share the tensor pipe (tails of the launch).
 template <class G>
 __device__ inline void compute_unit_mma(double (&acc)[G::R], const char* stage, int s0, int s1) {
     constexpr int T = G::T;
@@ -263,14 +265,22 @@ __device__ inline void compute_unit_mma(double (&acc)[G::R], const char* stage, 
     double2 af[T];
 #pragma unroll
     for (int t = 1; t < T; ++t) af[t] = *reinterpret_cast<const double2*>(arow + (t - s0 * T) * G::ROW_STRIDE);
+    // operands of the first block
+    double2 a_nxt = *reinterpret_cast<const double2*>(arow - (s0 * T) * G::ROW_STRIDE);
+    double b1_nxt = gch[8 * s0 * T], b0_nxt = gch[8 * s0 * T + 4];
 #pragma unroll 1
     for (int mg = s0 * T; mg < s1 * T; mg += T) {
 #pragma unroll
         for (int j = 0; j < T; ++j) {
             const int mi = mg + j;
             // tile t uses slot (t - mi) mod T; the new fragment (tile 0) replaces the one tile T-1 used last time
-            af[(T - j) % T] = *reinterpret_cast<const double2*>(arow - mi * G::ROW_STRIDE);
-            const double b1 = gch[8 * mi], b0 = gch[8 * mi + 4];
+            af[(T - j) % T] = a_nxt;
+            const double b1 = b1_nxt, b0 = b0_nxt;
+            // next block (one past the unit's last block reads valid but unused shared memory: the window row below
+            // and the 64 bytes of padding behind the field chunk)
+            a_nxt = *reinterpret_cast<const double2*>(arow - (mi + 1) * G::ROW_STRIDE);
+            b1_nxt = gch[8 * (mi + 1)];
+            b0_nxt = gch[8 * (mi + 1) + 4];
 #pragma unroll
             for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].x, b0);
 #pragma unroll
@@ -431,6 +441,19 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
 // CTA that owns unit u when `total` units are dealt to `G` CTAs as [k*total/G, (k+1)*total/G)
 __device__ inline int64_t span_owner(int64_t u, int64_t total, int64_t G) { return ((u + 1) * G - 1) / total; }
 
+#ifdef FRX_K2_TRACE
+// tuning aid (not in production builds): per-CTA timestamps of the phases of the history kernel
+__device__ unsigned long long frx_k2_trace[1024 * 8];
+__device__ inline unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define FRX_TRACE(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) frx_k2_trace[blockIdx.x * 8 + (slot)] = trace_now(); } while (0)
+#else
+#define FRX_TRACE(slot) do { } while (0)
+#endif
+
 template <class G>
 __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const HistParams p) {
     extern __shared__ __align__(128) char smem[];
@@ -442,9 +465,15 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
     const int64_t total_groups = p.total_units * G::SUBS;
     const int64_t gbeg = k * total_groups / NG, gend = (k + 1) * total_groups / NG;
     if (gbeg >= gend) return;
+    FRX_TRACE(0);
+#ifdef FRX_K2_TRACE
+    long long trace_compute = 0, trace_groups = 0;
+    const long long trace_c0 = clock64();
+#endif
     const int64_t ubeg = gbeg / G::SUBS, uend = (gend + G::SUBS - 1) / G::SUBS;
     Cursor cur = cursor_at<G>(p, ubeg), nxt = cur;
     frx_grid_dependency_wait();   // tables / padded fields / tickets come from the prepare kernel
+    FRX_TRACE(1);
     double acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
@@ -460,10 +489,24 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
+#ifdef FRX_K2_TRACE
+        if (u == ubeg) FRX_TRACE(2);
+        if (u + 1 == uend) FRX_TRACE(3);
+#endif
         const int s0 = u == ubeg ? (int)(gbeg - ubeg * G::SUBS) : 0;
         const int s1 = u + 1 == uend ? (int)(gend - u * G::SUBS) : G::SUBS;
+#ifdef FRX_K2_TRACE
+        const long long tc0 = clock64();
+#endif
         compute_unit<G>(acc, stage, s0, s1);
+#ifdef FRX_K2_TRACE
+        trace_compute += clock64() - tc0;
+        trace_groups += s1 - s0;
+#endif
         __syncthreads();
+#ifdef FRX_K2_TRACE
+        if (u + 1 == uend) FRX_TRACE(4);
+#endif
         const bool tile_done = (cur.v + 1 == cur.units && s1 == G::SUBS), span_done = (u + 1 == uend);
         if (tile_done || span_done) {
             if (tile_done && from_start) {
@@ -517,6 +560,15 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
         }
         cur = nxt;
     }
+#ifdef FRX_K2_TRACE
+    FRX_TRACE(5);
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        frx_k2_trace[blockIdx.x * 8 + 6] = smid | ((unsigned long long)trace_groups << 32);
+        frx_k2_trace[blockIdx.x * 8 + 7] = (unsigned long long)trace_compute | ((unsigned long long)(clock64() - trace_c0) << 32);
+    }
+#endif
 }
 
 // prepare kernel: blocks [0, n_tab) generate the weight tables (K1); the remaining blocks build the padded
@@ -722,6 +774,8 @@ static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, c
         case 4: return history_impl<MGeo<4, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 5: return history_impl<MGeo<4, 1024, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 6: return history_impl<MGeo<4, 512, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        case 7: return history_impl<MGeo<4, 512, 2>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        case 8: return history_impl<MGeo<4, 512, 1>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         default: return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
     }
 }
@@ -870,3 +924,9 @@ extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const d
     FRX_CUDA(cudaStreamSynchronize(ctx->stream));
     return FRX_OK;
 }
+
+#ifdef FRX_K2_TRACE
+extern "C" int frx_debug_k2_trace(unsigned long long* h_out /*[1024*8]*/) {
+    return cudaMemcpyFromSymbol(h_out, frx_k2_trace, sizeof(unsigned long long) * 1024 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
