@@ -23,7 +23,8 @@
 //     of a gathered result array (frx_history_gather).
 //   * 'simpson': two interleaved weight sequences -> two half-size problems (row parity) of two passes each over
 //     decimated tables and fields (see frx_table_block), same N^2/2 FMA as the other rules.
-// Tensor variant MGeo (default): block-Toeplitz formulation on mma.m8n8k4.f64 (DMMA), see MGeo below.
+// Tensor variant MGeo (default MGeo<4,1024,2>: units of 1024 rows x 1024 columns, 2 CTAs of 4 warps per SM): block-Toeplitz
+//   formulation on mma.m8n8k4.f64 (DMMA), see MGeo below.
 // DFMA variant Geo (FRX_K2_VARIANT=0/1, kept for comparison): each thread owns R consecutive rows and slides a register
 //   window of 2R field values: per R distances R*R DFMAs for R/2 LDS.128 of field values (chunk stride 8R+16 bytes ->
 //   conflict-free) and R/2 broadcast LDS.128 of weights.
@@ -764,10 +765,10 @@ static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, c
                             int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy,
                             const PeerTargets* peers = nullptr, const void* raw_spec = nullptr) {
     if (raw_spec)
-        return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, nullptr,
-                                             (const RawSpec*)raw_spec);
+        return history_impl<MGeo<4, 1024, 2>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, nullptr,
+                                              (const RawSpec*)raw_spec);
     // tile geometry: FRX_K2_VARIANT is a tuning/experiment switch, the default is the measured best
-    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 9;
+    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 10;
     switch (variant) {
         case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
@@ -776,7 +777,8 @@ static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, c
         case 6: return history_impl<MGeo<4, 512, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 7: return history_impl<MGeo<4, 512, 2>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 8: return history_impl<MGeo<4, 512, 1>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
-        default: return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        case 9: return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        default: return history_impl<MGeo<4, 1024, 2>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
     }
 }
 
