@@ -45,10 +45,15 @@ namespace {
 
 constexpr int kNT = 128;      // threads per CTA
 constexpr int kLdcQuantum = 256;
+// partial slots loaded together in the split-tile fix-up: as many as the register budget of the geometry allows (with
+// 4 CTAs per SM, i.e. 128 registers, more than 2 costs the main loop its schedule)
 #ifndef FRX_FIXUP_BATCH
-#define FRX_FIXUP_BATCH 2
+#define FRX_FIXUP_BATCH 8
 #endif
-constexpr int kFixupBatch = FRX_FIXUP_BATCH;   // partial slots loaded together in the split-tile fix-up
+template <class G>
+struct FixupBatch {
+    static constexpr int value = G::CTAS_PER_SM <= 2 ? FRX_FIXUP_BATCH : 2;
+};
 
 template <int R_, int TD_, int CTAS_>
 struct Geo {
@@ -67,6 +72,7 @@ struct Geo {
     static constexpr int C_PAD = 0;              // c tables: natural order, no front padding
     static constexpr int C_PERM = 0;
     static constexpr bool TENSOR = false;
+    static constexpr int WBUF_BYTES = 0;         // no epilogue-operand prefetch
     static_assert(TI % TD == 0, "tile rows must be a multiple of the distance chunk");
     static_assert(STAGE_BYTES >= TI * 8, "the epilogue stages one tile of rows in a stage buffer");
     static_assert((TD / R) % 2 == 0, "inner loop is unrolled by two blocks");
@@ -99,6 +105,9 @@ struct MGeo {
     static constexpr int C_PAD = PADF;
     static constexpr int C_PERM = 1;
     static constexpr bool TENSOR = true;
+    // epilogue operands (w0 and mult of the tile's rows) are prefetched into shared memory together with the unit that
+    // ends a tile or a span, one buffer per stage, when the shared-memory budget allows (<= 2 CTAs per SM)
+    static constexpr int WBUF_BYTES = CTAS_ <= 2 ? 2 * TI * 8 : 0;
     static_assert(TI % TD == 0 && TD % 8 == 0 && MC % T == 0, "bad tile geometry");
     static_assert(STAGE_BYTES >= TI * 8, "the epilogue stages one tile of rows in a stage buffer");
     static_assert(T == 4, "ROW_STRIDE = 80 is conflict free for T = 4 only");
@@ -221,6 +230,21 @@ __device__ inline void cursor_advance(const HistParams& p, Cursor& c) {
 __device__ inline void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ inline void cp_async8(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+// w0[i], mult[i] of the rows i = I*TI + local + 1 of tile c.I -> wbuf[local], wbuf[TI + local]
+template <class G>
+__device__ inline void stage_epilogue_operands(const HistParams& p, const Cursor& c, double* wbuf) {
+    const double* w0 = p.w0 + c.a * p.ldw + c.I * G::TI + 1;
+    const double* mu = p.mult + c.a * p.ldw + c.I * G::TI + 1;
+    const int64_t left = p.N - c.I * G::TI;   // rows of this tile that exist
+    for (int local = threadIdx.x; local < G::TI && local < left; local += kNT) {
+        cp_async8(wbuf + local, w0 + local);
+        cp_async8(wbuf + G::TI + local, mu + local);
+    }
 }
 __device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -381,7 +405,8 @@ __device__ inline int acc_pair_row(int q) {
 
 // scale, add the first column / right-of-point terms and store the R rows of this thread
 template <class G>
-__device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I, const double (&acc)[G::R], double* srow) {
+__device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I, const double (&acc)[G::R], double* srow,
+                                   const double* wsm) {
     // prob counts sub-problems: ((alpha * n_fields + field) * n_sub + q)
     const int64_t pf = prob / p.n_sub, q = prob - pf * p.n_sub, a = pf / p.n_fields, f = pf - a * p.n_fields;
     prob = pf;   // from here on: the (alpha, field) pair that owns the output row
@@ -430,9 +455,10 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
         if (i == 1 && (p.rule == FRX_RULE_RECTANGLE || p.rule == FRX_RULE_SIMPSON)) {
             v = nan("");  // the reference cannot build this stencil
         } else {
-            double s = fma(p.w0[a * p.ldw + i], g0, sum);
+            // wsm: this tile's w0 / mult rows, prefetched into shared memory with the unit (n_sub == 1 only)
+            double s = fma(wsm ? wsm[local] : p.w0[a * p.ldw + i], g0, sum);
             if (p.rule == FRX_RULE_SIMPSON && (i & 1)) s = fma(cm1, g_odd[(i - 1) >> 1], s);
-            v = p.mult[a * p.ldw + i] * s;
+            v = (wsm ? wsm[G::TI + local] : p.mult[a * p.ldw + i]) * s;
         }
         store_row(i, v);
     }
@@ -479,13 +505,18 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
     bool from_start = (cur.v == 0 && gbeg == ubeg * G::SUBS);
+    const bool wpref = G::WBUF_BYTES > 0 && !p.raw && p.n_sub == 1;
+    double* const wbufs = reinterpret_cast<double*>(smem + 2 * G::STAGE_BYTES);
     stage_unit<G>(p, cur, smem);
+    if (wpref && (cur.v + 1 == cur.units || ubeg + 1 == uend)) stage_epilogue_operands<G>(p, cur, wbufs);
     cp_async_commit();
     for (int64_t u = ubeg; u < uend; ++u) {
         char* stage = smem + ((u - ubeg) & 1) * G::STAGE_BYTES;
         if (u + 1 < uend) {
             cursor_advance<G>(p, nxt);
             stage_unit<G>(p, nxt, smem + ((u + 1 - ubeg) & 1) * G::STAGE_BYTES);
+            if (wpref && (nxt.v + 1 == nxt.units || u + 2 == uend))
+                stage_epilogue_operands<G>(p, nxt, wbufs + ((u + 1 - ubeg) & 1) * (G::WBUF_BYTES / 8));
         }
         cp_async_commit();
         cp_async_wait<1>();
@@ -511,7 +542,8 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
         const bool tile_done = (cur.v + 1 == cur.units && s1 == G::SUBS), span_done = (u + 1 == uend);
         if (tile_done || span_done) {
             if (tile_done && from_start) {
-                finish_rows<G>(p, cur.prob, cur.I, acc, reinterpret_cast<double*>(stage));
+                finish_rows<G>(p, cur.prob, cur.I, acc, reinterpret_cast<double*>(stage),
+                            wpref ? wbufs + ((u - ubeg) & 1) * (G::WBUF_BYTES / 8) : nullptr);
             } else {
                 // tile shared with other CTAs.  Slot 2k: continuation of a tile begun by an earlier CTA;
                 // slot 2k+1: tile begun here but not finished here.
@@ -537,6 +569,7 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
                     for (int r = 0; r < R; ++r) acc[r] = __ldcg(src + acc_pair_row<G>(r >> 1) + (r & 1));
                     // slots are added in CTA order, the loads of kFixupBatch slots in flight together (a small problem can
                     // split one tile over a hundred CTAs: one L2 round trip per slot would dominate it)
+                    constexpr int kFixupBatch = FixupBatch<G>::value;
                     for (int64_t kk = k0 + 1; kk <= k1; kk += kFixupBatch) {
                         double part[kFixupBatch][R];
 #pragma unroll
@@ -552,7 +585,8 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
                                 for (int r = 0; r < R; ++r) acc[r] += part[j][r];
                             }
                     }
-                    finish_rows<G>(p, cur.prob, cur.I, acc, reinterpret_cast<double*>(stage));
+                    finish_rows<G>(p, cur.prob, cur.I, acc, reinterpret_cast<double*>(stage),
+                            wpref ? wbufs + ((u - ubeg) & 1) * (G::WBUF_BYTES / 8) : nullptr);
                 }
             }
 #pragma unroll
@@ -750,7 +784,7 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     int smem_sm = 0;
     FRX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
     int dyn = (smem_sm / G::CTAS_PER_SM - 1024 - 64) / 128 * 128;
-    if (dyn < 2 * G::STAGE_BYTES) dyn = 2 * G::STAGE_BYTES;
+    if (dyn < 2 * G::STAGE_BYTES + 2 * G::WBUF_BYTES) dyn = 2 * G::STAGE_BYTES + 2 * G::WBUF_BYTES;
     FRX_CUDA(cudaFuncSetAttribute(frx_k2_history_main<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     FRX_LAUNCH(ctx, FRX_K_HISTORY_MAIN,
                FRX_CUDA(frx_launch_dependent(frx_k2_history_main<G>, dim3((unsigned)NG), dim3(kNT), (size_t)dyn, ctx->stream, p)));

@@ -35,3 +35,11 @@ print('thread-0 cycles inside compute_unit per group (4 column blocks = 32 DMMA 
 per_sm_exit = np.array([t[sm == s, 5].max() for s in np.unique(sm)])
 print('SMs used', len(np.unique(sm)), 'CTAs per SM min/max', np.bincount(sm).min(), np.bincount(sm).max(),
       'per-SM last exit spread: min %.2f max %.2f us' % ((per_sm_exit.min() - t0) / 1e3, (per_sm_exit.max() - t0) / 1e3))
+order = np.argsort(-t[:, 5])[:12]
+print('latest CTAs (blockIdx, smid, first-unit, last-compute, exit us, groups, cycles/group):')
+for k in order:
+    print('  %4d %4d %8.2f %8.2f %8.2f %6d %6.0f' % (k, sm[k], (t[k, 2] - t0) / 1e3, (t[k, 4] - t0) / 1e3, (t[k, 5] - t0) / 1e3, groups[k], comp[k] / max(groups[k], 1)))
+cpg = comp / np.maximum(groups, 1)
+print('cycles/group by blockIdx decile:', [round(float(np.median(cpg[i::10])), 0) for i in range(1)], 'min %.0f max %.0f' % (cpg.min(), cpg.max()))
+late_sm = np.unique(sm[order])
+print('SMs of the latest CTAs:', late_sm.tolist())
