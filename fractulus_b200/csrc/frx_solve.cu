@@ -195,12 +195,19 @@ __global__ void __launch_bounds__(kSolveThreads) frx_k4_assemble_solve(const Sol
 // Retired U rows (2nb+1 entries) and the transformed right-hand side stream to a per-warp scratch in global memory
 // (L2) and are read back, prefetched four rows ahead, by the back substitution.  Needs nb <= 31.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kStreamWarps = 1;   // one-warp CTAs: shared memory (19 KB per system) is the occupancy limit, small CTAs pack it best
+// Shared memory per system is the occupancy limit (19 KB at the widest band -> 11 warps per SM), and the kernel is
+// latency bound, so the host sorts the systems of a batch into bins by band width and launches one grid per bin with
+// the window sized for that bin: narrow bands run with up to 32 one-warp CTAs per SM.
+constexpr int kStreamWarps = 1;   // one-warp CTAs pack shared memory best
 constexpr int kStreamMaxNb = 31;
-constexpr int kStreamC = 2 * kStreamMaxNb + 1;
 constexpr int kStreamMaxN = 256;
-constexpr int kStreamRS = (kStreamC + 7) / 8 * 8 + 1;   // largest row stride: ring padded to a multiple of 8, +1 -> odd
-constexpr int kStreamWarpDoubles = 32 * kStreamRS + kStreamC + 1 + kStreamMaxN;   // window + band coefficients (+1 pad) + rhs
+constexpr int kStreamBins = 4;    // bins by nb = res + 1: <= 8, <= 16, <= 24, <= 31
+__host__ __device__ inline int stream_c(int nb_max) { return 2 * nb_max + 1; }
+__host__ __device__ inline int stream_rs(int nb_max) { return ((stream_c(nb_max) + 7) & ~7) + 1; }   // ring padded to 8, +1 -> odd
+// window + band coefficients (+1 pad) + rhs, rounded to an even number of doubles
+__host__ __device__ inline int stream_warp_doubles(int nb_max) {
+    return (32 * stream_rs(nb_max) + stream_c(nb_max) + 1 + kStreamMaxN + 1) & ~1;
+}
 
 struct StreamParams {
     int64_t n_sys;
@@ -213,18 +220,22 @@ struct StreamParams {
     double* x;
     int64_t ldx;
     int32_t* info;
-    double* uscratch;   // [total warps][n * kStreamC]
+    double* uscratch;   // [total warps][n * (2 * nb_max + 1)]
+    const int32_t* order;   // the systems of this launch (a bin), n_sys of them
+    int nb_max;             // widest band (res + 1) among them: sizes the shared-memory window and the U rows
 };
 
 __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const StreamParams p) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
-    double* W = sm + warp * kStreamWarpDoubles;          // W[row slot * RS + column slot]
-    double* a = W + 32 * kStreamRS;                      // a[k + nb]
-    double* bs = a + kStreamC + 1;                       // right-hand side, overwritten in place by the transformed one
+    const int ustride = stream_c(p.nb_max);
+    double* W = sm + warp * stream_warp_doubles(p.nb_max);   // W[row slot * RS + column slot]
+    double* a = W + 32 * stream_rs(p.nb_max);            // a[k + nb]
+    double* bs = a + ustride + 1;                        // right-hand side, overwritten in place by the transformed one
     const int64_t gw = (int64_t)blockIdx.x * kStreamWarps + warp, nw = (int64_t)gridDim.x * kStreamWarps;
-    double* U = p.uscratch + gw * (int64_t)n * kStreamC;
-    for (int64_t s = gw; s < p.n_sys; s += nw) {
+    double* U = p.uscratch + gw * (int64_t)n * ustride;
+    for (int64_t si = gw; si < p.n_sys; si += nw) {
+        const int64_t s = p.order[si];
         const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
         const int nb_a = res + 1;
         const int nb = nb_a > n - 1 ? n - 1 : nb_a;      // rows below k+nb are zero in column k
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
             // retire the pivot row: U[k][0..len] and the transformed right-hand side
             for (int c = lane; c <= len; c += 32) {
                 int cs = kc + c; if (cs >= C) cs -= C;
-                U[(int64_t)k * kStreamC + c] = prow[cs];
+                U[(int64_t)k * ustride + c] = prow[cs];
             }
             if (lane == 0) bs[k] = bt;                     // slot k is free: rhs[k] entered the window long ago
             // eliminate
@@ -326,7 +337,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
         double u0[PF], u1[PF], u2[PF];
         auto load_row = [&](int k, double& r0, double& r1, double& r2) {
             const int len = min(n - 1, k + 2 * nb) - k;
-            const double* ur = U + (int64_t)k * kStreamC;
+            const double* ur = U + (int64_t)k * ustride;
             r0 = (k >= 0 && lane <= len) ? __ldcg(ur + lane) : 0.0;
             r1 = (k >= 0 && lane + 32 <= len) ? __ldcg(ur + lane + 32) : 0.0;
             r2 = 0.0;
@@ -433,13 +444,13 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                                           const int64_t*, int64_t, void*, int32_t*, double*);
     rc = frx_launch_stencil_weights(ctx, rule, FRX_SIDE_RIESZ_CAPUTO, n_sys, d_par, d_par + n_sys, d_par + 2 * n_sys,
                                     (const int64_t*)(ws + o_wptr), total_w, ws + o_k5, nullptr, (double*)(ws + o_w));
-    free(wptr); free(lf);
-    if (rc) return rc;
+    free(lf);
+    if (rc) { free(wptr); return rc; }
     // every band narrow enough: one warp per system, window in shared memory, U streamed through L2
     static const int force_cta = getenv("FRX_K4_VARIANT") ? atoi(getenv("FRX_K4_VARIANT")) == 1 : 0;
     if (!d_dense && !force_cta && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
+        // bins by band width (counting sort on the host; wptr is still alive here)
         StreamParams q;
-        q.n_sys = n_sys;
         q.n = n;
         q.rcw = (const double*)(ws + o_w);
         q.wptr = (const int64_t*)(ws + o_wptr);
@@ -449,20 +460,60 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.x = d_x;
         q.ldx = ldx;
         q.info = d_info;
-        const size_t dyn_s = sizeof(double) * (size_t)kStreamWarps * kStreamWarpDoubles;
-        FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_s));
-        int per_sm_s = 1;
-        FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, frx_k4_band_stream, kStreamWarps * 32, dyn_s));
-        if (per_sm_s < 1) per_sm_s = 1;
-        int64_t grid_s = (int64_t)ctx->sm_count * per_sm_s;
-        if (grid_s * kStreamWarps > n_sys) grid_s = (n_sys + kStreamWarps - 1) / kStreamWarps;
-        // per-warp U scratch lives in the io buffer (the workspace holds the stencil weights)
-        rc = frx_io_reserve(ctx, sizeof(double) * (size_t)grid_s * kStreamWarps * n * kStreamC);
-        if (rc) return rc;
-        q.uscratch = (double*)ctx->io;
-        FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4_band_stream<<<(unsigned)grid_s, kStreamWarps * 32, dyn_s, ctx->stream>>>(q));
+        int64_t bin_count[kStreamBins] = {0, 0, 0, 0}, bin_begin[kStreamBins + 1];
+        int bin_nb[kStreamBins] = {0, 0, 0, 0};
+        auto bin_of = [](int nb_a) { return nb_a <= 8 ? 0 : nb_a <= 16 ? 1 : nb_a <= 24 ? 2 : 3; };
+        for (int64_t s = 0; s < n_sys; ++s) {
+            const int nb_a = (int)((wptr[s + 1] - wptr[s] - 1) / 2) + 1, b = bin_of(nb_a);
+            ++bin_count[b];
+            if (nb_a > bin_nb[b]) bin_nb[b] = nb_a;
+        }
+        bin_begin[0] = 0;
+        for (int b = 0; b < kStreamBins; ++b) bin_begin[b + 1] = bin_begin[b] + bin_count[b];
+        int32_t* h_order = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_sys);
+        if (!h_order) { free(wptr); frx_set_error("host allocation failed"); return FRX_ERR_ALLOC; }
+        {
+            int64_t fill[kStreamBins] = {bin_begin[0], bin_begin[1], bin_begin[2], bin_begin[3]};
+            for (int64_t s = 0; s < n_sys; ++s) h_order[fill[bin_of((int)((wptr[s + 1] - wptr[s] - 1) / 2) + 1)]++] = (int32_t)s;
+        }
+        free(wptr);
+        // launch geometry per bin; the io buffer holds [order][U scratch of the largest launch]
+        int64_t grid_b[kStreamBins];
+        size_t dyn_b[kStreamBins], scratch = 0;
+        for (int b = 0; b < kStreamBins; ++b) {
+            grid_b[b] = 0;
+            if (!bin_count[b]) continue;
+            dyn_b[b] = sizeof(double) * (size_t)kStreamWarps * stream_warp_doubles(bin_nb[b]);
+            FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_b[b]));
+            int per_sm = 1;
+            FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4_band_stream, kStreamWarps * 32, dyn_b[b]));
+            if (per_sm < 1) per_sm = 1;
+            grid_b[b] = (int64_t)ctx->sm_count * per_sm;
+            if (grid_b[b] * kStreamWarps > bin_count[b]) grid_b[b] = (bin_count[b] + kStreamWarps - 1) / kStreamWarps;
+            const size_t need = sizeof(double) * (size_t)grid_b[b] * kStreamWarps * n * stream_c(bin_nb[b]);
+            if (need > scratch) scratch = need;
+        }
+        const size_t o_order = 0, o_scr = frx_align_up(sizeof(int32_t) * (size_t)n_sys, 256);
+        rc = frx_io_reserve(ctx, o_scr + scratch);
+        if (rc) { free(h_order); return rc; }
+        e = cudaMemcpyAsync((char*)ctx->io + o_order, h_order, sizeof(int32_t) * (size_t)n_sys, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // h_order is freed below
+        free(h_order);
+        if (e != cudaSuccess) { frx_set_error("order upload failed: %s", cudaGetErrorString(e)); return FRX_ERR_CUDA; }
+        q.uscratch = (double*)((char*)ctx->io + o_scr);
+        for (int b = 0; b < kStreamBins; ++b) {
+            if (!bin_count[b]) continue;
+            q.n_sys = bin_count[b];
+            q.order = (const int32_t*)((char*)ctx->io + o_order) + bin_begin[b];
+            q.nb_max = bin_nb[b];
+            // (the attribute is the maximum the function may use: raise it to this launch's size)
+            FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_b[b]));
+            FRX_LAUNCH(ctx, FRX_K_SOLVE,
+                       frx_k4_band_stream<<<(unsigned)grid_b[b], kStreamWarps * 32, dyn_b[b], ctx->stream>>>(q));
+        }
         return FRX_OK;
     }
+    free(wptr);
     SolveParams p;
     p.n_sys = n_sys;
     p.n = n;
