@@ -61,6 +61,8 @@ SIGNATURES = {
     'frx_toeplitz_product': (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, c_void_p, ctypes.c_int64, ctypes.c_double, c_void_p, ctypes.c_int64,
                                             ctypes.c_int64]),
+    'frx_stencil_compose': (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, ctypes.c_int64, c_void_p]),
     'frx_assemble_solve': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int32, c_double_p, c_double_p,
                                           c_double_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, c_void_p]),
     'frx_assemble_dense': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int32, c_double_p, c_double_p,

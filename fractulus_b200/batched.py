@@ -228,6 +228,37 @@ def toeplitz_product(c, g, paired=False, scale=1.0, n_cols=0, out=None):
     return out
 
 
+def stencil_compose(ptr_a, off_a, w_a, ptr_b, off_b, w_b, device=None):
+    """(f)(1): batched stencil o stencil composition, the expansion of fdm.Operator(A, fdm.Operator(B)) with the dict-merge's
+    own term order (bit-identical to it).  Ragged NumPy inputs: item k owns entries ptr[k]:ptr[k+1] of (off, w); offsets
+    are integers on a common grid; B's offsets ascend within an item.  -> (ptr_c, off_c) NumPy (distinct sums, ascending)
+    and the composed weights as a CUDA tensor."""
+    ptr_a = np.ascontiguousarray(ptr_a, dtype=np.int64)
+    ptr_b = np.ascontiguousarray(ptr_b, dtype=np.int64)
+    off_a = np.ascontiguousarray(off_a, dtype=np.int32)
+    off_b = np.ascontiguousarray(off_b, dtype=np.int32)
+    n = len(ptr_a) - 1
+    if len(ptr_b) - 1 != n:
+        raise ValueError('A and B must hold the same number of items')
+    outs = []
+    for k in range(n):                      # host-side structure: the distinct offset sums of every pair
+        oa, ob = off_a[ptr_a[k]:ptr_a[k + 1]], off_b[ptr_b[k]:ptr_b[k + 1]]
+        if len(ob) > 1 and np.any(np.diff(ob) <= 0):
+            raise ValueError("B's offsets must ascend within an item")
+        outs.append(np.unique(oa[:, None].astype(np.int64) + ob[None, :]).astype(np.int32))
+    ptr_c = np.zeros(n + 1, dtype=np.int64)
+    ptr_c[1:] = np.cumsum([len(o) for o in outs])
+    off_c = np.concatenate(outs) if outs else np.zeros(0, dtype=np.int32)
+    dev = default_device() if device is None else torch.device(device)
+    ctx, idx = _ctx_for(dev)
+    t = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x), dtype=dt, device=dev)
+    d = [t(ptr_a, torch.int64), t(off_a, torch.int32), t(w_a, torch.float64), t(ptr_b, torch.int64), t(off_b, torch.int32),
+         t(w_b, torch.float64), t(ptr_c, torch.int64), t(off_c, torch.int32)]
+    w_c = torch.empty((len(off_c),), dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().frx_stencil_compose(ctx.handle, n, *[_ptr(x) for x in d], len(off_c), _ptr(w_c)))
+    return ptr_c, off_c, w_c
+
+
 def _solve_params(alpha, h, res, n_sys=None):
     a = np.ascontiguousarray(np.atleast_1d(np.asarray(alpha, dtype=np.float64)))
     n_sys = len(a) if n_sys is None else n_sys

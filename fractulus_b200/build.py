@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT_DIR = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT_DIR, 'libfrx_b200.so')
-SOURCES = ['frx_api.cu', 'frx_weights.cu', 'frx_history.cu', 'frx_solve.cu', 'frx_ode.cu', 'frx_bench.cu']
+SOURCES = ['frx_api.cu', 'frx_weights.cu', 'frx_history.cu', 'frx_solve.cu', 'frx_ode.cu', 'frx_compose.cu', 'frx_bench.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 

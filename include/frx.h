@@ -176,6 +176,17 @@ int frx_toeplitz_product(frx_ctx* ctx, int64_t n_seq, const double* d_c, int64_t
                          int32_t paired, const double* d_g, int64_t ldg, double scale, double* d_y, int64_t ldy,
                          int64_t n_cols);
 
+/* ---- stencil o stencil composition on the device ---------------------------
+ * Batched expansion of fdm.Operator(stencil_a, fdm.Operator(stencil_b)) as the reference's call sites build it
+ * (test/integration/test_equation.py:61-66): C[o] = sum over A's nodes, in A's order, of wa * wb with off_a + off_b == o,
+ * first term assigned, later ones added -- the floating-point operations of the dict-merging expansion, hence
+ * bit-identical to it.  Ragged arrays: item k owns entries [ptr[k], ptr[k+1]).  Offsets are integers in a unit chosen by
+ * the caller (the finest grid both stencils live on); d_off_b must ascend within an item; the caller provides the
+ * output structure (d_ptr_c, d_off_c: the distinct sums, any order), the weights come back in d_w_c. */
+int frx_stencil_compose(frx_ctx* ctx, int64_t n_items, const int64_t* d_ptr_a, const int32_t* d_off_a, const double* d_w_a,
+                        const int64_t* d_ptr_b, const int32_t* d_off_b, const double* d_w_b, const int64_t* d_ptr_c,
+                        const int32_t* d_off_c, int64_t total_c, double* d_w_c);
+
 /* ---- K4: assemble + batch-solve small fractional boundary-value systems -------------------------
  * No counterpart in the reference (upstream `fdm` would do it): PARITY UNPINNED, see DESIGN.md section 6.
  * System s has n unknowns u_1..u_n at x_k = k*h[s] and the matrix of

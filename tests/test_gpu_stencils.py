@@ -204,3 +204,41 @@ def test_large_single_stencil_and_float_resolution():
     assert a == b
     with pytest.raises(ValueError):
         fr.create_left_stencil('caputo', Settings(0.5, 1.0, 4.5))
+
+
+def test_stencil_composition_equals_operator_expansion():
+    """(f)(1) frx_stencil_compose: d/dx o D^alpha_RC o d/dx composed on the device in two steps, against the oracle's
+    dict-merging expansion Operator(central, Operator(rc, Operator(central))) -- same terms in the same order: bit-exact."""
+    from oracle import assemble as oasm, fdm_shim
+    cases = [('caputo', 0.5, 0.25, 4), ('caputo', 0.8, 0.1, 7), ('trapezoidal', 0.3, 0.05, 12), ('rectangle', 0.6, 0.5, 3),
+             ('simpson', 0.4, 0.125, 6), ('caputo', 1.5, 0.2, 5)]
+    items, want = [], []
+    for rule, alpha, h, res in cases:
+        rc = oasm.rc_stencil(rule, alpha, h, res)
+        central = fdm_shim.Stencil.central(h)
+        op = fdm_shim.Operator(central, fdm_shim.Operator(rc, fdm_shim.Operator(central)))
+        exp = op.expand(fdm_shim.Point(0.))
+        want.append({int(round(node.x / (h / 2.))): w for node, w in exp.items()})
+        first, w = clib.riesz_caputo_arrays(rule, (alpha, res * h, res))
+        rc_off = 2 * (first + np.arange(len(w)))                   # units of h/2
+        items.append((np.array([-1, 1]), np.array([-1. / h, 1. / h]), rc_off, np.asarray(w, dtype=np.float64)))
+
+    def ragged(parts):
+        ptr = np.zeros(len(parts) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum([len(p) for p in parts])
+        return ptr, np.concatenate(parts)
+
+    # step 1: B1 = rc o central   (outer = rc in its own node order, inner = central)
+    pa, oa = ragged([it[2] for it in items]); _, wa = ragged([it[3] for it in items])
+    pb, ob = ragged([it[0] for it in items]); _, wb = ragged([it[1] for it in items])
+    p1, o1, w1 = batched.stencil_compose(pa, oa, wa, pb, ob, wb)
+    # step 2: C = central o B1
+    p2, o2, w2 = batched.stencil_compose(pb, ob, wb, p1, o1, w1.cpu().numpy())
+    w2 = w2.cpu().numpy()
+    for k in range(len(cases)):
+        got = {int(o): float(w) for o, w in zip(o2[p2[k]:p2[k + 1]], w2[p2[k]:p2[k + 1]])}
+        assert set(got) == set(want[k]), cases[k]
+        for o in got:
+            assert got[o] == want[k][o], (cases[k], o, got[o], want[k][o])      # bit-exact
+    with pytest.raises(ValueError):
+        batched.stencil_compose([0, 2], [0, 1], [1., 1.], [0, 2], [1, 0], [1., 1.])     # B not ascending
