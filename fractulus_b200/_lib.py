@@ -51,9 +51,9 @@ SIGNATURES = {
     'frx_history_gather': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, c_void_p, ctypes.c_double, ctypes.c_int64,
                                           ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                           ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64, ctypes.c_int64]),
-    'frx_history_host': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, c_double_p, ctypes.c_double,
-                                        ctypes.c_int64, ctypes.c_int64, c_double_p, ctypes.c_int64, ctypes.c_int64,
-                                        c_double_p, ctypes.c_int64]),
+    'frx_history_host': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, c_void_p, ctypes.c_double,
+                                        ctypes.c_int64, ctypes.c_int64, c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                        c_void_p, ctypes.c_int64]),   # host arrays by raw address
     'frx_history_solve': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, c_void_p, ctypes.c_double, ctypes.c_int64,
                                          c_void_p, ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int64]),
     'frx_toeplitz_apply': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int64,

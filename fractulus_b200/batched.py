@@ -306,29 +306,39 @@ def pinned_empty(shape):
     return torch.empty(tuple(shape), dtype=torch.float64).pin_memory().numpy()
 
 
+def _f64_c(x, ndim_min=0):
+    """x as a C-contiguous float64 ndarray (no copy, no work when it already is one)."""
+    if type(x) is np.ndarray and x.dtype == np.float64 and x.flags.c_contiguous and x.ndim >= ndim_min:
+        return x
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    return x.reshape(1) if x.ndim < ndim_min else x
+
+
 def history_host(approximation, alpha, h, g, N=None, device=None, out=None):
     """Same operator through the host-buffer entry point frx_history_host: NumPy in, NumPy out, the
     host<->device transfers happen inside the call.  `out`: optional C-contiguous float64 array [n_alpha, n_fields, N+1]
     to receive the result (a pinned one, see pinned_empty, is written directly by the kernel)."""
     rule = _lib.RULES[approximation]
-    a_h = np.ascontiguousarray(np.atleast_1d(np.asarray(alpha, dtype=np.float64)))
-    g_h = np.ascontiguousarray(g, dtype=np.float64)
-    g2 = g_h.reshape(-1, g_h.shape[-1])
-    n_fields, n_g = g2.shape
+    a_h = _f64_c(alpha, 1)
+    g_h = _f64_c(g)
+    n_g = g_h.shape[-1]
+    n_fields = g_h.size // n_g if n_g else 0
     if N is None:
         N = n_g - 1 - (1 if approximation == 'simpson' else 0)
+    n_alpha = a_h.shape[0]
     ctx = _lib.context(device)
     if out is None:
-        y = np.empty((len(a_h), n_fields, N + 1), dtype=np.float64)
+        y = np.empty((n_alpha, n_fields, N + 1), dtype=np.float64)
     else:
         y = out
-        if not (isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous and y.flags.writeable
-                and y.size == len(a_h) * n_fields * (N + 1)):
+        if not (type(y) is np.ndarray and y.dtype == np.float64 and y.flags.c_contiguous and y.flags.writeable
+                and y.size == n_alpha * n_fields * (N + 1)):
             raise ValueError('out must be a writeable C-contiguous float64 array with n_alpha*n_fields*(N+1) elements')
-        y = y.reshape(len(a_h), n_fields, N + 1)
-    _lib.check(_lib.lib().frx_history_host(ctx.handle, rule, len(a_h), a_h.ctypes.data_as(_lib.c_double_p), float(h),
-                                           int(N), n_fields, g2.ctypes.data_as(_lib.c_double_p), n_g, n_g,
-                                           y.ctypes.data_as(_lib.c_double_p), N + 1))
+        if y.ndim != 3:
+            y = y.reshape(n_alpha, n_fields, N + 1)
+    # raw addresses: ndarray.ctypes.data_as costs microseconds per argument, as much as the rest of the call
+    _lib.check(_lib.lib().frx_history_host(ctx.handle, rule, n_alpha, a_h.ctypes.data, float(h), int(N), n_fields,
+                                           g_h.ctypes.data, n_g, n_g, y.ctypes.data, N + 1))
     if g_h.ndim == 1:
         y = y[:, 0]
     if np.ndim(alpha) == 0:
