@@ -783,8 +783,14 @@ int history_impl(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double
     // dynamic shared memory: at least the double buffer, padded so that exactly CTAS_PER_SM CTAs fit per SM
     int smem_sm = 0;
     FRX_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
-    int dyn = (smem_sm / G::CTAS_PER_SM - 1024 - 64) / 128 * 128;
-    if (dyn < 2 * G::STAGE_BYTES + 2 * G::WBUF_BYTES) dyn = 2 * G::STAGE_BYTES + 2 * G::WBUF_BYTES;
+    // exactly CTAS_PER_SM CTAs per SM: the request is padded only if one more CTA would fit otherwise.  What is left of
+    // the SM's shared memory lets CTAs of the (small) prepare kernel stay resident next to the early-launched CTAs of
+    // this one (programmatic dependent launch), so the CTA launch ramp hides behind the prepare kernel.
+    const int need = 2 * G::STAGE_BYTES + 2 * G::WBUF_BYTES, per_cta_overhead = 1024 + 128;
+    int dyn = need;
+    if (smem_sm / (need + per_cta_overhead) > G::CTAS_PER_SM)
+        dyn = (smem_sm / (G::CTAS_PER_SM + 1) - per_cta_overhead + 128) / 128 * 128;   // too big for CTAS_PER_SM + 1
+    if (dyn < need) dyn = need;
     FRX_CUDA(cudaFuncSetAttribute(frx_k2_history_main<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     FRX_LAUNCH(ctx, FRX_K_HISTORY_MAIN,
                FRX_CUDA(frx_launch_dependent(frx_k2_history_main<G>, dim3((unsigned)NG), dim3(kNT), (size_t)dyn, ctx->stream, p)));
