@@ -452,8 +452,9 @@ __device__ inline void finish_rows(const HistParams& p, int64_t prob, int64_t I,
         }
         if (ip == 0) store_row(0, 0.0);               // row 0 has no stencil: y_0 = 0 by convention
         double v;
-        if (i == 1 && (p.rule == FRX_RULE_RECTANGLE || p.rule == FRX_RULE_SIMPSON)) {
-            v = nan("");  // the reference cannot build this stencil
+        if ((i == 1 && (p.rule == FRX_RULE_RECTANGLE || p.rule == FRX_RULE_SIMPSON)) ||
+            (rev && p.rule == FRX_RULE_SIMPSON && i == p.N && (i & 1))) {
+            v = nan("");  // the reference cannot build this stencil (resolution 1; mirrored 'simpson' node left of node 0)
         } else {
             // wsm: this tile's w0 / mult rows, prefetched into shared memory with the unit (n_sub == 1 only)
             double s = fma(wsm ? wsm[local] : p.w0[a * p.ldw + i], g0, sum);
@@ -653,7 +654,9 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
         // holds every second column, slot padf + k <-> j' = 2k + e
         // ('simpson' also keeps node N+1, column j' = N: no row reaches it, the epilogue of the last odd row reads it)
         const int64_t jj = (n_pass == 1 ? j : 2 * j + pass) + 1;
-        if (j >= 0 && jj <= N + (n_pass == 2 ? 1 : 0)) v = g[f * ldg + (reverse ? N - jj : jj)];
+        // (mirrored field: node N+1 would be node -1 of the caller's field -- it stays 0 and the one row that needs it,
+        // the right-sided 'simpson' row of node 0 with odd N, is NaN in the epilogue)
+        if (j >= 0 && jj <= N + (n_pass == 2 && !reverse ? 1 : 0)) v = g[f * ldg + (reverse ? N - jj : jj)];
         gp[e] = v;
         if (j == 0 && pass == 0 && !raw_c) g0[f] = g[f * ldg + (reverse ? N : 0)];
     }
@@ -832,8 +835,6 @@ extern "C" int frx_history_sided(frx_ctx* ctx, int rule, int side, int64_t n_alp
                 "n_alpha (<= 65535) / n_fields (<= 32767) out of range");
     FRX_REQUIRE(side == FRX_SIDE_LEFT || rule != FRX_RULE_GRUNWALD_LETNIKOV, FRX_ERR_DOMAIN,
                 "the Gruenwald-Letnikov extension offers the left operator only");
-    FRX_REQUIRE(side == FRX_SIDE_LEFT || rule != FRX_RULE_SIMPSON, FRX_ERR_DOMAIN,
-                "'simpson' rows of odd resolution read one node beyond the evaluation point: only the left operator is offered");
     const int64_t need_g = N + 1 + (rule == FRX_RULE_SIMPSON ? 1 : 0);
     FRX_REQUIRE(n_g >= need_g && ldg >= n_g && ldy >= N + 1, FRX_ERR_INVALID_ARG,
                 "field too short (needs N+1 nodes, N+2 for 'simpson') or leading dimension too small");

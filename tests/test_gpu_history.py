@@ -273,11 +273,14 @@ def test_right_and_riesz_caputo_growing_history_vs_oracle():
     x = np.arange(N + 1) * h
     g = np.exp(-x) * (1. + x) + 0.3 * np.sin(5 * x)
     rows = list(range(2, N - 1, 23)) + [N - 2]
-    for rule in ('caputo', 'trapezoidal', 'rectangle'):
+    for rule in ('caputo', 'trapezoidal', 'rectangle', 'simpson'):
         for alpha in (0.3, 0.8):
             yl, yr = _oracle_sided_rows(rule, alpha, h, g, N, rows)
-            got_r = batched.history(rule, alpha, h, dev(g), N=N, side='right').cpu().numpy()
-            got_rc = batched.history(rule, alpha, h, dev(g), N=N, side='riesz_caputo').cpu().numpy()
+            # 'simpson' fields carry one extra node (the left operator's odd rows read node i+1); the mirrored rows of
+            # the right operator read node i-1 instead
+            gd = dev(np.append(g, 0.)) if rule == 'simpson' else dev(g)
+            got_r = batched.history(rule, alpha, h, gd, N=N, side='right').cpu().numpy()
+            got_rc = batched.history(rule, alpha, h, gd, N=N, side='riesz_caputo').cpu().numpy()
             scale_r, scale = np.abs(yr).max(), None
             assert np.abs(got_r[rows] - yr).max() <= 1e-12 * scale_r, (rule, alpha)
             K, sgn = 0.5 * math.gamma(2. - alpha) / math.gamma(2.), (-1.) ** (math.floor(alpha) + 1.)
@@ -288,8 +291,18 @@ def test_right_and_riesz_caputo_growing_history_vs_oracle():
     yl_full = batched.history('caputo', 0.5, h, dev(g), N=N).cpu().numpy()
     yr_rev = batched.history('caputo', 0.5, h, dev(g[::-1].copy()), N=N, side='right').cpu().numpy()
     assert np.array_equal(yr_rev[::-1][1:], -yl_full[1:])
-    with pytest.raises(ValueError):
-        batched.history('simpson', 0.5, h, dev(np.append(g, 0.)), N=N, side='right')
+    # 'simpson', odd N: the mirrored stencil of node 0 would need node -1 -> NaN, like the resolution-1 rows
+    N2 = 701
+    g2 = np.cos(np.arange(N2 + 2) / 300.)
+    yr2 = batched.history('simpson', 0.5, 1. / N2, dev(g2), N=N2, side='right').cpu().numpy()
+    assert np.isnan(yr2[0]) and np.isnan(yr2[N2 - 1]) and yr2[N2] == 0. and np.isfinite(yr2[1:N2 - 1]).all()
+    rows2 = [1, 2, 3, 350, 351, N2 - 3, N2 - 2]
+    want2 = []
+    for i in rows2:
+        first, w = clib.right_arrays('simpson', (0.5, (N2 - i) * (1. / N2), N2 - i))
+        want2.append(sum(float(g2[i + first + k]) * float(wk) for k, wk in enumerate(w)))
+    want2 = np.array(want2)
+    assert np.abs(yr2[rows2] - want2).max() <= 1e-12 * np.abs(want2).max()
 
 
 def test_grunwald_letnikov_history_extension():
