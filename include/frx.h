@@ -132,7 +132,8 @@ int frx_history(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, 
 /* The same for the right-sided operator (row i = create_right_stencil(rule, Settings(alpha, (N-i)*h, N-i)),
  * equation.py:32-39; y_N = 0) and for the two-sided Riesz-Caputo combination of both growing histories,
  * 1./2.*gamma(2.-alpha)/gamma(2.) * (left + (-1.)**n * right) (equation.py:20-25; nodes 0 and N = NaN).
- * side: frx_side.  'simpson' is offered for FRX_SIDE_LEFT only. */
+ * side: frx_side.  'simpson' fields carry N+2 nodes on every side (the left operator's odd rows read node i+1; the
+ * mirrored rows of the right operator read node i-1, and the right-sided row of node 0 with odd N is NaN). */
 int frx_history_sided(frx_ctx* ctx, int rule, int side, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                       int64_t n_fields, const double* d_g, int64_t ldg, int64_t n_g, double* d_y, int64_t ldy);
 /* Fused compute + gather (sweeps sharded over the GPUs of one box): like frx_history for
