@@ -162,7 +162,7 @@ def history_gather(approximation, alpha, h, g, peer_ptrs, row0, N, validate=Fals
 def history_solve(approximation, alpha, h, f, u0):
     """Inverse of history(side='left'): u[a, :] with u[a, 0] = u0[a] and history(approximation, alpha_a, h, u[a])[i] = f[a, i]
     for i = 1..N (f[:, 0] is ignored).  alpha: 1-D (host); f: cuda float64 [n_alpha, N+1]; u0: scalar or [n_alpha].
-    'caputo' / 'trapezoidal'.  Extension: the reference has no solver."""
+    'caputo' / 'trapezoidal' / 'grunwald_letnikov' (the implicit GL scheme).  Extension: the reference has no solver."""
     rule = _lib.RULES[approximation]
     a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha)
     if not torch.is_tensor(f) or not f.is_cuda or f.dim() != 2 or f.shape[0] != len(a_h):

@@ -168,8 +168,9 @@ __global__ void __launch_bounds__(256) frx_ode_trailing_update(int64_t N, int64_
 extern "C" int frx_history_solve(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                                  const double* d_f, int64_t ldf, const double* d_u0, double* d_u, int64_t ldu) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    FRX_REQUIRE(rule == FRX_RULE_CAPUTO || rule == FRX_RULE_TRAPEZOIDAL, FRX_ERR_DOMAIN,
-                "frx_history_solve offers the 'caputo' and 'trapezoidal' operators");
+    // rules whose weight of the evaluation point itself, c[0], is non-zero ('rectangle': c[0] = 0, 'simpson': two sequences)
+    FRX_REQUIRE(rule == FRX_RULE_CAPUTO || rule == FRX_RULE_TRAPEZOIDAL || rule == FRX_RULE_GRUNWALD_LETNIKOV, FRX_ERR_DOMAIN,
+                "frx_history_solve offers the 'caputo', 'trapezoidal' and 'grunwald_letnikov' operators");
     FRX_REQUIRE(N >= 1 && N < ((int64_t)1 << 30) && n_alpha >= 0 && n_alpha <= 65535, FRX_ERR_INVALID_ARG, "bad N / n_alpha");
     FRX_REQUIRE(ldf >= N + 1 && ldu >= N + 1, FRX_ERR_INVALID_ARG, "leading dimension too small (N+1 nodes)");
     if (n_alpha == 0) return FRX_OK;

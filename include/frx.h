@@ -152,7 +152,7 @@ int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const double* h_al
  * For every alpha: given f_1..f_N (d_f[a*ldf + i]) and the initial value u0[a], find u with
  *   frx_history(rule, alpha, h, u)[i] = f_i, i = 1..N     (u_0 = u0; rows = Settings(alpha, i*h, i) stencils),
  * by Newton iteration for the inverse series on the tensor-core Toeplitz kernel (csrc/frx_ode.cu).  One implicit step of a
- * fractional ODE / Volterra equation; 'caputo' and 'trapezoidal' only.  d_u[a*ldu + i], i = 0..N. */
+ * fractional ODE / Volterra equation; 'caputo', 'trapezoidal' and the 'grunwald_letnikov' extension (the implicit GL scheme).  d_u[a*ldu + i], i = 0..N. */
 int frx_history_solve(frx_ctx* ctx, int rule, int64_t n_alpha, const double* d_alpha, double h, int64_t N,
                       const double* d_f, int64_t ldf, const double* d_u0, double* d_u, int64_t ldu);
 

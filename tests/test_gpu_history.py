@@ -325,6 +325,28 @@ def test_grunwald_letnikov_history_extension():
     assert np.max(np.abs(y[N // 2:] - exact[N // 2 - 1:]) / exact[N // 2 - 1:]) < 5e-3
 
 
+def test_grunwald_letnikov_solve_is_the_implicit_gl_scheme():
+    """EXTENSION: frx_history_solve for 'grunwald_letnikov' = the implicit Gruenwald-Letnikov scheme
+    u_i = (f_i / mult_i - sum_{k=1..i} w_k u_{i-k}) / w_0; against that recurrence with exact (mpmath) weights."""
+    from oracle import gl_exact
+    N, h, alpha = 2500, 1. / 2500, 0.6
+    x = np.arange(N + 1) * h
+    u_true = np.sin(3 * x) + x * x + 0.5
+    f = batched.history('grunwald_letnikov', [alpha], h, dev(u_true), N=N)
+    u = batched.history_solve('grunwald_letnikov', [alpha], h, f, u_true[0]).cpu().numpy()[0]
+    assert np.abs(u - u_true).max() <= 1e-11 * np.abs(u_true).max()                # round trip
+    w = gl_exact.weights(alpha, N + 1)
+    steps = (np.arange(1, N + 1) * h) / np.arange(1, N + 1)
+    us = np.unique(steps)
+    mult = np.array([gl_exact.multiplier(alpha, s, 1) for s in us])[np.searchsorted(us, steps)]
+    fh = f[0].cpu().numpy()
+    want = np.empty(N + 1)
+    want[0] = u_true[0]
+    for i in range(1, N + 1):
+        want[i] = (fh[i] / mult[i - 1] - np.dot(w[1:i + 1], want[i - 1::-1][:i])) / w[0]
+    assert np.abs(u - want).max() <= 1e-11 * np.abs(want).max()
+
+
 def test_fused_gather_entry_point_single_gpu():
     """frx_history_gather with the only peer being this GPU: rows land at row0 + problem of the target array and
     equal the plain history bit for bit."""
