@@ -478,6 +478,9 @@ __device__ inline unsigned long long trace_now() {
     return t;
 }
 #define FRX_TRACE(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) frx_k2_trace[blockIdx.x * 8 + (slot)] = trace_now(); } while (0)
+// upper-bound experiments (WRONG results, timing only): bit 0 = stage only the first unit of a span, bit 1 = drop the
+// barrier after compute
+__device__ int frx_k2_debug_mode;
 #else
 #define FRX_TRACE(slot) do { } while (0)
 #endif
@@ -515,6 +518,9 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
         char* stage = smem + ((u - ubeg) & 1) * G::STAGE_BYTES;
         if (u + 1 < uend) {
             cursor_advance<G>(p, nxt);
+#ifdef FRX_K2_TRACE
+            if (!(frx_k2_debug_mode & 1))
+#endif
             stage_unit<G>(p, nxt, smem + ((u + 1 - ubeg) & 1) * G::STAGE_BYTES);
             if (wpref && (nxt.v + 1 == nxt.units || u + 2 == uend))
                 stage_epilogue_operands<G>(p, nxt, wbufs + ((u + 1 - ubeg) & 1) * (G::WBUF_BYTES / 8));
@@ -535,6 +541,9 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
 #ifdef FRX_K2_TRACE
         trace_compute += clock64() - tc0;
         trace_groups += s1 - s0;
+#endif
+#ifdef FRX_K2_TRACE
+        if (!(frx_k2_debug_mode & 2))
 #endif
         __syncthreads();
 #ifdef FRX_K2_TRACE
@@ -969,6 +978,9 @@ extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const d
 }
 
 #ifdef FRX_K2_TRACE
+extern "C" int frx_debug_k2_mode(int mode) {
+    return cudaMemcpyToSymbol(frx_k2_debug_mode, &mode, sizeof(int)) == cudaSuccess ? 0 : -1;
+}
 extern "C" int frx_debug_k2_trace(unsigned long long* h_out /*[1024*8]*/) {
     return cudaMemcpyFromSymbol(h_out, frx_k2_trace, sizeof(unsigned long long) * 1024 * 8) == cudaSuccess ? 0 : -1;
 }
