@@ -29,7 +29,9 @@
 //   window of 2R field values: per R distances R*R DFMAs for R/2 LDS.128 of field values (chunk stride 8R+16 bytes ->
 //   conflict-free) and R/2 broadcast LDS.128 of weights.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include "frx_internal.h"
 #include "frx_table.cuh"
@@ -951,6 +953,16 @@ extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const d
     }
     if (n_alpha == 0 || n_fields == 0) return FRX_OK;
     FRX_REQUIRE(ldg >= n_g && ldy >= N + 1, FRX_ERR_INVALID_ARG, "leading dimension too small");
+    // FRX_HOST_PROFILE=1: accumulate where the host-side time of this call goes (printed every 64 calls)
+    static const bool prof = getenv("FRX_HOST_PROFILE") != nullptr;
+    static double prof_acc[3];
+    static int prof_calls;
+    auto now = []() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+    };
+    const double pt0 = prof ? now() : 0.0;
     FRX_CUDA(cudaSetDevice(ctx->device));
     // FRX_HOST_ZERO_COPY: bit 0 = read the field in place, bit 1 = store the result in place
     static const int zero_copy = getenv("FRX_HOST_ZERO_COPY") ? atoi(getenv("FRX_HOST_ZERO_COPY")) : 3;
@@ -970,10 +982,23 @@ extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const d
     FRX_CUDA(cudaMemcpyAsync(d_alpha, h_alpha, sizeof(double) * n_alpha, cudaMemcpyHostToDevice, ctx->stream));
     if (!map_g)
         FRX_CUDA(cudaMemcpyAsync(io + b_alpha, h_g, sizeof(double) * (size_t)n_fields * ldg, cudaMemcpyHostToDevice, ctx->stream));
+    const double pt1 = prof ? now() : 0.0;
     rc = frx_history(ctx, rule, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, n_g, d_y, ldy);
     if (rc) return rc;
     if (!map_y) FRX_CUDA(cudaMemcpyAsync(h_y, d_y, b_y, cudaMemcpyDeviceToHost, ctx->stream));
+    const double pt2 = prof ? now() : 0.0;
     FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (prof) {
+        const double pt3 = now();
+        prof_acc[0] += pt1 - pt0;
+        prof_acc[1] += pt2 - pt1;
+        prof_acc[2] += pt3 - pt2;
+        if (++prof_calls % 64 == 0) {
+            fprintf(stderr, "frx_history_host: setup + alpha copy %.1f us, launches %.1f us, wait %.1f us (mean of 64 calls)\n",
+                    prof_acc[0] / 64, prof_acc[1] / 64, prof_acc[2] / 64);
+            prof_acc[0] = prof_acc[1] = prof_acc[2] = 0.0;
+        }
+    }
     return FRX_OK;
 }
 
