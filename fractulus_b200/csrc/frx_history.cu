@@ -657,19 +657,32 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
     }
     const int64_t n_pad_blocks = gridDim.x - n_tab, pb = bx - n_tab;
     const int64_t total = n_fp * ldgp, stride = n_pad_blocks * blockDim.x;
-    for (int64_t e = pb * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int64_t fp = e / ldgp, x = e - fp * ldgp;
-        const int64_t f = fp / n_pass, pass = fp - f * n_pass, j = x - padf;
-        double v = 0.0;
-        // slot padf + j' holds column j = j' + 1 (shifted coordinates, see tile_chunks); 'simpson' (n_pass = 2): pass e
-        // holds every second column, slot padf + k <-> j' = 2k + e
-        // ('simpson' also keeps node N+1, column j' = N: no row reaches it, the epilogue of the last odd row reads it)
-        const int64_t jj = (n_pass == 1 ? j : 2 * j + pass) + 1;
-        // (mirrored field: node N+1 would be node -1 of the caller's field -- it stays 0 and the one row that needs it,
-        // the right-sided 'simpson' row of node 0 with odd N, is NaN in the epilogue)
-        if (j >= 0 && jj <= N + (n_pass == 2 && !reverse ? 1 : 0)) v = g[f * ldg + (reverse ? N - jj : jj)];
-        gp[e] = v;
-        if (j == 0 && pass == 0 && !raw_c) g0[f] = g[f * ldg + (reverse ? N : 0)];
+    // batches of 8 elements per thread: all loads of a batch are issued before the first store, so a field that lives in
+    // pinned host memory (frx_history_host) costs one PCIe round trip per batch, not per element
+    for (int64_t e0 = pb * blockDim.x + threadIdx.x; e0 < total; e0 += 8 * stride) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t e = e0 + q * stride;
+            v[q] = 0.0;
+            if (e < total) {
+                const int64_t fp = e / ldgp, x = e - fp * ldgp;
+                const int64_t f = fp / n_pass, pass = fp - f * n_pass, j = x - padf;
+                // slot padf + j' holds column j = j' + 1 (shifted coordinates, see tile_chunks); 'simpson' (n_pass = 2):
+                // pass e holds every second column, slot padf + k <-> j' = 2k + e ('simpson' also keeps node N+1, column
+                // j' = N: no row reaches it, the epilogue of the last odd row reads it).  Mirrored field: node N+1 would be
+                // node -1 of the caller's field -- it stays 0 and the one row that needs it, the right-sided 'simpson' row
+                // of node 0 with odd N, is NaN in the epilogue.
+                const int64_t jj = (n_pass == 1 ? j : 2 * j + pass) + 1;
+                if (j >= 0 && jj <= N + (n_pass == 2 && !reverse ? 1 : 0)) v[q] = g[f * ldg + (reverse ? N - jj : jj)];
+                if (j == 0 && pass == 0 && !raw_c) g0[f] = g[f * ldg + (reverse ? N : 0)];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t e = e0 + q * stride;
+            if (e < total) gp[e] = v[q];
+        }
     }
     for (int64_t e = pb * blockDim.x + threadIdx.x; e < n_tickets; e += stride) tickets[e] = 0;
 }
