@@ -473,13 +473,13 @@ __device__ inline int64_t span_owner(int64_t u, int64_t total, int64_t G) { retu
 
 #ifdef FRX_K2_TRACE
 // tuning aid (not in production builds): per-CTA timestamps of the phases of the history kernel
-__device__ unsigned long long frx_k2_trace[1024 * 8];
+__device__ unsigned long long frx_k2_trace[1024 * 16];
 __device__ inline unsigned long long trace_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define FRX_TRACE(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) frx_k2_trace[blockIdx.x * 8 + (slot)] = trace_now(); } while (0)
+#define FRX_TRACE(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) frx_k2_trace[blockIdx.x * 16 + (slot)] = trace_now(); } while (0)
 // upper-bound experiments (WRONG results, timing only): bit 0 = stage only the first unit of a span, bit 1 = drop the
 // barrier after compute
 __device__ int frx_k2_debug_mode;
@@ -567,6 +567,9 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
                 const int64_t k0 = span_owner(tile_begin, total_groups, NG), k1 = span_owner(tile_end - 1, total_groups, NG);
                 __threadfence();
                 __syncthreads();
+#ifdef FRX_K2_TRACE
+                if (u + 1 == uend) FRX_TRACE(8);    // partial slot published
+#endif
                 if (threadIdx.x == 0) {
                     int* ticket = p.tickets + (cur.prob * p.n_tiles + cur.I);
                     const int old = atomicAdd(ticket, 1);
@@ -574,6 +577,10 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
                     if (s_last) *ticket = 0;  // leave the tickets clean for the next call
                 }
                 __syncthreads();
+#ifdef FRX_K2_TRACE
+                if (u + 1 == uend) FRX_TRACE(9);    // ticket taken
+                if (u + 1 == uend && threadIdx.x == 0 && blockIdx.x < 1024) frx_k2_trace[blockIdx.x * 16 + 12] = s_last;
+#endif
                 if (s_last) {  // every other participant has published its slot: add them in CTA order
                     __threadfence();
                     const double* src = p.partial + (2 * k0 + 1) * G::TI;
@@ -597,8 +604,14 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
                                 for (int r = 0; r < R; ++r) acc[r] += part[j][r];
                             }
                     }
+#ifdef FRX_K2_TRACE
+                    if (u + 1 == uend) FRX_TRACE(10);   // slots summed
+#endif
                     finish_rows<G>(p, cur.prob, cur.I, acc, reinterpret_cast<double*>(stage),
                             wpref ? wbufs + ((u - ubeg) & 1) * (G::WBUF_BYTES / 8) : nullptr);
+#ifdef FRX_K2_TRACE
+                    if (u + 1 == uend) FRX_TRACE(11);   // rows stored
+#endif
                 }
             }
 #pragma unroll
@@ -612,8 +625,8 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
     if (threadIdx.x == 0 && blockIdx.x < 1024) {
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        frx_k2_trace[blockIdx.x * 8 + 6] = smid | ((unsigned long long)trace_groups << 32);
-        frx_k2_trace[blockIdx.x * 8 + 7] = (unsigned long long)trace_compute | ((unsigned long long)(clock64() - trace_c0) << 32);
+        frx_k2_trace[blockIdx.x * 16 + 6] = smid | ((unsigned long long)trace_groups << 32);
+        frx_k2_trace[blockIdx.x * 16 + 7] = (unsigned long long)trace_compute | ((unsigned long long)(clock64() - trace_c0) << 32);
     }
 #endif
 }
@@ -1019,7 +1032,7 @@ extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const d
 extern "C" int frx_debug_k2_mode(int mode) {
     return cudaMemcpyToSymbol(frx_k2_debug_mode, &mode, sizeof(int)) == cudaSuccess ? 0 : -1;
 }
-extern "C" int frx_debug_k2_trace(unsigned long long* h_out /*[1024*8]*/) {
-    return cudaMemcpyFromSymbol(h_out, frx_k2_trace, sizeof(unsigned long long) * 1024 * 8) == cudaSuccess ? 0 : -1;
+extern "C" int frx_debug_k2_trace(unsigned long long* h_out /*[1024*16]*/) {
+    return cudaMemcpyFromSymbol(h_out, frx_k2_trace, sizeof(unsigned long long) * 1024 * 16) == cudaSuccess ? 0 : -1;
 }
 #endif

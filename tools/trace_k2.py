@@ -13,11 +13,11 @@ for _ in range(5):
     flush.zero_()
     y = batched.history('caputo', alphas, h, g, N=N, validate=False)
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * (1024 * 8))()
+buf = (ctypes.c_ulonglong * (1024 * 16))()
 L = _lib.lib()
 assert L.frx_debug_k2_trace(buf) == 0
 n_cta = int(os.environ.get('FRX_TRACE_CTAS', '592'))
-raw = np.array(buf, dtype=np.uint64).reshape(1024, 8)[:n_cta]
+raw = np.array(buf, dtype=np.uint64).reshape(1024, 16)[:n_cta]
 t = raw.astype(np.int64)
 t0 = t[:, 0].min()
 names = ['start', 'after dependency wait', 'first unit in smem', 'last unit in smem', 'last compute done', 'exit']
@@ -43,3 +43,10 @@ cpg = comp / np.maximum(groups, 1)
 print('cycles/group by blockIdx decile:', [round(float(np.median(cpg[i::10])), 0) for i in range(1)], 'min %.0f max %.0f' % (cpg.min(), cpg.max()))
 late_sm = np.unique(sm[order])
 print('SMs of the latest CTAs:', late_sm.tolist())
+
+fin = np.nonzero(raw[:, 12] == 1)[0]
+if len(fin):
+    d = lambda a, b: (t[fin, a] - t[fin, b]) / 1e3
+    print('finishers of a split tile at their span end: %d CTAs; medians (us): last compute -> slot published %.2f, -> ticket %.2f, '
+          '-> slots summed %.2f, -> rows stored %.2f, -> exit %.2f' % (len(fin), np.median(d(8, 4)), np.median(d(9, 8)),
+          np.median(d(10, 9)), np.median(d(11, 10)), np.median(d(5, 11))))
