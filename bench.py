@@ -563,8 +563,8 @@ K2_DRAM_TRAFFIC_BYTES = 3266816
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=('b200', 'reference'))
     ap.add_argument('--alphas-per-gpu', type=int, default=1)
     ap.add_argument('--workload', default='cfg2', choices=('cfg2', 'cfg3', 'cfg4'),
