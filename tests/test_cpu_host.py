@@ -195,3 +195,16 @@ def test_product_never_touches_the_oracle():
                     assert not re.search(r'\b(import|from|include|CDLL)\b.*oracle', code), (name, line)
     out = subprocess.run(['ldd', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert 'oracle' not in out
+
+
+def test_host_side_argument_handling_without_gpu():
+    """Host logic of the batched layer that runs before any device work."""
+    from fractulus_b200 import batched
+    a = np.linspace(0., 1., 5)
+    assert batched._f64_c(a) is a                                        # conforming arrays pass through untouched
+    assert batched._f64_c(a[::2]).flags.c_contiguous and batched._f64_c([1, 2]).dtype == np.float64
+    assert batched._f64_c(0.5, 1).shape == (1,)
+    with pytest.raises(ValueError):                                      # item counts differ
+        batched.stencil_compose([0, 1], [0], [1.], [0, 1, 2], [0, 1], [1., 1.])
+    with pytest.raises(ValueError):                                      # B's offsets must ascend
+        batched.stencil_compose([0, 2], [0, 1], [1., 1.], [0, 2], [1, 0], [1., 1.])
