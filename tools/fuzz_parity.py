@@ -1,6 +1,6 @@
 """Randomised differential check of the history paths against the C oracle (tests' own tolerance helpers): random rules,
 sizes around the tile boundaries, batch shapes, both entry points, pinned and pageable host buffers, the solve round
-trip.  Usage: python tools/fuzz_parity.py [n_cases] [seed]"""
+trip.  Usage: python tools/fuzz_parity.py [n_cases] [seed] [largest N]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,12 +9,13 @@ from fractulus_b200 import batched
 from oracle import clib
 from test_gpu_history import assert_history_close
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+n_max = int(sys.argv[3]) if len(sys.argv) > 3 else 6000
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 7)
 special = [1, 2, 3, 7, 8, 9, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 3071, 3072, 3073, 4097]
 fails = 0
 for case in range(n_cases):
     rule = ['caputo', 'rectangle', 'trapezoidal', 'simpson'][rng.integers(4)]
-    N = int(special[rng.integers(len(special))] if rng.random() < 0.6 else rng.integers(1, 6000))
+    N = int(special[rng.integers(len(special))] if rng.random() < 0.6 else rng.integers(1, n_max))
     if rule == 'simpson':
         N = max(N, 2)
     n_alpha, n_fields = int(rng.integers(1, 4)), int(rng.integers(1, 4))
