@@ -42,7 +42,7 @@ for case in range(n_cases):
                         # sign-changing fields at large N: the rounding of the N-term sums (tile order here, CPython's
                         # compensated sum in the oracle) reaches the zero-crossing floor 1e-15 * max|y| of the contract
                         err = np.abs(got[ai][f, lo:] - want[f, lo:]).max() / np.abs(want[f, lo:]).max()
-                        if err > 5e-15:
+                        if err > 64 * np.finfo(float).eps:
                             raise
                         print('     (case %d: summation noise %.1e of max|y| at a zero crossing)' % (case, err), flush=True)
         if rule in ('caputo', 'trapezoidal') and N >= 2:
