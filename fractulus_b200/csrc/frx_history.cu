@@ -23,7 +23,8 @@
 //     of a gathered result array (frx_history_gather).
 //   * 'simpson': two interleaved weight sequences -> two half-size problems (row parity) of two passes each over
 //     decimated tables and fields (see frx_table_block), same N^2/2 FMA as the other rules.
-// Tensor variant MGeo (default MGeo<4,1024,2>: units of 1024 rows x 1024 columns, 2 CTAs of 4 warps per SM): block-Toeplitz
+// Tensor variant MGeo (default MGeo<4,1024,2,true>: units of 1024 rows x 1024 columns, 2 CTAs of 4 warps per SM, units staged
+//   by two cp.async.bulk copies (TMA engine) against an mbarrier): block-Toeplitz
 //   formulation on mma.m8n8k4.f64 (DMMA), see MGeo below.
 // DFMA variant Geo (FRX_K2_VARIANT=0/1, kept for comparison): each thread owns R consecutive rows and slides a register
 //   window of 2R field values: per R distances R*R DFMAs for R/2 LDS.128 of field values (chunk stride 8R+16 bytes ->
@@ -74,6 +75,7 @@ struct Geo {
     static constexpr int C_PAD = 0;              // c tables: natural order, no front padding
     static constexpr int C_PERM = 0;
     static constexpr bool TENSOR = false;
+    static constexpr bool BULK = false;
     static constexpr int WBUF_BYTES = 0;         // no epilogue-operand prefetch
     static_assert(TI % TD == 0, "tile rows must be a multiple of the distance chunk");
     static_assert(STAGE_BYTES >= TI * 8, "the epilogue stages one tile of rows in a stage buffer");
@@ -88,8 +90,11 @@ struct Geo {
 // is a (P x 8) x (8 x 8) product, i.e. two mma.m8n8k4 per 8 block-rows p: M = p, K = s, N = r.  A warp owns
 // T interleaved 8-row-block tiles (tile t holds p = P0 + t + T*k, k = 0..7), so the A fragment of tile t at
 // column block m is the A fragment of tile t-1 at block m-1: ONE new LDS.128 per column block feeds 2T DMMAs.
-template <int T_, int TD_, int CTAS_>
+template <int T_, int TD_, int CTAS_, bool BULK_ = false>
 struct MGeo {
+    // BULK: units are staged with cp.async.bulk (the TMA engine's 1-D copies: one 64-byte copy per window row, one copy
+    // for the field chunk) completing on an mbarrier, instead of 16-byte cp.async per thread
+    static constexpr bool BULK = BULK_;
     static constexpr int T = T_;                 // interleaved tiles per warp
     static constexpr int R = 2 * T;              // accumulator doubles per thread
     static constexpr int TD = TD_;               // columns per unit
@@ -100,12 +105,15 @@ struct MGeo {
     static constexpr int TI = WARPS * 64 * T;    // rows per tile
     static constexpr int PADF = TI + TD;         // zero padding in front of padded fields and c tables
     static constexpr int NU = (TI + TD) / 8;     // 8-distance rows of the c window
-    static constexpr int ROW_STRIDE = 80;        // 64 B of data + 16 B: LDS.128 of 8 lanes x (k, k+1) conflict free for T = 4
+    // cp.async staging: 64 B of data + 16 B of padding per window row (LDS.128 of 8 lanes x (k, k+1) conflict free for
+    // T = 4).  BULK staging: dense 64-byte rows, the conflict-free placement comes from the table's own row swizzle
+    // (frx_table_slot, c_perm = 2): the window is ONE bulk copy.
+    static constexpr int ROW_STRIDE = BULK_ ? 64 : 80;
     static constexpr int CWIN_BYTES = NU * ROW_STRIDE;
     static constexpr int GCH_ELEMS = TD + 8;     // 8-element halo in front (B fragments reach back 7)
     static constexpr int STAGE_BYTES = (CWIN_BYTES + GCH_ELEMS * 8 + 64 + 127) / 128 * 128;   // + 64: see compute_unit_mma
     static constexpr int C_PAD = PADF;
-    static constexpr int C_PERM = 1;
+    static constexpr int C_PERM = BULK_ ? 2 : 1;
     static constexpr bool TENSOR = true;
     // epilogue operands (w0 and mult of the tile's rows) are prefetched into shared memory together with the unit that
     // ends a tile or a span, one buffer per stage, when the shared-memory budget allows (<= 2 CTAs per SM)
@@ -254,6 +262,47 @@ __device__ inline void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+__device__ inline unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ inline void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ inline void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ inline void bulk_copy(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// BULK staging of one unit: the same bytes to the same places as stage_unit_mma
+template <class G>
+__device__ inline void stage_unit_bulk(const HistParams& p, const Cursor& c, char* stage, unsigned long long* bar) {
+    const int64_t pass = c.pass, j0 = c.chunk * G::TD, q = c.q, a = c.a, f = c.f;
+    const int64_t d_base = c.I * G::TI - j0 - G::TD;
+    const double* csrc = p.tabs + ((a * p.n_sub + q) * p.n_pass + pass) * p.ldc + G::C_PAD + d_base;
+    const int64_t fg = p.paired ? a * p.n_fields + f : f;
+    const double* gsrc = p.gp + (fg * p.n_pass + pass) * p.ldgp + G::PADF + j0 - 8;
+    const int t = threadIdx.x;
+    // the buffer was last touched through the generic proxy (operand loads, epilogue scratch)
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (t == 0) {   // two copies per unit, issued by one thread
+        mbar_expect_tx(bar, (unsigned)(G::CWIN_BYTES + G::GCH_ELEMS * 8));
+        bulk_copy(stage, csrc, (unsigned)G::CWIN_BYTES, bar);
+        bulk_copy(stage + G::CWIN_BYTES, gsrc, (unsigned)(G::GCH_ELEMS * 8), bar);
+    }
+}
+
 // tensor variant: unit = TI rows x TD columns [j0, j0+TD).  Stage the c window (all distances i - j of the unit,
 // as NU rows of 8, in the table's permuted order) and the column chunk of the padded field (+8 halo).
 template <class G>
@@ -285,33 +334,75 @@ __device__ inline void compute_unit_mma(double (&acc)[G::R], const char* stage, 
     constexpr int T = G::T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = lane >> 2, sp = lane & 3;
-    // A fragments: row (8T*warp + t + MC - mi + T*k) of the c window, 16 bytes at 16*s' = {c[..+s'], c[..+s'+4]}
-    const char* arow = stage + (8 * T * warp + G::MC + T * k) * G::ROW_STRIDE + 16 * sp;
     // B fragments: g[8m + k - s' - 4kh] = gch[8 + 8mi + k - s' - 4kh]
     const double* gch = reinterpret_cast<const double*>(stage + G::CWIN_BYTES) + (4 + k - sp);
     double2 af[T];
+    if constexpr (!G::BULK) {
+        // A fragments: row (8T*warp + t + MC - mi + T*k) of the c window, 16 bytes at 16*s' = {c[..+s'], c[..+s'+4]}
+        const char* arow = stage + (8 * T * warp + G::MC + T * k) * G::ROW_STRIDE + 16 * sp;
 #pragma unroll
-    for (int t = 1; t < T; ++t) af[t] = *reinterpret_cast<const double2*>(arow + (t - s0 * T) * G::ROW_STRIDE);
-    // operands of the first block
-    double2 a_nxt = *reinterpret_cast<const double2*>(arow - (s0 * T) * G::ROW_STRIDE);
-    double b1_nxt = gch[8 * s0 * T], b0_nxt = gch[8 * s0 * T + 4];
+        for (int t = 1; t < T; ++t) af[t] = *reinterpret_cast<const double2*>(arow + (t - s0 * T) * G::ROW_STRIDE);
+        // operands of the first block
+        double2 a_nxt = *reinterpret_cast<const double2*>(arow - (s0 * T) * G::ROW_STRIDE);
+        double b1_nxt = gch[8 * s0 * T], b0_nxt = gch[8 * s0 * T + 4];
 #pragma unroll 1
-    for (int mg = s0 * T; mg < s1 * T; mg += T) {
+        for (int mg = s0 * T; mg < s1 * T; mg += T) {
 #pragma unroll
-        for (int j = 0; j < T; ++j) {
-            const int mi = mg + j;
-            // tile t uses slot (t - mi) mod T; the new fragment (tile 0) replaces the one tile T-1 used last time
-            af[(T - j) % T] = a_nxt;
-            const double b1 = b1_nxt, b0 = b0_nxt;
-            // next block (one past the unit's last block reads valid but unused shared memory: the window row below
-            // and the 64 bytes of padding behind the field chunk)
-            a_nxt = *reinterpret_cast<const double2*>(arow - (mi + 1) * G::ROW_STRIDE);
-            b1_nxt = gch[8 * (mi + 1)];
-            b0_nxt = gch[8 * (mi + 1) + 4];
+            for (int j = 0; j < T; ++j) {
+                const int mi = mg + j;
+                // tile t uses slot (t - mi) mod T; the new fragment (tile 0) replaces the one tile T-1 used last time
+                af[(T - j) % T] = a_nxt;
+                const double b1 = b1_nxt, b0 = b0_nxt;
+                // next block (one past the unit's last block reads valid but unused shared memory: the window row
+                // below and the 64 bytes of padding behind the field chunk)
+                a_nxt = *reinterpret_cast<const double2*>(arow - (mi + 1) * G::ROW_STRIDE);
+                b1_nxt = gch[8 * (mi + 1)];
+                b0_nxt = gch[8 * (mi + 1) + 4];
 #pragma unroll
-            for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].x, b0);
+                for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].x, b0);
 #pragma unroll
-            for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].y, b1);
+                for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].y, b1);
+            }
+        }
+    } else {
+        // dense window (64-byte rows): row u sits at u ^ ((u >> 2) & 1) (frx_table_slot).  The four rows U-4 .. U-1 that
+        // one loop iteration loads (U = ubase - mg, a multiple of 4) share that bit, which alternates from one
+        // iteration to the next: byte offsets {0,64,128,192} from row U-4, XORed with x = 64 * bit, i.e. constant
+        // offsets from the two pointers base + x and base - x.
+        static_assert(T == 4, "row swizzle of the dense window is laid out for T = 4");
+        const int ubase = 8 * T * warp + G::MC + T * k;
+        const char* abase = stage + 16 * sp;
+        const int U0 = ubase - s0 * T;                         // multiple of 4
+        {
+            const int x0 = ((U0 >> 2) & 1) * 64;               // rows U0 .. U0+3
+            const char* q = abase + U0 * 64;
+#pragma unroll
+            for (int t = 1; t < T; ++t) af[t] = *reinterpret_cast<const double2*>(q + ((t * 64) ^ x0));
+        }
+        double2 a_nxt = *reinterpret_cast<const double2*>(abase + (U0 ^ ((U0 >> 2) & 1)) * 64);
+        double b1_nxt = gch[8 * s0 * T], b0_nxt = gch[8 * s0 * T + 4];
+        const char* base = abase + (U0 - 4) * 64;              // row U-4 of the current iteration
+        int x = (((U0 - 4) >> 2) & 1) * 64;
+#pragma unroll 1
+        for (int mg = s0 * T; mg < s1 * T; mg += T) {
+            const char* pp = base + x;                         // offsets with bit 6 clear: (c ^ x) = c + x
+            const char* pm = base - x;                         // offsets with bit 6 set:   (c ^ x) = c - x
+#pragma unroll
+            for (int j = 0; j < T; ++j) {
+                const int mi = mg + j;
+                af[(T - j) % T] = a_nxt;
+                const double b1 = b1_nxt, b0 = b0_nxt;
+                constexpr int kRowOff[4] = {192, 128, 64, 0};  // row U-1-j relative to row U-4
+                a_nxt = *reinterpret_cast<const double2*>(((kRowOff[j] & 64) ? pm : pp) + kRowOff[j]);
+                b1_nxt = gch[8 * (mi + 1)];
+                b0_nxt = gch[8 * (mi + 1) + 4];
+#pragma unroll
+                for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].x, b0);
+#pragma unroll
+                for (int t = 0; t < T; ++t) dmma884(acc[2 * t], acc[2 * t + 1], af[(t - j + T) % T].y, b1);
+            }
+            base -= 4 * 64;
+            x ^= 64;
         }
     }
 }
@@ -491,6 +582,7 @@ template <class G>
 __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const HistParams p) {
     extern __shared__ __align__(128) char smem[];
     __shared__ int s_last;
+    __shared__ __align__(8) unsigned long long full_bar[2];   // BULK: "unit landed" barriers of the two stage buffers
     constexpr int R = G::R;
     // spans are cut at sub-step granularity (groups of T column blocks for the tensor variant): every CTA gets
     // total_groups / grid groups to within one, so a span may start and end in the middle of a unit
@@ -513,23 +605,43 @@ __global__ void __launch_bounds__(kNT, G::CTAS_PER_SM) frx_k2_history_main(const
     bool from_start = (cur.v == 0 && gbeg == ubeg * G::SUBS);
     const bool wpref = G::WBUF_BYTES > 0 && !p.raw && p.n_sub == 1;
     double* const wbufs = reinterpret_cast<double*>(smem + 2 * G::STAGE_BYTES);
-    stage_unit<G>(p, cur, smem);
+    if constexpr (G::BULK) {
+        if (threadIdx.x == 0) {
+            mbar_init(&full_bar[0], 1);
+            mbar_init(&full_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+        stage_unit_bulk<G>(p, cur, smem, &full_bar[0]);
+    } else {
+        stage_unit<G>(p, cur, smem);
+    }
     if (wpref && (cur.v + 1 == cur.units || ubeg + 1 == uend)) stage_epilogue_operands<G>(p, cur, wbufs);
     cp_async_commit();
     for (int64_t u = ubeg; u < uend; ++u) {
         char* stage = smem + ((u - ubeg) & 1) * G::STAGE_BYTES;
         if (u + 1 < uend) {
             cursor_advance<G>(p, nxt);
+            if constexpr (G::BULK) {
+                stage_unit_bulk<G>(p, nxt, smem + ((u + 1 - ubeg) & 1) * G::STAGE_BYTES, &full_bar[(u + 1 - ubeg) & 1]);
+            } else {
 #ifdef FRX_K2_TRACE
-            if (!(frx_k2_debug_mode & 1))
+                if (!(frx_k2_debug_mode & 1))
 #endif
-            stage_unit<G>(p, nxt, smem + ((u + 1 - ubeg) & 1) * G::STAGE_BYTES);
+                stage_unit<G>(p, nxt, smem + ((u + 1 - ubeg) & 1) * G::STAGE_BYTES);
+            }
             if (wpref && (nxt.v + 1 == nxt.units || u + 2 == uend))
                 stage_epilogue_operands<G>(p, nxt, wbufs + ((u + 1 - ubeg) & 1) * (G::WBUF_BYTES / 8));
         }
         cp_async_commit();
         cp_async_wait<1>();
-        __syncthreads();
+        if constexpr (G::BULK) {
+            // every thread waits for the unit itself (the async writes are visible to a thread that saw the phase
+            // complete); buffer (u - ubeg) & 1 is used for the ((u - ubeg) >> 1)-th time
+            mbar_wait(&full_bar[(u - ubeg) & 1], (unsigned)(((u - ubeg) >> 1) & 1));
+        } else {
+            __syncthreads();
+        }
 #ifdef FRX_K2_TRACE
         if (u == ubeg) FRX_TRACE(2);
         if (u + 1 == uend) FRX_TRACE(3);
@@ -659,8 +771,7 @@ __global__ void __launch_bounds__(FRX_TAB_BLOCK, 8) frx_k12_prepare(int rule, co
             double* cA = tabs + a * ldc;
             if (x < 0) cA[X] = 0.0;
             else
-                cA[c_perm ? c_pad + (x & ~(int64_t)7) + ((x & 3) * 2 + ((x >> 2) & 1)) : c_pad + x] =
-                    x < N ? raw_c[a * raw_ldc + x] : 0.0;
+                cA[frx_table_slot(c_pad, c_perm, x)] = x < N ? raw_c[a * raw_ldc + x] : 0.0;
             return;
         }
         // tables of alpha a: n_tab_per_alpha consecutive tables of ldc entries (1; 'simpson': the 4 decimated ones)
@@ -845,10 +956,10 @@ static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, c
                             int64_t n_fields, const double* d_g, int64_t ldg, double* d_y, int64_t ldy,
                             const PeerTargets* peers = nullptr, const void* raw_spec = nullptr) {
     if (raw_spec)
-        return history_impl<MGeo<4, 1024, 2>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, nullptr,
-                                              (const RawSpec*)raw_spec);
+        return history_impl<MGeo<4, 1024, 2, true>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, nullptr,
+                                                    (const RawSpec*)raw_spec);
     // tile geometry: FRX_K2_VARIANT is a tuning/experiment switch, the default is the measured best
-    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 10;
+    static const int variant = getenv("FRX_K2_VARIANT") ? atoi(getenv("FRX_K2_VARIANT")) : 11;
     switch (variant) {
         case 0: return history_impl<Geo<8, 256, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 1: return history_impl<Geo<16, 128, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
@@ -857,8 +968,9 @@ static int history_dispatch(frx_ctx* ctx, int rule, int side, int64_t n_alpha, c
         case 6: return history_impl<MGeo<4, 512, 3>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 7: return history_impl<MGeo<4, 512, 2>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 8: return history_impl<MGeo<4, 512, 1>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        case 10: return history_impl<MGeo<4, 1024, 2>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
         case 9: return history_impl<MGeo<4, 512, 4>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
-        default: return history_impl<MGeo<4, 1024, 2>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
+        default: return history_impl<MGeo<4, 1024, 2, true>>(ctx, rule, side, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy, peers);
     }
 }
 

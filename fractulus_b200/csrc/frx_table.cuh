@@ -14,6 +14,18 @@
 #pragma once
 #include "frx_rules.cuh"
 
+// Storage slot of distance d in a weight table.  c_perm = 0: natural order.  c_perm >= 1 (DMMA history kernel): every
+// aligned group of 8 distances is stored as [0 4 1 5 2 6 3 7].  c_perm = 2 (bulk-staged geometry): additionally the
+// 8-distance rows R and R^1 are swapped where bit 2 of R is set, so that a window copied densely into shared memory
+// (64-byte rows, no padding) is read without bank conflicts by the A-fragment LDS.128 pattern (rows 4 apart per lane
+// group).  c_pad is a multiple of 64, so the pattern is the same in table and window coordinates.
+__host__ __device__ inline long long frx_table_slot(int c_pad, int c_perm, long long d) {
+    if (!c_perm) return c_pad + d;
+    long long R = (c_pad + d) >> 3;
+    if (c_perm == 2) R ^= (R >> 2) & 1;
+    return R * 8 + ((d & 3) * 2 + ((d >> 2) & 1));
+}
+
 constexpr int FRX_TAB_THREADS = 128;              // threads per CTA: one power base / table entry each
 constexpr int FRX_TAB_BLOCK = FRX_TAB_THREADS;
 constexpr int FRX_TAB_HALO = 2;
@@ -150,7 +162,7 @@ __device__ __forceinline__ void frx_table_block(frx_table_smem& S, const frx_alp
         if (rule == FRX_R_SIMPSON) cb = frx_raw_toeplitz_pw(P, xd, false, pw);
     }
     // the DMMA history kernel wants every aligned group of 8 distances stored as [0 4 1 5 2 6 3 7]
-    auto slot_of = [&](int64_t d) { return c_perm ? c_pad + (d & ~(int64_t)7) + ((d & 3) * 2 + ((d >> 2) & 1)) : c_pad + d; };
+    auto slot_of = [&](int64_t d) { return (int64_t)frx_table_slot(c_pad, c_perm, d); };
     if (!dec) {
         cA[slot_of(x)] = ca;
         if (cB) cB[slot_of(x)] = cb;

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) frx_k1_gl_table(const double* __restrict_
     if (threadIdx.x == 0 && cm1) cm1[a] = 0.0;
     __syncthreads();
     frx_gl_block<256>(GS, alpha[a], N + 1, [&](long long x, double w) {
-        if (x < N) ca[c_perm ? c_pad + (x & ~7LL) + ((x & 3) * 2 + ((x >> 2) & 1)) : c_pad + x] = w;
+        if (x < N) ca[frx_table_slot(c_pad, c_perm, x)] = w;
         double m = 0.0, wf = 0.0;
         if (x >= 1) {
             const double xd = (double)x, step = FRX_DIV(FRX_MUL(xd, h), xd);
