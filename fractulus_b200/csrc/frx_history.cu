@@ -11,7 +11,8 @@
 //     (alpha, field, [row parity], row tile, pass, chunk) and dealt in contiguous spans, cut at sub-unit granularity, to
 //     a grid of exactly sm_count * CTAS_PER_SM persistent CTAs (stream-K); dynamic shared memory is sized so that
 //     exactly CTAS_PER_SM CTAs fit on an SM (all CTAs resident, evenly spread).
-//   * tables and field chunks are staged global -> shared with 16-byte cp.async into a double buffer.
+//   * tables and field chunks are staged global -> shared into a double buffer: by two cp.async.bulk copies per unit (TMA
+//     engine, completion on an mbarrier) in the default geometry, by 16-byte cp.async in the others.
 //   * the triangular edge is handled by zero padding (tables have zeros for negative distances, the prepare kernel makes
 //     a zero-padded copy of every field), so the inner loops have no predicates.
 //   * a row tile finished inside one CTA is scaled and written directly; a tile split between CTAs goes through per-CTA
