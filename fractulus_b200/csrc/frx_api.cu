@@ -40,23 +40,38 @@ extern "C" int frx_ctx_create(int device, frx_ctx** out) {
         return FRX_ERR_NO_DEVICE;
     }
     FRX_REQUIRE(device >= 0 && device < n, FRX_ERR_INVALID_ARG, "device index out of range");
-    FRX_CUDA(cudaSetDevice(device));
     frx_ctx* c = (frx_ctx*)calloc(1, sizeof(frx_ctx));
     FRX_REQUIRE(c != nullptr, FRX_ERR_ALLOC, "host allocation failed");
     c->device = device;
-    FRX_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     c->stream = 0;
-    FRX_CUDA(cudaMalloc(&c->scalars, 256));
+    frx_device_guard guard(device);
+    cudaError_t e = guard.err;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&c->scalars, 256);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->hstage_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->switch_ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        frx_set_error("context creation on device %d failed: %s", device, cudaGetErrorString(e));
+        if (c->scalars) cudaFree(c->scalars);
+        if (c->hstage_ev) cudaEventDestroy(c->hstage_ev);
+        if (c->switch_ev) cudaEventDestroy(c->switch_ev);
+        free(c);
+        return FRX_ERR_CUDA;
+    }
     *out = c;
     return FRX_OK;
 }
 
 extern "C" int frx_ctx_destroy(frx_ctx* ctx) {
     if (!ctx) return FRX_OK;
-    cudaSetDevice(ctx->device);
+    frx_device_guard guard(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->scalars) cudaFree(ctx->scalars);
+    if (ctx->hstage) cudaFreeHost(ctx->hstage);
+    if (ctx->hstage_ev) cudaEventDestroy(ctx->hstage_ev);
+    if (ctx->switch_ev) cudaEventDestroy(ctx->switch_ev);
     for (int i = 0; i < FRX_EV_POOL; ++i) {
         if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
         if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
@@ -65,15 +80,53 @@ extern "C" int frx_ctx_destroy(frx_ctx* ctx) {
     return FRX_OK;
 }
 
+// The context owns one workspace, one io buffer and one scalars block, so everything it queues must execute in
+// order.  Within one stream that is the stream's order; when the caller moves the context to another stream,
+// an event recorded on the old stream (covering all work queued so far) is made a dependency of the new one.
 extern "C" int frx_ctx_set_stream(frx_ctx* ctx, void* s) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    ctx->stream = (cudaStream_t)s;
+    cudaStream_t ns = (cudaStream_t)s;
+    if (ns == ctx->stream) return FRX_OK;
+    FRX_ON_DEVICE(ctx);
+    FRX_CUDA(cudaEventRecord(ctx->switch_ev, ctx->stream));
+    FRX_CUDA(cudaStreamWaitEvent(ns, ctx->switch_ev, 0));
+    ctx->stream = ns;
+    return FRX_OK;
+}
+
+int frx_hstage_reserve(frx_ctx* ctx, size_t bytes) {
+    FRX_ON_DEVICE(ctx);
+    if (ctx->hstage_pending) {
+        FRX_CUDA(cudaEventSynchronize(ctx->hstage_ev));
+        ctx->hstage_pending = 0;
+    }
+    if (bytes <= ctx->hstage_bytes) return FRX_OK;
+    if (ctx->hstage) {
+        FRX_CUDA(cudaFreeHost(ctx->hstage));
+        ctx->hstage = nullptr;
+        ctx->hstage_bytes = 0;
+    }
+    const size_t want = frx_align_up(bytes + bytes / 8, (size_t)1 << 16);
+    cudaError_t e = cudaMallocHost(&ctx->hstage, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ctx->hstage = nullptr;
+        frx_set_error("pinned staging allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        return FRX_ERR_ALLOC;
+    }
+    ctx->hstage_bytes = want;
+    return FRX_OK;
+}
+
+int frx_hstage_release(frx_ctx* ctx) {
+    FRX_CUDA(cudaEventRecord(ctx->hstage_ev, ctx->stream));
+    ctx->hstage_pending = 1;
     return FRX_OK;
 }
 
 extern "C" int frx_ctx_synchronize(frx_ctx* ctx) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     FRX_CUDA(cudaStreamSynchronize(ctx->stream));
     return FRX_OK;
 }
@@ -121,7 +174,7 @@ int frx_timing_flush(frx_ctx* ctx) {
 
 extern "C" int frx_ctx_set_timing(frx_ctx* ctx, int on) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     int rc = frx_timing_flush(ctx);
     if (rc) return rc;
     ctx->timing = on ? 1 : 0;
@@ -136,7 +189,7 @@ extern "C" int frx_ctx_set_timing(frx_ctx* ctx, int on) {
 
 extern "C" int frx_ctx_kernel_times(frx_ctx* ctx, double* ms, int64_t* calls) {
     FRX_REQUIRE(ctx && ms && calls, FRX_ERR_INVALID_ARG, "NULL argument");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     int rc = frx_timing_flush(ctx);
     if (rc) return rc;
     for (int k = 0; k < FRX_K_COUNT; ++k) {
@@ -148,7 +201,7 @@ extern "C" int frx_ctx_kernel_times(frx_ctx* ctx, double* ms, int64_t* calls) {
 
 int frx_ws_reserve(frx_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return FRX_OK;
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     if (ctx->ws) {
         FRX_CUDA(cudaStreamSynchronize(ctx->stream));
         FRX_CUDA(cudaFree(ctx->ws));
@@ -168,7 +221,7 @@ int frx_ws_reserve(frx_ctx* ctx, size_t bytes) {
 
 int frx_io_reserve(frx_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->io_bytes) return FRX_OK;
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     if (ctx->io) {
         FRX_CUDA(cudaStreamSynchronize(ctx->stream));
         FRX_CUDA(cudaFree(ctx->io));

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) frx_probe_dmma(double* out, int iters, do
 // best-of-`repeats` sustained FP64 throughput in TFLOP/s of (a) the DFMA pipe, (b) mma.sync m8n8k4 f64
 extern "C" int frx_measure_fp64_peak(frx_ctx* ctx, int repeats, double* tflops_dfma, double* tflops_dmma) {
     FRX_REQUIRE(ctx && tflops_dfma && tflops_dmma && repeats > 0, FRX_ERR_INVALID_ARG, "bad argument");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
     int rc = frx_ws_reserve(ctx, sizeof(double) * (size_t)blocks * threads);
     if (rc) return rc;

@@ -55,7 +55,7 @@ extern "C" int frx_stencil_compose(frx_ctx* ctx, int64_t n_items, const int64_t*
     if (n_items == 0 || total_c == 0) return FRX_OK;
     FRX_REQUIRE(d_ptr_a && d_off_a && d_w_a && d_ptr_b && d_off_b && d_w_b && d_ptr_c && d_off_c && d_w_c, FRX_ERR_INVALID_ARG,
                 "NULL buffer");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     int64_t blocks = (total_c + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;

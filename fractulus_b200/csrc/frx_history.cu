@@ -990,7 +990,7 @@ extern "C" int frx_history_sided(frx_ctx* ctx, int rule, int side, int64_t n_alp
                 "field too short (needs N+1 nodes, N+2 for 'simpson') or leading dimension too small");
     if (n_alpha == 0 || n_fields == 0) return FRX_OK;
     FRX_REQUIRE(d_alpha && d_g && d_y, FRX_ERR_INVALID_ARG, "NULL buffer");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     if (side == FRX_SIDE_RIESZ_CAPUTO) {   // K * (left + (-1.)**n * right): the left pass leaves its result in y
         int rc = history_dispatch(ctx, rule, FRX_SIDE_LEFT, n_alpha, d_alpha, h, N, n_fields, d_g, ldg, d_y, ldy);
         if (rc) return rc;
@@ -1016,7 +1016,7 @@ extern "C" int frx_history_gather(frx_ctx* ctx, int rule, int64_t n_alpha, const
                 "field too short (needs N+1 nodes, N+2 for 'simpson') or leading dimension too small");
     if (n_alpha == 0 || n_fields == 0) return FRX_OK;
     FRX_REQUIRE(d_alpha && d_g, FRX_ERR_INVALID_ARG, "NULL buffer");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     PeerTargets pt;
     pt.n_peers = n_peers;
     pt.row0 = row0;
@@ -1051,7 +1051,7 @@ extern "C" int frx_toeplitz_product(frx_ctx* ctx, int64_t n_seq, const double* d
     FRX_REQUIRE(ldc >= N && ldg >= N && ldy >= N, FRX_ERR_INVALID_ARG, "leading dimension too small");
     if (n_seq == 0 || n_fields == 0) return FRX_OK;
     FRX_REQUIRE(d_c && d_g && d_y, FRX_ERR_INVALID_ARG, "NULL buffer");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     // the kernel's rows and columns are numbered from 1 (node 0 is the first-column term, absent here)
     return frx_toeplitz_raw(ctx, n_seq, d_c, ldc, N, n_fields, paired, d_g - 1, ldg, scale, d_y - 1, ldy, n_cols);
 }
@@ -1063,7 +1063,7 @@ extern "C" int frx_toeplitz_apply(frx_ctx* ctx, int rule, double alpha, double h
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
     int rc = frx_check_rule_alpha(rule, alpha);
     if (rc) return rc;
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     FRX_CUDA(cudaMemcpyAsync(ctx->scalars, &alpha, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     return frx_history(ctx, rule, 1, (const double*)ctx->scalars, h, N, n_fields, d_G, ldg, n_g, d_Y, ldy);
 }
@@ -1102,7 +1102,7 @@ extern "C" int frx_history_host(frx_ctx* ctx, int rule, int64_t n_alpha, const d
         return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
     };
     const double pt0 = prof ? now() : 0.0;
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     // FRX_HOST_ZERO_COPY: bit 0 = read the field in place, bit 1 = store the result in place
     static const int zero_copy = getenv("FRX_HOST_ZERO_COPY") ? atoi(getenv("FRX_HOST_ZERO_COPY")) : 3;
     const double* map_g = (zero_copy & 1) ? (const double*)mapped_device_pointer(h_g) : nullptr;

@@ -19,6 +19,14 @@ struct frx_ctx {
     void* io;
     size_t io_bytes;
     void* scalars;         // 256 bytes of device memory for by-value scalar arguments
+    // grow-only pinned host staging block for batches of host-side parameters (frx_hstage_reserve / _release):
+    // filled by the host, uploaded with one async copy, reused only after the event behind that copy has fired
+    void* hstage;
+    size_t hstage_bytes;
+    cudaEvent_t hstage_ev;
+    int hstage_pending;
+    // cross-stream ordering: everything this context has queued is ordered before work on a newly set stream
+    cudaEvent_t switch_ev;
     // optional per-kernel CUDA-event timing (frx_ctx_set_timing): bench.py's roofline numbers
     int timing;
     int ev_n;
@@ -65,11 +73,40 @@ void frx_set_error(const char* fmt, ...);
 // ensure ctx->ws holds at least `bytes`; contents are NOT preserved on growth
 int frx_ws_reserve(frx_ctx* ctx, size_t bytes);
 int frx_io_reserve(frx_ctx* ctx, size_t bytes);
+// pinned staging: reserve waits for the previous upload out of the block (if any) and grows it; release records the
+// event after the caller has queued its copy on ctx->stream
+int frx_hstage_reserve(frx_ctx* ctx, size_t bytes);
+int frx_hstage_release(frx_ctx* ctx);
 // host-side domain check of one Settings triple against the reference's behaviour
 int frx_check_settings(int rule, double alpha, double resolution);
 int frx_check_rule_alpha(int rule, double alpha);
 
 static inline size_t frx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#ifdef __cplusplus
+// Entry points run on the context's device and leave the caller's current device as they found it.
+struct frx_device_guard {
+    int prev, target;
+    cudaError_t err;
+    explicit frx_device_guard(int device) : prev(-1), target(device), err(cudaSuccess) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        if (err != cudaSuccess) cudaGetLastError();
+    }
+    bool ok() const { return err == cudaSuccess; }
+    ~frx_device_guard() {
+        if (prev >= 0 && prev != target) cudaSetDevice(prev);
+    }
+};
+#define FRX_ON_DEVICE(ctx)                                                            \
+    frx_device_guard frx_guard_((ctx)->device);                                       \
+    do {                                                                              \
+        if (!frx_guard_.ok()) {                                                       \
+            frx_set_error("cudaSetDevice(%d) failed: %s", (ctx)->device, cudaGetErrorString(frx_guard_.err)); \
+            return FRX_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+#endif
 
 #ifdef __CUDACC__
 #include <utility>

@@ -175,7 +175,7 @@ extern "C" int frx_history_solve(frx_ctx* ctx, int rule, int64_t n_alpha, const 
     FRX_REQUIRE(ldf >= N + 1 && ldu >= N + 1, FRX_ERR_INVALID_ARG, "leading dimension too small (N+1 nodes)");
     if (n_alpha == 0) return FRX_OK;
     FRX_REQUIRE(d_alpha && d_f && d_u0 && d_u, FRX_ERR_INVALID_ARG, "NULL buffer");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     static const int variant = getenv("FRX_ODE_VARIANT") ? atoi(getenv("FRX_ODE_VARIANT")) : 0;
     const int64_t ldc = frx_table_ldc(N), ldw = N + 1, nblk = (N + kNB - 1) / kNB, ldb = nblk * kNB;
     // sequences of the Newton variant carry one pad element in front (the history kernel's node 0) and are a whole

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "frx_internal.h"
+#include "frx_solve_dmma.cuh"
 
 namespace {
 
@@ -202,6 +203,7 @@ constexpr int kStreamWarps = 1;   // one-warp CTAs pack shared memory best
 constexpr int kStreamMaxNb = 31;
 constexpr int kStreamMaxN = 256;
 constexpr int kStreamBins = 4;    // bins by nb = res + 1: <= 8, <= 16, <= 24, <= 31
+constexpr int kDefaultDmmaBins = 0xF;   // bins that run the blocked tensor-core kernel (frx_solve_dmma.cuh)
 __host__ __device__ inline int stream_c(int nb_max) { return 2 * nb_max + 1; }
 __host__ __device__ inline int stream_rs(int nb_max) { return ((stream_c(nb_max) + 7) & ~7) + 1; }   // ring padded to 8, +1 -> odd
 // window + band coefficients (+1 pad) + rhs, rounded to an even number of doubles
@@ -372,85 +374,115 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
 
 }  // namespace
 
+// launch geometry of one band-width bin: grid (persistent one-warp CTAs), dynamic shared memory, U scratch
+struct BinLaunch {
+    int64_t grid;
+    size_t dyn, scratch;
+    int kind;   // 0: frx_k4_band_stream, 1..4: frx_k4_band_dmma<2,3> / <3,5> / <4,7> / <5,9>
+};
+
+template <int RT, int CT>
+static int band_dmma_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, BinLaunch* out) {
+    using G = frx_k4::BandGeo<RT, CT>;
+    out->dyn = sizeof(double) * (size_t)G::smem_doubles(n);
+    FRX_CUDA(cudaFuncSetAttribute(frx_k4::frx_k4_band_dmma<RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->dyn));
+    int per_sm = 1;
+    FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4::frx_k4_band_dmma<RT, CT>, 32, out->dyn));
+    if (per_sm < 1) per_sm = 1;
+    out->grid = (int64_t)ctx->sm_count * per_sm;
+    if (out->grid > count) out->grid = count;
+    out->scratch = sizeof(double) * (size_t)out->grid * n * (2 * nb_bin + 1);
+    return FRX_OK;
+}
+
+template <int RT, int CT>
+static int band_dmma_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
+    FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_dmma<RT, CT><<<(unsigned)L.grid, 32, L.dyn, ctx->stream>>>(q));
+    return FRX_OK;
+}
+
 static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
                         const double* h_res, const double* d_rhs, int64_t ldb, double* d_x, int64_t ldx, int32_t* d_info,
                         double* d_dense) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
-    FRX_REQUIRE(n_sys >= 0 && n >= 1 && n <= 4096, FRX_ERR_INVALID_ARG, "bad n_sys / n");
+    FRX_REQUIRE(n_sys >= 0 && n_sys < ((int64_t)1 << 31) && n >= 1 && n <= 4096, FRX_ERR_INVALID_ARG, "bad n_sys / n");
     if (n_sys == 0) return FRX_OK;
     FRX_REQUIRE(h_alpha && h_h && h_res, FRX_ERR_INVALID_ARG, "NULL parameter array");
     FRX_REQUIRE(d_dense || (d_rhs && d_x && ldb >= n && ldx >= n), FRX_ERR_INVALID_ARG, "NULL buffer or bad leading dimension");
-    FRX_CUDA(cudaSetDevice(ctx->device));
-    // host pass: domain checks, stencil row pointers, storage requirement
-    int64_t* wptr = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_sys + 1));
-    double* lf = (double*)malloc(sizeof(double) * (size_t)n_sys);
-    FRX_REQUIRE(wptr && lf, FRX_ERR_ALLOC, "host allocation failed");
+    FRX_ON_DEVICE(ctx);
+    // One host pass (domain checks, stencil row pointers, band-width bins) into the context's pinned staging block,
+    // laid out like its device image:  [alpha | lf | res | h : 4 n_sys doubles][wptr : n_sys + 1][order : n_sys int32]
+    const size_t o_par = 0;
+    const size_t o_wptr = frx_align_up(sizeof(double) * 4 * (size_t)n_sys, 256);
+    const size_t o_order = o_wptr + frx_align_up(sizeof(int64_t) * (size_t)(n_sys + 1), 256);
+    const size_t stage_bytes = o_order + frx_align_up(sizeof(int32_t) * (size_t)n_sys, 256);
+    int rc = frx_hstage_reserve(ctx, stage_bytes);
+    if (rc) return rc;
+    char* hs = (char*)ctx->hstage;
+    double* s_par = (double*)(hs + o_par);
+    int64_t* wptr = (int64_t*)(hs + o_wptr);
+    int32_t* h_order = (int32_t*)(hs + o_order);
+    auto bin_of = [](int nb_a) { return nb_a <= 8 ? 0 : nb_a <= 16 ? 1 : nb_a <= 24 ? 2 : 3; };
+    int64_t bin_count[kStreamBins] = {0, 0, 0, 0}, bin_begin[kStreamBins + 1];
+    int bin_nb[kStreamBins] = {0, 0, 0, 0};
     wptr[0] = 0;
-    int max_store = 0, max_res = 0, rc = FRX_OK;
-    for (int64_t s = 0; s < n_sys && !rc; ++s) {
+    int max_store = 0, max_res = 0;
+    for (int64_t s = 0; s < n_sys; ++s) {
         int32_t first, count;
         rc = frx_stencil_layout(rule, FRX_SIDE_RIESZ_CAPUTO, h_alpha[s], h_res[s], &first, &count);
-        if (!rc && !(h_h[s] > 0.0)) { frx_set_error("grid step must be positive"); rc = FRX_ERR_DOMAIN; }
-        if (!rc && (rule == FRX_RULE_SIMPSON && ((int64_t)h_res[s] & 1))) {
+        if (rc) return rc;
+        if (!(h_h[s] > 0.0)) { frx_set_error("grid step must be positive"); return FRX_ERR_DOMAIN; }
+        if (rule == FRX_RULE_SIMPSON && ((int64_t)h_res[s] & 1)) {
             frx_set_error("'simpson' with odd resolution has a node right of the point; use an even resolution here");
-            rc = FRX_ERR_DOMAIN;
+            return FRX_ERR_DOMAIN;
         }
-        if (rc) break;
         wptr[s + 1] = wptr[s] + count;
-        lf[s] = h_res[s] * h_h[s];
-        int res = (count - 1) / 2, nb = res + 1 > n - 1 ? n - 1 : res + 1;   // res = stencil half-width
-        int store = d_dense ? 0 : ((3 * nb + 1 < n) ? n * (3 * nb + 1) : n * n);  // band columns are 3nb+1 long
+        s_par[s] = h_alpha[s];
+        s_par[n_sys + s] = h_res[s] * h_h[s];
+        s_par[2 * n_sys + s] = h_res[s];
+        s_par[3 * n_sys + s] = h_h[s];
+        const int res = (count - 1) / 2, nb_a = res + 1, nb = nb_a > n - 1 ? n - 1 : nb_a;   // res = stencil half-width
+        const int store = d_dense ? 0 : ((3 * nb + 1 < n) ? n * (3 * nb + 1) : n * n);      // band columns are 3nb+1 long
         if (store > max_store) max_store = store;
         if (res > max_res) max_res = res;
+        const int b = bin_of(nb_a);
+        ++bin_count[b];
+        if (nb_a > bin_nb[b]) bin_nb[b] = nb_a;
     }
-    if (rc) { free(wptr); free(lf); return rc; }
+    bin_begin[0] = 0;
+    for (int b = 0; b < kStreamBins; ++b) bin_begin[b + 1] = bin_begin[b] + bin_count[b];
+    {
+        int64_t fill[kStreamBins] = {bin_begin[0], bin_begin[1], bin_begin[2], bin_begin[3]};
+        for (int64_t s = 0; s < n_sys; ++s) h_order[fill[bin_of((int)((wptr[s + 1] - wptr[s] - 1) / 2) + 1)]++] = (int32_t)s;
+    }
+    const int64_t total_w = wptr[n_sys];
     const int a_len = (2 * (max_res + 1) + 1 + 1) & ~1;
     const size_t smem = sizeof(double) * ((size_t)((max_store + 1) & ~1) + n + a_len) + sizeof(int) * (size_t)(n + 4);
-    int smem_max = 0;
-    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
-    if (!d_dense && smem > (size_t)smem_max) {
-        free(wptr); free(lf);
-        frx_set_error("system too large for shared memory: needs %zu bytes, device offers %d (n = %d, max resolution %d)",
-                      smem, smem_max, n, max_res);
-        return FRX_ERR_INVALID_ARG;
-    }
-    // workspace: [alpha | lf | res | h][wptr][rc weights]
-    size_t off = 0;
+    // workspace: [staging image][rc weights][K5 scalars]
+    size_t off = stage_bytes;
     auto carve = [&](size_t bytes) { size_t o = off; off += frx_align_up(bytes, 256); return o; };
-    const size_t o_par = carve(sizeof(double) * 4 * (size_t)n_sys);
-    const size_t o_wptr = carve(sizeof(int64_t) * (size_t)(n_sys + 1) * 2);
-    const size_t o_w = carve(sizeof(double) * (size_t)wptr[n_sys]);
+    const size_t o_w = carve(sizeof(double) * (size_t)total_w);
     extern size_t frx_k5_scratch_bytes(int64_t);
     const size_t o_k5 = carve(frx_k5_scratch_bytes(n_sys));
-    const int64_t total_w = wptr[n_sys];
     rc = frx_ws_reserve(ctx, off);
-    if (rc) { free(wptr); free(lf); return rc; }
+    if (rc) return rc;
     char* ws = (char*)ctx->ws;
     double* d_par = (double*)(ws + o_par);
-    cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, h_alpha, sizeof(double) * n_sys, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + n_sys, lf, sizeof(double) * n_sys, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + 2 * n_sys, h_res, sizeof(double) * n_sys, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_par + 3 * n_sys, h_h, sizeof(double) * n_sys, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + o_wptr, wptr, sizeof(int64_t) * (n_sys + 1), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // host staging arrays are freed below
-    if (e != cudaSuccess) {
-        free(wptr); free(lf);
-        frx_set_error("parameter upload failed: %s", cudaGetErrorString(e));
-        return FRX_ERR_CUDA;
-    }
+    FRX_CUDA(cudaMemcpyAsync(ws, hs, stage_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = frx_hstage_release(ctx);     // event after the copy: the staging block is reused only once it has been read
+    if (rc) return rc;
     // K5 for the whole batch (row pointer already on the device)
     extern int frx_launch_stencil_weights(frx_ctx*, int, int, int64_t, const double*, const double*, const double*,
                                           const int64_t*, int64_t, void*, int32_t*, double*);
     rc = frx_launch_stencil_weights(ctx, rule, FRX_SIDE_RIESZ_CAPUTO, n_sys, d_par, d_par + n_sys, d_par + 2 * n_sys,
                                     (const int64_t*)(ws + o_wptr), total_w, ws + o_k5, nullptr, (double*)(ws + o_w));
-    free(lf);
-    if (rc) { free(wptr); return rc; }
-    // every band narrow enough: one warp per system, window in shared memory, U streamed through L2
-    static const int force_cta = getenv("FRX_K4_VARIANT") ? atoi(getenv("FRX_K4_VARIANT")) == 1 : 0;
-    if (!d_dense && !force_cta && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
-        // bins by band width (counting sort on the host; wptr is still alive here)
-        StreamParams q;
+    if (rc) return rc;
+    // FRX_K4_VARIANT: 1 = CTA-per-system kernel for everything, 2 = column-at-a-time warp kernel for every bin;
+    // FRX_K4_DMMA_BINS: bit b set = bin b runs the blocked tensor-core kernel (default: see kDefaultDmmaBins)
+    static const int variant = getenv("FRX_K4_VARIANT") ? atoi(getenv("FRX_K4_VARIANT")) : 0;
+    static const int dmma_bins = variant == 2 ? 0 : (getenv("FRX_K4_DMMA_BINS") ? atoi(getenv("FRX_K4_DMMA_BINS")) : kDefaultDmmaBins);
+    if (!d_dense && variant != 1 && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
+        frx_k4::BandParams q;
         q.n = n;
         q.rcw = (const double*)(ws + o_w);
         q.wptr = (const int64_t*)(ws + o_wptr);
@@ -460,60 +492,64 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.x = d_x;
         q.ldx = ldx;
         q.info = d_info;
-        int64_t bin_count[kStreamBins] = {0, 0, 0, 0}, bin_begin[kStreamBins + 1];
-        int bin_nb[kStreamBins] = {0, 0, 0, 0};
-        auto bin_of = [](int nb_a) { return nb_a <= 8 ? 0 : nb_a <= 16 ? 1 : nb_a <= 24 ? 2 : 3; };
-        for (int64_t s = 0; s < n_sys; ++s) {
-            const int nb_a = (int)((wptr[s + 1] - wptr[s] - 1) / 2) + 1, b = bin_of(nb_a);
-            ++bin_count[b];
-            if (nb_a > bin_nb[b]) bin_nb[b] = nb_a;
-        }
-        bin_begin[0] = 0;
-        for (int b = 0; b < kStreamBins; ++b) bin_begin[b + 1] = bin_begin[b] + bin_count[b];
-        int32_t* h_order = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_sys);
-        if (!h_order) { free(wptr); frx_set_error("host allocation failed"); return FRX_ERR_ALLOC; }
-        {
-            int64_t fill[kStreamBins] = {bin_begin[0], bin_begin[1], bin_begin[2], bin_begin[3]};
-            for (int64_t s = 0; s < n_sys; ++s) h_order[fill[bin_of((int)((wptr[s + 1] - wptr[s] - 1) / 2) + 1)]++] = (int32_t)s;
-        }
-        free(wptr);
-        // launch geometry per bin; the io buffer holds [order][U scratch of the largest launch]
-        int64_t grid_b[kStreamBins];
-        size_t dyn_b[kStreamBins], scratch = 0;
+        BinLaunch L[kStreamBins];
+        size_t scratch = 0;
         for (int b = 0; b < kStreamBins; ++b) {
-            grid_b[b] = 0;
+            L[b].grid = 0;
             if (!bin_count[b]) continue;
-            dyn_b[b] = sizeof(double) * (size_t)kStreamWarps * stream_warp_doubles(bin_nb[b]);
-            FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_b[b]));
-            int per_sm = 1;
-            FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4_band_stream, kStreamWarps * 32, dyn_b[b]));
-            if (per_sm < 1) per_sm = 1;
-            grid_b[b] = (int64_t)ctx->sm_count * per_sm;
-            if (grid_b[b] * kStreamWarps > bin_count[b]) grid_b[b] = (bin_count[b] + kStreamWarps - 1) / kStreamWarps;
-            const size_t need = sizeof(double) * (size_t)grid_b[b] * kStreamWarps * n * stream_c(bin_nb[b]);
-            if (need > scratch) scratch = need;
+            if (dmma_bins & (1 << b)) {
+                L[b].kind = 1 + b;
+                rc = b == 0 ? band_dmma_geometry<2, 3>(ctx, n, bin_count[b], bin_nb[b], &L[b])
+                   : b == 1 ? band_dmma_geometry<3, 5>(ctx, n, bin_count[b], bin_nb[b], &L[b])
+                   : b == 2 ? band_dmma_geometry<4, 7>(ctx, n, bin_count[b], bin_nb[b], &L[b])
+                            : band_dmma_geometry<5, 9>(ctx, n, bin_count[b], bin_nb[b], &L[b]);
+                if (rc) return rc;
+            } else {
+                L[b].kind = 0;
+                L[b].dyn = sizeof(double) * (size_t)kStreamWarps * stream_warp_doubles(bin_nb[b]);
+                FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L[b].dyn));
+                int per_sm = 1;
+                FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4_band_stream, kStreamWarps * 32, L[b].dyn));
+                if (per_sm < 1) per_sm = 1;
+                L[b].grid = (int64_t)ctx->sm_count * per_sm;
+                if (L[b].grid * kStreamWarps > bin_count[b]) L[b].grid = (bin_count[b] + kStreamWarps - 1) / kStreamWarps;
+                L[b].scratch = sizeof(double) * (size_t)L[b].grid * kStreamWarps * n * stream_c(bin_nb[b]);
+            }
+            if (L[b].scratch > scratch) scratch = L[b].scratch;
         }
-        const size_t o_order = 0, o_scr = frx_align_up(sizeof(int32_t) * (size_t)n_sys, 256);
-        rc = frx_io_reserve(ctx, o_scr + scratch);
-        if (rc) { free(h_order); return rc; }
-        e = cudaMemcpyAsync((char*)ctx->io + o_order, h_order, sizeof(int32_t) * (size_t)n_sys, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // h_order is freed below
-        free(h_order);
-        if (e != cudaSuccess) { frx_set_error("order upload failed: %s", cudaGetErrorString(e)); return FRX_ERR_CUDA; }
-        q.uscratch = (double*)((char*)ctx->io + o_scr);
-        for (int b = 0; b < kStreamBins; ++b) {
+        rc = frx_io_reserve(ctx, scratch);     // U rows of the resident systems (L2-resident: each warp reuses its slab)
+        if (rc) return rc;
+        q.uscratch = (double*)ctx->io;
+        for (int b = kStreamBins - 1; b >= 0; --b) {    // widest bands first: the longest-running CTAs start first
             if (!bin_count[b]) continue;
             q.n_sys = bin_count[b];
-            q.order = (const int32_t*)((char*)ctx->io + o_order) + bin_begin[b];
+            q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
             q.nb_max = bin_nb[b];
-            // (the attribute is the maximum the function may use: raise it to this launch's size)
-            FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_b[b]));
-            FRX_LAUNCH(ctx, FRX_K_SOLVE,
-                       frx_k4_band_stream<<<(unsigned)grid_b[b], kStreamWarps * 32, dyn_b[b], ctx->stream>>>(q));
+            if (L[b].kind == 0) {
+                StreamParams sp;
+                sp.n_sys = q.n_sys; sp.n = n; sp.rcw = q.rcw; sp.wptr = q.wptr; sp.h = q.h; sp.rhs = q.rhs; sp.ldb = ldb;
+                sp.x = d_x; sp.ldx = ldx; sp.info = d_info; sp.uscratch = q.uscratch; sp.order = q.order; sp.nb_max = q.nb_max;
+                // (the attribute is the maximum the function may use: raise it to this launch's size)
+                FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L[b].dyn));
+                FRX_LAUNCH(ctx, FRX_K_SOLVE,
+                           frx_k4_band_stream<<<(unsigned)L[b].grid, kStreamWarps * 32, L[b].dyn, ctx->stream>>>(sp));
+            } else {
+                rc = L[b].kind == 1 ? band_dmma_launch<2, 3>(ctx, q, L[b])
+                   : L[b].kind == 2 ? band_dmma_launch<3, 5>(ctx, q, L[b])
+                   : L[b].kind == 3 ? band_dmma_launch<4, 7>(ctx, q, L[b])
+                                    : band_dmma_launch<5, 9>(ctx, q, L[b]);
+                if (rc) return rc;
+            }
         }
         return FRX_OK;
     }
-    free(wptr);
+    int smem_max = 0;
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    if (!d_dense && smem > (size_t)smem_max) {
+        frx_set_error("system too large for shared memory: needs %zu bytes, device offers %d (n = %d, max resolution %d)",
+                      smem, smem_max, n, max_res);
+        return FRX_ERR_INVALID_ARG;
+    }
     SolveParams p;
     p.n_sys = n_sys;
     p.n = n;
@@ -529,7 +565,6 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     p.max_store = (max_store + 1) & ~1;
     p.a_len = a_len;
     const size_t dyn = smem;
-    FRX_REQUIRE(dyn <= (size_t)smem_max, FRX_ERR_INVALID_ARG, "system too large for shared memory");
     FRX_CUDA(cudaFuncSetAttribute(frx_k4_assemble_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int per_sm = 1;
     FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4_assemble_solve, kSolveThreads, dyn));

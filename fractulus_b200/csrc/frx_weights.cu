@@ -176,7 +176,7 @@ extern "C" int frx_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_s
     FRX_REQUIRE(n_settings >= 0 && n_settings < ((int64_t)1 << 31), FRX_ERR_INVALID_ARG, "bad n_settings");
     if (n_settings == 0) return FRX_OK;
     FRX_REQUIRE(d_alpha && d_lf && d_resolution && h_row_ptr && d_weights, FRX_ERR_INVALID_ARG, "NULL buffer");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     // row_ptr travels through the workspace (it is host data describing the caller's layout): [row_ptr][scalars]
     const size_t bytes = frx_align_up(sizeof(int64_t) * (size_t)(n_settings + 1), 256);
     int rc = frx_ws_reserve(ctx, bytes + frx_k5_scratch_bytes(n_settings));
@@ -195,7 +195,7 @@ extern "C" int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double
     if (rc) return rc;
     *count = cnt;
     FRX_REQUIRE(capacity >= cnt, FRX_ERR_INVALID_ARG, "capacity smaller than the stencil length");
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     // workspace: [row_ptr (2 x i64) + scalars, written by frx_stencil_weights] [3 doubles] [weights] [offsets]
     size_t off_par = 256 + frx_align_up(frx_k5_scratch_bytes(1), 256), off_w = off_par + 64,
            off_o = off_w + frx_align_up(sizeof(double) * cnt, 64);
@@ -314,6 +314,6 @@ extern "C" int frx_weights_table(frx_ctx* ctx, int rule, int64_t n_alpha, const 
     FRX_REQUIRE(d_alpha && d_cA && d_w0 && d_mult, FRX_ERR_INVALID_ARG, "NULL buffer");
     FRX_REQUIRE(rule != FRX_RULE_SIMPSON || (d_cB && d_cm1), FRX_ERR_INVALID_ARG, "'simpson' needs d_cB and d_cm1");
     if (n_alpha == 0) return FRX_OK;
-    FRX_CUDA(cudaSetDevice(ctx->device));
+    FRX_ON_DEVICE(ctx);
     return frx_launch_weights_table(ctx, rule, n_alpha, d_alpha, h, N, d_cA, d_cB, ldc, d_w0, d_mult, ldw, d_cm1);
 }
