@@ -37,15 +37,20 @@ def _as_f64(x, device):
     return torch.as_tensor(x, dtype=torch.float64, device=device).contiguous()
 
 
-def _check_alpha_host(rule_name, alpha):
-    """Domain of the rules, enforced on the host like the reference would fail (equation.py:68 ...)."""
+def _check_alpha_host(rule_name, alpha, side='left'):
+    """Domain of the rules, enforced on the host like the reference would fail (mirrors frx_check_rule_alpha /
+    frx_check_riesz_alpha in csrc/frx_api.cu)."""
     a = np.atleast_1d(np.asarray(alpha, dtype=np.float64))
     if not np.all(np.isfinite(a)) or np.any(a < 0):
         raise ValueError('alpha must be finite and >= 0')
     if rule_name == 'rectangle' and np.any(a > 1.0):
-        raise ZeroDivisionError("'rectangle' with alpha > 1: 0.0 cannot be raised to a negative power")
-    if rule_name in ('trapezoidal', 'simpson') and np.any(a > 1.0):
-        raise ValueError("%r is only defined for alpha <= 1" % rule_name)
+        raise ZeroDivisionError("'rectangle' with alpha > 1: 0.0 cannot be raised to a negative power")   # equation.py:68
+    if rule_name == 'trapezoidal' and np.any(a > 2.0):
+        raise ZeroDivisionError("'trapezoidal' with alpha > 2: 0.0 cannot be raised to a negative power")  # equation.py:95
+    if rule_name == 'simpson' and np.any(a >= 2.0):
+        raise ValueError("'simpson' is only defined for alpha < 2 (gamma(2 - alpha), equation.py:114-139)")
+    if side == 'riesz_caputo' and np.any(a >= 2.0):
+        raise ValueError('Riesz-Caputo needs alpha < 2 (gamma(2. - alpha), equation.py:23)')
     return a
 
 
@@ -61,7 +66,7 @@ def stencil_weights(approximation, side, alpha, lf, resolution, device=None):
     rule = _lib.RULES[approximation]
     sd = _lib.SIDES[side]
     device = torch.device(device) if device is not None else default_device()
-    a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha)
+    a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha, side)
     r_h = np.atleast_1d(np.asarray(resolution.cpu().numpy() if torch.is_tensor(resolution) else resolution,
                                    dtype=np.float64))
     n = len(a_h)
@@ -123,7 +128,7 @@ def history(approximation, alpha, h, g, N=None, out=None, validate=True, side='l
         d_alpha = alpha.to(torch.float64).reshape(-1).contiguous()
         squeeze_a = alpha.dim() == 0
     else:
-        a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha)
+        a_h = _check_alpha_host(approximation, alpha.cpu().numpy() if torch.is_tensor(alpha) else alpha, side)
         squeeze_a = np.ndim(alpha) == 0
         d_alpha = _as_f64(a_h, device)
     n_alpha = d_alpha.numel()

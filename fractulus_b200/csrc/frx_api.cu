@@ -254,8 +254,27 @@ int frx_check_rule_alpha(int rule, double alpha) {
         frx_set_error("'rectangle' with alpha > 1: 0.0 ** negative (reference: ZeroDivisionError, equation.py:68)");
         return FRX_ERR_ZERO_DIVISION;
     }
-    if ((rule == FRX_RULE_TRAPEZOIDAL || rule == FRX_RULE_SIMPSON) && alpha > 1.0) {
-        frx_set_error("rule is only defined for alpha <= 1 (reference yields negative bases / complex weights)");
+    // 'trapezoidal' and 'simpson' give real weights for every alpha < 2 (all pow bases are >= 0 for resolution >= 2 and
+    // (1.-alpha)**2 has an integer exponent); beyond that the reference fails:
+    if (rule == FRX_RULE_TRAPEZOIDAL && alpha > 2.0) {
+        frx_set_error("'trapezoidal' with alpha > 2: 0.0 ** negative (reference: ZeroDivisionError, equation.py:95)");
+        return FRX_ERR_ZERO_DIVISION;
+    }
+    if (rule == FRX_RULE_SIMPSON && alpha >= 2.0) {
+        frx_set_error("'simpson' with alpha >= 2: gamma(2 - alpha) at a pole / 0.0 ** negative / complex weights in the "
+                      "reference (equation.py:114-139)");
+        return FRX_ERR_DOMAIN;
+    }
+    return FRX_OK;
+}
+
+// create_riesz_caputo_stencil multiplies by gamma(2. - alpha) (equation.py:23): a pole for alpha = 2, 3, ...
+// (reference: ValueError "math domain error").  For non-integer alpha > 2 the reference evaluates CPython's
+// reflection branch of math.gamma through libm sin/cos; that branch is not restated here -- rejected (documented).
+int frx_check_riesz_alpha(double alpha) {
+    if (alpha >= 2.0) {
+        frx_set_error("Riesz-Caputo with alpha >= 2: gamma(2 - alpha) is not positive-argument (reference: ValueError "
+                      "at integer alpha, equation.py:23)");
         return FRX_ERR_DOMAIN;
     }
     return FRX_OK;
@@ -291,6 +310,11 @@ extern "C" int frx_stencil_layout(int rule, int side, double alpha, double resol
                 "the Gruenwald-Letnikov extension offers the left stencil only");
     int rc = frx_check_settings(rule, alpha, resolution);
     if (rc) return rc;
+    if (side == FRX_SIDE_RIESZ_CAPUTO) {
+        rc = frx_check_riesz_alpha(alpha);
+        if (rc) return rc;
+        FRX_REQUIRE(resolution <= 1.0e9, FRX_ERR_DOMAIN, "Riesz-Caputo stencil of 2*resolution+1 nodes exceeds int32");
+    }
     long long f, c;
     frx_left_layout(rule, (long long)resolution, &f, &c);
     long long last = f + c - 1;

@@ -80,6 +80,7 @@ int frx_hstage_release(frx_ctx* ctx);
 // host-side domain check of one Settings triple against the reference's behaviour
 int frx_check_settings(int rule, double alpha, double resolution);
 int frx_check_rule_alpha(int rule, double alpha);
+int frx_check_riesz_alpha(double alpha);
 
 static inline size_t frx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -168,9 +168,9 @@ FRX_HD_CALL frx_dd frx_log_dd(double x) {
 }
 
 // x ** y for the domain the reference reaches: x >= 0 finite, y finite.  Python semantics at the
-// edges: x ** 0 == 1, 0 ** y == 0 for y > 0; 0 ** negative raises ZeroDivisionError and a negative
-// base gives a complex number in the reference -- both are rejected on the host before launch, the
-// device returns NaN for them.
+// edges: x ** 0 == 1, 0 ** y == 0 for y > 0, negative base with an integer-valued exponent = +-|x| ** y;
+// 0 ** negative raises ZeroDivisionError and a negative base with a fractional exponent gives a complex number
+// in the reference -- both are rejected on the host before launch, the device returns NaN for them.
 FRX_HD_CALL double frx_pow_core(frx_dd L, double y) {  // exp(y * L) rounded once, L = log(x) as a double-double
     frx_dd z = frx_dd_mul_d(L, y);
     int e;
@@ -195,6 +195,10 @@ FRX_HD double frx_pow_from_log(double x, double y, frx_dd L) {
 FRX_HD_CALL double frx_pow_cr(double x, double y) {
     if (y == 0.0 || x == 1.0) return 1.0;
     if (x == 0.0) return y > 0.0 ? 0.0 : NAN;
+    if (x < 0.0 && y == floor(y)) {            // (1.-alpha)**2 with alpha > 1 (reference equation.py:158): a float result
+        const double m = frx_pow_core(frx_log_dd(-x), y);
+        return fmod(y, 2.0) != 0.0 ? -m : m;
+    }
     if (!(x > 0.0)) return NAN;
     if (y == 1.0) return x;
     return frx_pow_core(frx_log_dd(x), y);

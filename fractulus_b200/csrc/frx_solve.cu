@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kSolveThreads) frx_k4_assemble_solve(const Sol
 constexpr int kStreamWarps = 1;   // one-warp CTAs pack shared memory best
 constexpr int kStreamMaxNb = 31;
 constexpr int kStreamMaxN = 256;
-constexpr int kStreamBins = 4;    // bins by nb = res + 1: <= 8, <= 16, <= 24, <= 31
+constexpr int kStreamBins = 4;    // bins by nb = res + 1: <= 7, <= 15, <= 23, <= 31
 constexpr int kDefaultDmmaBins = 0xF;   // bins that run the blocked tensor-core kernel (frx_solve_dmma.cuh)
 __host__ __device__ inline int stream_c(int nb_max) { return 2 * nb_max + 1; }
 __host__ __device__ inline int stream_rs(int nb_max) { return ((stream_c(nb_max) + 7) & ~7) + 1; }   // ring padded to 8, +1 -> odd
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
 struct BinLaunch {
     int64_t grid;
     size_t dyn, scratch;
-    int kind;   // 0: frx_k4_band_stream, 1..4: frx_k4_band_dmma<2,3> / <3,5> / <4,7> / <5,9>
+    int kind;   // 0: frx_k4_band_stream, 1..4: frx_k4_band_dmma<1,3> / <2,5> / <3,7> / <4,9>
 };
 
 template <int RT, int CT>
@@ -422,7 +422,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     double* s_par = (double*)(hs + o_par);
     int64_t* wptr = (int64_t*)(hs + o_wptr);
     int32_t* h_order = (int32_t*)(hs + o_order);
-    auto bin_of = [](int nb_a) { return nb_a <= 8 ? 0 : nb_a <= 16 ? 1 : nb_a <= 24 ? 2 : 3; };
+    auto bin_of = [](int nb_a) { return nb_a <= 7 ? 0 : nb_a <= 15 ? 1 : nb_a <= 23 ? 2 : 3; };
     int64_t bin_count[kStreamBins] = {0, 0, 0, 0}, bin_begin[kStreamBins + 1];
     int bin_nb[kStreamBins] = {0, 0, 0, 0};
     wptr[0] = 0;
@@ -499,10 +499,10 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             if (!bin_count[b]) continue;
             if (dmma_bins & (1 << b)) {
                 L[b].kind = 1 + b;
-                rc = b == 0 ? band_dmma_geometry<2, 3>(ctx, n, bin_count[b], bin_nb[b], &L[b])
-                   : b == 1 ? band_dmma_geometry<3, 5>(ctx, n, bin_count[b], bin_nb[b], &L[b])
-                   : b == 2 ? band_dmma_geometry<4, 7>(ctx, n, bin_count[b], bin_nb[b], &L[b])
-                            : band_dmma_geometry<5, 9>(ctx, n, bin_count[b], bin_nb[b], &L[b]);
+                rc = b == 0 ? band_dmma_geometry<1, 3>(ctx, n, bin_count[b], bin_nb[b], &L[b])
+                   : b == 1 ? band_dmma_geometry<2, 5>(ctx, n, bin_count[b], bin_nb[b], &L[b])
+                   : b == 2 ? band_dmma_geometry<3, 7>(ctx, n, bin_count[b], bin_nb[b], &L[b])
+                            : band_dmma_geometry<4, 9>(ctx, n, bin_count[b], bin_nb[b], &L[b]);
                 if (rc) return rc;
             } else {
                 L[b].kind = 0;
@@ -534,10 +534,10 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                 FRX_LAUNCH(ctx, FRX_K_SOLVE,
                            frx_k4_band_stream<<<(unsigned)L[b].grid, kStreamWarps * 32, L[b].dyn, ctx->stream>>>(sp));
             } else {
-                rc = L[b].kind == 1 ? band_dmma_launch<2, 3>(ctx, q, L[b])
-                   : L[b].kind == 2 ? band_dmma_launch<3, 5>(ctx, q, L[b])
-                   : L[b].kind == 3 ? band_dmma_launch<4, 7>(ctx, q, L[b])
-                                    : band_dmma_launch<5, 9>(ctx, q, L[b]);
+                rc = L[b].kind == 1 ? band_dmma_launch<1, 3>(ctx, q, L[b])
+                   : L[b].kind == 2 ? band_dmma_launch<2, 5>(ctx, q, L[b])
+                   : L[b].kind == 3 ? band_dmma_launch<3, 7>(ctx, q, L[b])
+                                    : band_dmma_launch<4, 9>(ctx, q, L[b]);
                 if (rc) return rc;
             }
         }

@@ -7,22 +7,23 @@
 // and one dependent pivot search per column; ncu: FP64 pipe 12 %, stalled on the shared-memory round trips
 // (profiles/r01_k4_band_stream_final_ncu_full.txt).  Here the elimination advances in panels of 8 columns:
 //
-//   A  panel      lane = row slot: the 8 panel entries of a row (+ its right-hand side as a 9th column) sit in
-//                 registers; per column one pivot search (3 redux + 1), one broadcast of the pivot row's remaining
-//                 panel entries (shuffles), <= 8 FMAs per row.  Rows never move (implicit pivoting); the pivot
-//                 row retires as a row of U, reciprocal pivot on the diagonal.
-//   B  U12        lane = trailing column: U12 = L11^-1 * A12[pivot rows], 28 FMAs per column, stored as the B
-//                 operand (and to the U scratch the back substitution reads).
-//   C  update     every 8x8 tile of the window: C += (-L21) * U12 = two DMMA m8n8k4; the multipliers written by
-//                 phase A are the A fragments as they lie, U12 the B fragments: one LDS.128 + 2 DMMA + one STS.128
-//                 per tile.  Retired / empty row slots carry zero multipliers.
-//   D  refill     the 8 retired row slots take the 8 matrix rows that enter the band window, built from the
-//                 2nb+1 band coefficients; the freed column tile is zeroed and becomes the right-most one.
+//   A  panel      lane = row slot: the 8 panel entries of the lane's row (+ its right-hand side as a 9th column) sit
+//                 in registers; per column one pivot search (3 redux), one broadcast of the pivot row's remaining
+//                 panel entries (shuffles), <= 8 FMAs.  Rows never move (implicit pivoting).  The pivot row retires
+//                 as a row of U (reciprocal pivot on the diagonal): its trailing window entries go into registers
+//                 (lane = trailing column), its multipliers w.r.t. the earlier pivots of the panel into L11, and the
+//                 matrix row that enters the band at this column (k + nb + 1) takes its slot at once, built from the
+//                 2nb+1 band coefficients -- so nb + 1 <= 32 row slots are enough for every band this kernel takes.
+//   B  U12        lane = trailing column: U12 = L11^-1 * (retired rows), 28 FMAs per column in registers, stored as the
+//                 B operand (and to the U scratch the back substitution reads).
+//   C  update     every 8x8 tile of the window: C += (-L21) * U12 = two DMMA m8n8k4; the multipliers phase A left in
+//                 its registers go to shared memory once (`PB`) and are the A fragments as they lie, U12 the B
+//                 fragments: one LDS.128 + 2 DMMA + one STS.128 per tile, loads one column tile ahead.
 //
-// Window: (nb + 8) row slots x (2nb + 8) columns, row slots fixed, column tiles of 8 in a ring (tile of window
-// column jj of panel p: (p + jj/8) mod CT), plus a dense 8-column copy of the current panel (`PB`), which is what
-// phase A reads lane-per-row and phase C reads as A fragments.  Geometry <RT, CT> = row / column tiles:
-//   nb <= 8: <2,3>   nb <= 16: <3,5>   nb <= 24: <4,7>   nb <= 31: <5,9>      (CT odd: row stride = 8 mod 16 doubles,
+// Window: (nb + 1) row slots x (2nb + 8) columns, row slots fixed, column tiles of 8 in a ring (tile of window
+// column jj of panel p: (p + jj/8) mod CT), plus a dense 8-column copy of the current panel (`PB`).  The column tile a
+// panel frees is zeroed and becomes the right-most one.  Geometry <RT, CT> = row / column tiles:
+//   nb <= 7: <1,3>   nb <= 15: <2,5>   nb <= 23: <3,7>   nb <= 31: <4,9>      (CT odd: row stride = 8 mod 16 doubles,
 // so the C-fragment LDS.128/STS.128 are bank-conflict free).
 // Back substitution: blocks of 8 rows; the sums over the columns right of the block are taken lane-per-column and
 // transpose-reduced (9 shuffles for 8 sums), the 8x8 triangle is solved across lane groups; the next block's U rows
@@ -35,19 +36,19 @@ namespace frx_k4 {
 template <int RT_, int CT_>
 struct BandGeo {
     static constexpr int RT = RT_, CT = CT_;
-    static constexpr int S = RT * 8;                 // row slots
+    static constexpr int S = RT * 8;                 // row slots (<= 32: one per lane)
     static constexpr int WC = CT * 8;                // window columns
     static constexpr int RS = WC;                    // row stride of W (doubles); CT odd -> RS = 8 (mod 16)
     static constexpr int TW = (CT - 1) * 8;          // trailing columns
     static constexpr int TPL = (TW + 31) / 32;       // trailing columns per lane
+    static constexpr int WCL = (WC + 31) / 32;       // window columns per lane
     static constexpr int TS = TW + 2;                // stride of the B-operand staging (pairs); = 2 (mod 8)
-    static constexpr int RPL = (S + 31) / 32;        // row slots per lane
-    static constexpr int NB_MAX = (S - 8) < (WC - 8) / 2 ? (S - 8) : (WC - 8) / 2;
-    static constexpr int ALEN = (2 * NB_MAX + 2 + 1) & ~1;
+    static constexpr int NB_MAX = (S - 1) < (WC - 8) / 2 ? (S - 1) : (WC - 8) / 2;
+    static constexpr int APAD = WC + 32;             // band coefficients a[0 .. 2nb], zeros up to here
     static_assert(CT % 2 == 1, "CT must be odd");
-    static_assert(RPL <= 2, "at most two row slots per lane");
+    static_assert(S <= 32, "one row slot per lane");
     __host__ __device__ static inline int smem_doubles(int n) {
-        return S * RS + S * 8 + 8 * TS + ALEN + ((n + 1) & ~1);
+        return S * RS + S * 8 + 8 * TS + 64 + APAD + ((n + 1) & ~1);
     }
 };
 
@@ -76,15 +77,16 @@ struct BandParams {
 template <int RT, int CT>
 __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
     using G = BandGeo<RT, CT>;
-    constexpr int S = G::S, WC = G::WC, RS = G::RS, TW = G::TW, TPL = G::TPL, TS = G::TS, RPL = G::RPL;
+    constexpr int S = G::S, WC = G::WC, RS = G::RS, TW = G::TW, TPL = G::TPL, TS = G::TS, WCL = G::WCL;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x, g = lane >> 2, cp = lane & 3, n = p.n;
     double* W = sm;                         // W[slot * RS + tile * 8 + col]
-    double* PB = W + S * RS;                // PB[slot * 8 + c]: current panel / multipliers (negated)
+    double* PB = W + S * RS;                // PB[slot * 8 + c]: current panel, then the multipliers (negated)
     double* Ub = PB + S * 8;                // Ub[(m * TS + t) * 2 + {0,1}] = U12[2m + {0,1}][t]
-    double* a = Ub + 8 * TS;                // a[k + nb]
-    double* xs = a + G::ALEN;               // rhs, then transformed rhs, then the solution
+    double* L11 = Ub + 8 * TS;              // L11[q * 8 + c], c < q: multiplier (negated) of pivot row q w.r.t. pivot c
+    double* apad = L11 + 64;                // apad[e] = a_{e - nb} for e <= 2nb, 0 beyond
+    double* xs = apad + G::APAD;            // rhs, then transformed rhs, then the solution
     double* U = p.uscratch + (int64_t)blockIdx.x * n * (2 * p.nb_max + 1);
     const int n_panels = (n + 7) >> 3;
     for (int64_t si = blockIdx.x; si < p.n_sys; si += gridDim.x) {
@@ -98,6 +100,9 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
         const double* rhs = p.rhs + s * p.ldb;
         double* xo = p.x + s * p.ldx;
         __syncwarp();
+        for (int e = lane; e < G::APAD; e += 32) apad[e] = 0.0;
+        for (int i = lane; i < n; i += 32) xs[i] = rhs[i];
+        __syncwarp();
         for (int k = -nb_a + lane; k <= nb_a; k += 32) {     // band coefficients: terms and order of the dict-merging expansion
             double acc = 0.0;
             bool any = false;
@@ -106,227 +111,218 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
             if (k + 1 >= -res && k + 1 <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k + 1], -ih)));
             if (k - 1 >= -res && k - 1 <= res) add(__dmul_rn(ih, __dmul_rn(rc[k - 1], ih)));
             if (k >= -res && k <= res) add(__dmul_rn(ih, __dmul_rn(rc[k], -ih)));
-            if (k >= -nb && k <= nb) a[k + nb] = acc;
+            if (k >= -nb && k <= nb) apad[k + nb] = acc;
         }
-        for (int i = lane; i < n; i += 32) xs[i] = rhs[i];
         __syncwarp();
-        // ---- initial window: rows 0 .. min(n, nb + 8) - 1 in slots of the same number ---------------------------
-        const int rows0 = n < nb + 8 ? n : nb + 8;
-        int label[RPL];
-        double bval[RPL];
+        // ---- initial window: rows 0 .. min(n, nb + 1) - 1 in the slots of the same number --------------------------
+        const int rows0 = n < nb + 1 ? n : nb + 1;
+        int label = lane < rows0 ? lane : -1;
+        double bval = lane < rows0 ? xs[lane] : 0.0;
+        for (int r0 = 0; r0 < rows0; ++r0) {
 #pragma unroll
-        for (int j = 0; j < RPL; ++j) {
-            const int slot = lane + 32 * j;
-            label[j] = slot < rows0 ? slot : -1;
-            bval[j] = slot < rows0 ? xs[slot] : 0.0;
-        }
-        for (int r0 = 0; r0 < rows0; ++r0)
-            for (int jj = lane; jj < WC; jj += 32) {
-                const int d = jj - r0;
-                const double v = (jj < n && d >= -nb && d <= nb) ? a[d + nb] : 0.0;
-                W[r0 * RS + jj] = v;
-                if (jj < 8) PB[r0 * 8 + jj] = v;
+            for (int i = 0; i < WCL; ++i) {
+                const int jj = lane + 32 * i;
+                if (jj < WC) {
+                    const double v = jj < n ? apad[jj - r0 + nb] : 0.0;     // d = jj - r0 >= -nb; 0 beyond +nb
+                    W[r0 * RS + jj] = v;
+                    if (i == 0 && lane < 8) PB[r0 * 8 + lane] = v;
+                }
             }
+        }
         int info = 0, pm = 0;                                // pm = panel index mod CT
         __syncwarp();
         for (int pnl = 0; pnl < n_panels; ++pnl) {
             const int k0 = pnl * 8;
-            // ================= phase A: panel factorisation, lane = row slot =================================
-            double r[RPL][9];
-            int retq[RPL];
+            // shared-memory offsets of this lane's window columns in the ring: refill (window column jj) and copy-out
+            // (trailing column t = window column 8 + t)
+            int doff[WCL], colidx[TPL];
 #pragma unroll
-            for (int j = 0; j < RPL; ++j) {
-                const int slot = lane + 32 * j;
-                retq[j] = 99;
-                if (slot < S) {
-                    const double2* src = reinterpret_cast<const double2*>(PB + slot * 8);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const double2 v = src[q];
-                        r[j][2 * q] = v.x;
-                        r[j][2 * q + 1] = v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) r[j][q] = 0.0;
-                }
-                r[j][8] = bval[j];
+            for (int i = 0; i < WCL; ++i) {
+                const int jj = lane + 32 * i;
+                int tile = pm + (jj >> 3);
+                if (tile >= CT) tile -= CT;
+                doff[i] = tile * 8 + (jj & 7);
             }
-            int ps[8];
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                const int t = lane + 32 * i;
+                int tile = pm + 1 + (t >> 3);
+                if (tile >= CT) tile -= CT;
+                colidx[i] = tile * 8 + (t & 7);
+            }
+            // ================= phase A: panel factorisation, lane = row slot =================================
+            double r[9], u[TPL][8];
+            if (lane < S) {
+                const double2* src = reinterpret_cast<const double2*>(PB + lane * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 v = src[q];
+                    r[2 * q] = v.x;
+                    r[2 * q + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) r[q] = 0.0;
+            }
+            r[8] = bval;
+#pragma unroll
+            for (int i = 0; i < TPL; ++i)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) u[i][q] = 0.0;
+            int ps_valid = 0;                                // bit c: column k0 + c exists
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                ps[c] = -1;
                 if (k0 + c < n) {                            // warp-uniform
                     const int k = k0 + c;
-                    bool act[RPL];
-                    unsigned long long bits[RPL], best = 0ull;
-#pragma unroll
-                    for (int j = 0; j < RPL; ++j) {
-                        act[j] = label[j] >= 0 && retq[j] == 99;
-                        bits[j] = act[j] ? (unsigned long long)__double_as_longlong(fabs(r[j][c])) : 0ull;
-                        best = bits[j] > best ? bits[j] : best;
-                    }
+                    ps_valid |= 1 << c;
+                    const bool act = label >= 0;
                     // |v| >= 0 orders like its bit pattern: two 32-bit reductions; ties -> lowest row label (LAPACK: first maximum)
-                    const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+                    const unsigned long long bits = act ? (unsigned long long)__double_as_longlong(fabs(r[c])) : 0ull;
+                    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
                     const unsigned mh = __reduce_max_sync(FULL, hi);
                     const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
-                    const unsigned long long top = ((unsigned long long)mh << 32) | ml;
-                    int code = 0x7fffffff;
-#pragma unroll
-                    for (int j = 0; j < RPL; ++j)
-                        if (act[j] && bits[j] == top) {
-                            const int cj = (label[j] << 6) | (lane + 32 * j);
-                            code = cj < code ? cj : code;
-                        }
-                    code = __reduce_min_sync(FULL, code);
-                    const int pslot = code & 63, P = pslot & 31, jP = pslot >> 5, blog = code >> 6;
-                    ps[c] = pslot;
+                    const int code = __reduce_min_sync(FULL, (act && hi == mh && lo == ml) ? ((label << 5) | lane) : 0x7fffffff);
+                    const int P = code & 31, blog = code >> 5;
                     double prow[9];
 #pragma unroll
-                    for (int cc = c; cc < 9; ++cc) {
-                        const double mine = (RPL == 2 && jP) ? r[RPL - 1][cc] : r[0][cc];
-                        prow[cc] = __shfl_sync(FULL, mine, P);
-                    }
+                    for (int cc = c; cc < 9; ++cc) prow[cc] = __shfl_sync(FULL, r[cc], P);
                     const double pval = prow[c];
                     if (pval == 0.0 && info == 0) info = k + 1;
                     const double rinv = 1.0 / pval;
+                    const bool is_pivot = lane == P;
+                    if (act && !is_pivot) {
+                        const double l = r[c] * rinv;
+                        r[c] = l;
 #pragma unroll
-                    for (int j = 0; j < RPL; ++j) {
-                        const bool is_pivot = lane == P && j == jP;
-                        if (act[j] && !is_pivot) {
-                            const double l = r[j][c] * rinv;
-                            r[j][c] = l;
-#pragma unroll
-                            for (int cc = c + 1; cc < 9; ++cc) r[j][cc] = fma(-l, prow[cc], r[j][cc]);
-                            if (label[j] == k) label[j] = blog;    // the interchange, on labels only
-                        } else if (is_pivot) {
-                            retq[j] = c;
-                            r[j][c] = rinv;                        // U keeps the reciprocal pivot on its diagonal
-                        }
+                        for (int cc = c + 1; cc < 9; ++cc) r[cc] = fma(-l, prow[cc], r[cc]);
+                        if (label == k) label = blog;          // the interchange, on labels only
                     }
-                    if (lane == 0) xs[k] = prow[8];                // transformed right-hand side of row k of U
+                    // the pivot row leaves the window: trailing entries to the registers of their columns' lanes,
+                    // multipliers w.r.t. the earlier pivots to L11, panel entries to row k of U
+                    const double* wrow = W + P * RS;
+#pragma unroll
+                    for (int i = 0; i < TPL; ++i) u[i][c] = (lane + 32 * i < TW) ? wrow[colidx[i]] : 0.0;
+                    if (is_pivot) {
+#pragma unroll
+                        for (int cc = 0; cc < c; ++cc) L11[c * 8 + cc] = -r[cc];
+                        double* urow = U + (int64_t)k * us;
+                        urow[0] = rinv;                        // U keeps the reciprocal pivot on its diagonal
+#pragma unroll
+                        for (int cc = c + 1; cc < 8; ++cc)
+                            if (cc - c < us && k0 + cc < n) urow[cc - c] = r[cc];
+                        xs[k] = r[8];                          // transformed right-hand side of row k of U
+                    }
+                    __syncwarp();
+                    // ... and the matrix row that enters the band at this column takes its slot
+                    const int inew = k + nb + 1;
+                    if (inew < n) {                            // warp-uniform
+                        double* nrow = W + P * RS;
+#pragma unroll
+                        for (int i = 0; i < WCL; ++i) {
+                            const int jj = lane + 32 * i;
+                            if (jj >= 8 && jj < WC) nrow[doff[i]] = (k0 + jj < n) ? apad[jj - c - 1] : 0.0;
+                        }
+                        const double nbv = xs[inew];
+                        double nv[8];
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) nv[cc] = (cc > c && k0 + cc < n) ? apad[cc - c - 1] : 0.0;
+                        if (is_pivot) {
+#pragma unroll
+                            for (int cc = 0; cc < 8; ++cc) r[cc] = nv[cc];
+                            r[8] = nbv;
+                            label = inew;
+                        }
+                    } else if (is_pivot) {
+                        label = -1;
+#pragma unroll
+                        for (int cc = 0; cc < 9; ++cc) r[cc] = 0.0;
+                    }
+                    __syncwarp();
                 }
             }
-            // U11 (the retired rows' panel entries) to the U scratch; multipliers (negated) to PB as the A operand
+            // multipliers (negated) to PB: the A operand of the trailing update
+            if (lane < S) {
+                const bool alive = label >= 0;
+                double m[8];
 #pragma unroll
-            for (int j = 0; j < RPL; ++j) {
-                const int slot = lane + 32 * j;
-                const int q = retq[j];
-                if (q < 8) {
-                    double* urow = U + (int64_t)(k0 + q) * us;
+                for (int cc = 0; cc < 8; ++cc) m[cc] = (alive && k0 + cc < n) ? -r[cc] : 0.0;
+                double2* dst = reinterpret_cast<double2*>(PB + lane * 8);
 #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc)
-                        if (cc >= q && cc - q < us && k0 + cc < n) urow[cc - q] = r[j][cc];
+                for (int qq = 0; qq < 4; ++qq) dst[qq] = make_double2(m[2 * qq], m[2 * qq + 1]);
+            }
+            bval = r[8];
+            // ================= phase B: U12 = L11^-1 (retired rows), lane = trailing column ====================
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                if (ps_valid & (1 << q)) {
+                    const double2* mrow = reinterpret_cast<const double2*>(L11 + q * 8);
+                    double mq[8];
+#pragma unroll
+                    for (int qq = 0; qq < (q + 1) / 2; ++qq) {
+                        const double2 v = mrow[qq];
+                        mq[2 * qq] = v.x;
+                        mq[2 * qq + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < TPL; ++i)
+#pragma unroll
+                        for (int c = 0; c < q; ++c) u[i][q] = fma(mq[c], u[i][c], u[i][q]);
                 }
-                if (slot < S) {
-                    const bool alive = label[j] >= 0;
-                    double m[8];
+            }
 #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) m[cc] = (alive && cc < q && k0 + cc < n) ? -r[j][cc] : 0.0;
-                    double2* dst = reinterpret_cast<double2*>(PB + slot * 8);
+            for (int i = 0; i < TPL; ++i) {
+                const int t = lane + 32 * i;
+                if (t < TW) {
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) dst[qq] = make_double2(m[2 * qq], m[2 * qq + 1]);
+                    for (int m = 0; m < 4; ++m)
+                        *reinterpret_cast<double2*>(Ub + (m * TS + t) * 2) = make_double2(u[i][2 * m], u[i][2 * m + 1]);
+                    if (k0 + 8 + t < n) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int rel = 8 - q + t;
+                            if ((ps_valid & (1 << q)) && rel < us) U[(int64_t)(k0 + q) * us + rel] = u[i][q];
+                        }
+                    }
                 }
-                bval[j] = r[j][8];
             }
             __syncwarp();
-            // ================= phase B: U12 = L11^-1 A12[pivot rows], lane = trailing column ====================
-            {
-                double u[TPL][8];
-                int colidx[TPL];
-#pragma unroll
-                for (int jj = 0; jj < TPL; ++jj) {
-                    const int t = lane + 32 * jj;
-                    int tile = pm + 1 + (t >> 3);
-                    if (tile >= CT) tile -= CT;
-                    colidx[jj] = tile * 8 + (t & 7);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) u[jj][q] = (t < TW && ps[q] >= 0) ? W[ps[q] * RS + colidx[jj]] : 0.0;
-                }
-#pragma unroll
-                for (int q = 1; q < 8; ++q) {
-                    if (ps[q] >= 0) {
-                        const double2* mrow = reinterpret_cast<const double2*>(PB + ps[q] * 8);
-                        double mq[8];
-#pragma unroll
-                        for (int qq = 0; qq < (q + 1) / 2; ++qq) {
-                            const double2 v = mrow[qq];
-                            mq[2 * qq] = v.x;
-                            mq[2 * qq + 1] = v.y;
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < TPL; ++jj)
-#pragma unroll
-                            for (int c = 0; c < q; ++c) u[jj][q] = fma(mq[c], u[jj][c], u[jj][q]);
-                    }
-                }
-#pragma unroll
-                for (int jj = 0; jj < TPL; ++jj) {
-                    const int t = lane + 32 * jj;
-                    if (t < TW) {
-#pragma unroll
-                        for (int m = 0; m < 4; ++m)
-                            *reinterpret_cast<double2*>(Ub + (m * TS + t) * 2) = make_double2(u[jj][2 * m], u[jj][2 * m + 1]);
-                        if (k0 + 8 + t < n) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const int rel = 8 - q + t;
-                                if (ps[q] >= 0 && rel < us) U[(int64_t)(k0 + q) * us + rel] = u[jj][q];
-                            }
-                        }
-                    }
-                }
-            }
             // ================= phase C: trailing update on the tensor cores ====================================
             double2 am[RT];
-            __syncwarp();
 #pragma unroll
             for (int rt = 0; rt < RT; ++rt) am[rt] = *reinterpret_cast<const double2*>(PB + (8 * rt + g) * 8 + 2 * cp);
             __syncwarp();                                   // PB may now take the next panel
+            {
+                double2 cf[RT], cfn[RT];
+                int tile = pm + 1 == CT ? 0 : pm + 1;
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt) cf[rt] = *reinterpret_cast<const double2*>(W + (8 * rt + g) * RS + tile * 8 + 2 * cp);
+#pragma unroll
+                for (int ct = 0; ct < CT - 1; ++ct) {
+                    const int tile_next = tile + 1 == CT ? 0 : tile + 1;
+                    if (ct + 1 < CT - 1) {
+#pragma unroll
+                        for (int rt = 0; rt < RT; ++rt)
+                            cfn[rt] = *reinterpret_cast<const double2*>(W + (8 * rt + g) * RS + tile_next * 8 + 2 * cp);
+                    }
+                    const double2 bb = *reinterpret_cast<const double2*>(Ub + (cp * TS + 8 * ct + g) * 2);
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) {
+                        dmma884(cf[rt].x, cf[rt].y, am[rt].x, bb.x);
+                        dmma884(cf[rt].x, cf[rt].y, am[rt].y, bb.y);
+                    }
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) {
+                        if (ct == 0) *reinterpret_cast<double2*>(PB + (8 * rt + g) * 8 + 2 * cp) = cf[rt];   // the next panel
+                        else *reinterpret_cast<double2*>(W + (8 * rt + g) * RS + tile * 8 + 2 * cp) = cf[rt];
+                        cf[rt] = cfn[rt];
+                    }
+                    tile = tile_next;
+                }
+            }
 #pragma unroll
             for (int rt = 0; rt < RT; ++rt)                 // the freed column tile: zero, it becomes the right-most one
                 *reinterpret_cast<double2*>(W + (8 * rt + g) * RS + pm * 8 + 2 * cp) = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int ct = 0; ct < CT - 1; ++ct) {
-                int tile = pm + 1 + ct;
-                if (tile >= CT) tile -= CT;
-                const double2 bb = *reinterpret_cast<const double2*>(Ub + (cp * TS + 8 * ct + g) * 2);
-#pragma unroll
-                for (int rt = 0; rt < RT; ++rt) {
-                    double2* cptr = reinterpret_cast<double2*>(W + (8 * rt + g) * RS + tile * 8 + 2 * cp);
-                    double2 cf = *cptr;
-                    dmma884(cf.x, cf.y, am[rt].x, bb.x);
-                    dmma884(cf.x, cf.y, am[rt].y, bb.y);
-                    if (ct == 0) *reinterpret_cast<double2*>(PB + (8 * rt + g) * 8 + 2 * cp) = cf;   // the next panel
-                    else *cptr = cf;
-                }
-            }
-            __syncwarp();
-            // ================= phase D: retired slots take the rows that enter the window ========================
-            const int pm_next = pm + 1 == CT ? 0 : pm + 1;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (ps[q] >= 0) {
-                    const int slot = ps[q], inew = k0 + nb + 8 + q;
-                    if (inew < n) {
-                        for (int jj = lane; jj < WC; jj += 32) {
-                            const int j = k0 + 8 + jj, d = j - inew;
-                            const double v = (j < n && d >= -nb && d <= nb) ? a[d + nb] : 0.0;
-                            int tile = pm_next + (jj >> 3);
-                            if (tile >= CT) tile -= CT;
-                            W[slot * RS + tile * 8 + (jj & 7)] = v;
-                            if (jj < 8) PB[slot * 8 + jj] = v;
-                        }
-                    }
-                    if (lane == (slot & 31)) {
-                        const int nl = inew < n ? inew : -1;
-                        const double nbv = inew < n ? xs[inew] : 0.0;
-                        if (RPL == 2 && (slot >> 5)) { label[RPL - 1] = nl; bval[RPL - 1] = nbv; }
-                        else { label[0] = nl; bval[0] = nbv; }
-                    }
-                }
-            }
-            pm = pm_next;
+            pm = pm + 1 == CT ? 0 : pm + 1;
             __syncwarp();
         }
         // ---- back substitution in blocks of 8 rows ------------------------------------------------------------

@@ -172,3 +172,24 @@ class LazyOperation(Element):
             s = b.value_at(point)
             return {node: w * s for node, w in a.expand(point).items()}
         raise TypeError('only Number * element products are supported')
+
+
+def install_as_fdm():
+    """Register this carrier under the import name ``fdm`` (+ ``fdm.equation``, ``fdm.geometry``) for programs written
+    against the reference's dependency (``from fdm import Stencil``, ``import fdm; fdm.Operator(...)``, reference
+    fractulus/test/unit/test_equation.py:3-4, test/integration/test_equation.py:1,7) when the real ``fdm`` package is not
+    installed.  The module carries ``__fdm_shim__`` so that fractulus_b200.equation keeps returning carrier objects."""
+    import sys
+    import types
+    me = sys.modules[__name__]
+    fdm = types.ModuleType('fdm')
+    fdm.__fdm_shim__ = True
+    eq, geo = types.ModuleType('fdm.equation'), types.ModuleType('fdm.geometry')
+    for name in ('Stencil', 'Number', 'Operator', 'Element'):
+        setattr(fdm, name, getattr(me, name))
+        setattr(eq, name, getattr(me, name))
+    geo.Point = fdm.Point = Point
+    fdm.equation, fdm.geometry = eq, geo
+    fdm.__path__ = []
+    sys.modules['fdm'], sys.modules['fdm.equation'], sys.modules['fdm.geometry'] = fdm, eq, geo
+    return fdm

@@ -22,6 +22,17 @@
 #include <omp.h>
 #endif
 
+/* -DORC_CR_POW: the same restatement with the correctly rounded pow / exp of the product's scalar math
+ * (fractulus_b200/csrc/frx_math.cuh, host build in oracle/cr_math.cpp) instead of glibc's.  That variant
+ * (oracle/_build/libfrx_oracle_cr.so) isolates summation order from pow rounding: the GPU must agree with it to
+ * 1e-12 on every row (tests/test_gpu_history.py), while the glibc build stays the restatement of the reference. */
+#ifdef ORC_CR_POW
+double orc_cr_pow(double x, double y);
+double orc_cr_exp(double x);
+#define pow orc_cr_pow
+#define exp orc_cr_exp
+#endif
+
 #define ORC_OK 0
 #define ORC_ERR_RULE -1
 #define ORC_ERR_DOMAIN -2
@@ -156,7 +167,9 @@ static int check_domain(int rule, double alpha, double res) {
     if (rule < 0 || rule > 3) return ORC_ERR_RULE;
     if (res == 0.) return ORC_ERR_ZERODIV;
     if (res < 0. || res != floor(res) || !(alpha >= 0.)) return ORC_ERR_DOMAIN;
-    if (rule != 0 && alpha > 1.) return rule == 1 ? ORC_ERR_ZERODIV : ORC_ERR_DOMAIN;
+    if (rule == 1 && alpha > 1.) return ORC_ERR_ZERODIV;   /* 0.0 ** negative, equation.py:68 */
+    if (rule == 2 && alpha > 2.) return ORC_ERR_ZERODIV;   /* 0.0 ** negative, equation.py:95 */
+    if (rule == 3 && alpha >= 2.) return ORC_ERR_DOMAIN;   /* gamma(2 - alpha) pole / complex weights */
     if (rule == 1 && res < 2.) return ORC_ERR_ZERODIV;  /* zero-interval uniform stencil */
     if (rule == 3 && res < 2.) return ORC_ERR_DOMAIN;   /* (m-2)**x with m=1 is complex in Python */
     return ORC_OK;
@@ -308,6 +321,14 @@ int orc_history_solve(int rule, double alpha, double h, long N, const double* f,
     }
     free(cA);
     return ORC_OK;
+}
+
+/* this build's pow (glibc's, or the correctly rounded one with -DORC_CR_POW): lets tests locate the arguments on
+ * which the two differ */
+double orc_pow(double x, double y) { return pow(x, y); }
+void orc_pow_many(const double* x, const double* y, double* out, long n) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) out[i] = pow(x[i], y[i]);
 }
 
 int orc_num_threads(void) {

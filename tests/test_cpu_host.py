@@ -50,6 +50,9 @@ def test_layout_matches_unmodified_reference(golden_stencils):
         for side in ('left', 'right', 'riesz_caputo'):
             rc = L.frx_stencil_layout(_lib.RULES[c['rule']], _lib.SIDES[side], float.fromhex(c['alpha']),
                                       float(c['resolution']), ctypes.byref(first), ctypes.byref(count))
+            if 'raises' in c[side]:          # alpha = 2: gamma(2. - alpha) at a pole (reference: ValueError, equation.py:23)
+                assert rc == -5
+                continue
             assert rc == 0
             assert (first.value, count.value) == (c[side]['first_offset'], c[side]['count']), (c['rule'], side)
 

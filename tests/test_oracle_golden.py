@@ -43,8 +43,12 @@ def test_stencils_vs_unmodified_reference_bit_exact(impl, golden_stencils):
         settings = S(float.fromhex(c['alpha']), float.fromhex(c['lf']), c['resolution'])
         for side, fn in (('left', impl.left_arrays), ('right', impl.right_arrays),
                          ('riesz_caputo', impl.riesz_caputo_arrays)):
-            first, w = fn(c['rule'], settings)
             rec = c[side]
+            if 'raises' in rec:              # alpha = 2: the Riesz-Caputo constant gamma(2. - alpha) is at a pole
+                with pytest.raises(ValueError):
+                    fn(c['rule'], settings)
+                continue
+            first, w = fn(c['rule'], settings)
             assert first == rec['first_offset'] and len(w) == rec['count'], (c['rule'], settings, side)
             assert [float(x).hex() for x in w] == rec['weights'], (c['rule'], settings, side)
             checked += 1
