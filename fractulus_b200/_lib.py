@@ -31,6 +31,8 @@ SIGNATURES = {
     'frx_ctx_set_stream': (ctypes.c_int, [c_void_p, c_void_p]),
     'frx_ctx_synchronize': (ctypes.c_int, [c_void_p]),
     'frx_ctx_launch_count': (ctypes.c_int, [c_void_p, c_int64_p]),
+    'frx_host_register': (ctypes.c_int, [c_void_p, ctypes.c_uint64]),
+    'frx_host_unregister': (ctypes.c_int, [c_void_p]),
     'frx_ctx_set_timing': (ctypes.c_int, [c_void_p, ctypes.c_int]),
     'frx_ctx_kernel_times': (ctypes.c_int, [c_void_p, c_double_p, c_int64_p]),
     'frx_stencil_layout': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,

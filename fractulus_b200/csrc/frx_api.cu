@@ -94,6 +94,28 @@ extern "C" int frx_ctx_set_stream(frx_ctx* ctx, void* s) {
     return FRX_OK;
 }
 
+extern "C" int frx_host_register(void* h_ptr, uint64_t bytes) {
+    FRX_REQUIRE(h_ptr != nullptr && bytes > 0, FRX_ERR_INVALID_ARG, "NULL pointer or zero size");
+    cudaError_t e = cudaHostRegister(h_ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return FRX_OK;
+    }
+    FRX_CUDA(e);
+    return FRX_OK;
+}
+
+extern "C" int frx_host_unregister(void* h_ptr) {
+    FRX_REQUIRE(h_ptr != nullptr, FRX_ERR_INVALID_ARG, "NULL pointer");
+    cudaError_t e = cudaHostUnregister(h_ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        return FRX_OK;
+    }
+    FRX_CUDA(e);
+    return FRX_OK;
+}
+
 int frx_hstage_reserve(frx_ctx* ctx, size_t bytes) {
     FRX_ON_DEVICE(ctx);
     if (ctx->hstage_pending) {

@@ -64,11 +64,21 @@ const char* frx_last_error_string(void);
 int frx_device_count(int* n_devices);
 int frx_ctx_create(int device, frx_ctx** out);
 int frx_ctx_destroy(frx_ctx* ctx);
-/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = legacy default */
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = legacy default.
+ * A context owns ONE workspace: everything it queues executes in order.  Moving it to another stream inserts an event
+ * dependency (work queued so far on the old stream happens-before work queued afterwards on the new one). */
 int frx_ctx_set_stream(frx_ctx* ctx, void* cuda_stream);
 int frx_ctx_synchronize(frx_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int frx_ctx_launch_count(frx_ctx* ctx, int64_t* n_launches);
+
+/* Page-lock and map an existing host allocation (cudaHostRegister, portable + mapped) so that the "_host" entry points
+ * use it IN PLACE: the prepare kernel reads fields from it and the history kernel's epilogue stores result rows into it
+ * over PCIe, no staging copies.  Meant for buffers this library's caller did not allocate with cudaHostAlloc -- in
+ * particular a POSIX shared-memory segment that every process of a multi-GPU sweep maps, so that each GPU stores its
+ * share of the result straight into the one host array (fractulus_b200/sweep.py).  No counterpart in the reference. */
+int frx_host_register(void* h_ptr, uint64_t bytes);
+int frx_host_unregister(void* h_ptr);
 
 /* Per-kernel device timing with CUDA events on the context's stream (off by default; adds two event
  * records per launch).  frx_ctx_kernel_times synchronises, then fills ms[k] / calls[k] for the kernel

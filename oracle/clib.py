@@ -40,6 +40,8 @@ def lib(cr=False):
                                              lp, ctypes.c_long, dp, ctypes.c_int]
         L.orc_history_full.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long, dp,
                                        ctypes.c_long, ctypes.c_long, ctypes.c_long, dp, ctypes.c_long, ctypes.c_int]
+        L.orc_history_full_abs.argtypes = L.orc_history_full.argtypes
+        L.orc_history_rows_naive_abs.argtypes = L.orc_history_rows_naive.argtypes
         L.orc_history_solve.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long, dp, ctypes.c_double, dp]
         L.orc_pow.restype = ctypes.c_double
         L.orc_pow.argtypes = [ctypes.c_double, ctypes.c_double]
@@ -113,22 +115,25 @@ def tables(rule, alpha, h, N, cr=False):
     return cA, cB, w0, mult, cm1.value
 
 
-def history_rows_naive(rule, alpha, h, g, rows, n_threads=0, cr=False):
-    """The reference's own algorithm: every row rebuilds its stencil (O(i) pow) and sums."""
+def history_rows_naive(rule, alpha, h, g, rows, n_threads=0, cr=False, abs_terms=False):
+    """The reference's own algorithm: every row rebuilds its stencil (O(i) pow) and sums.
+    abs_terms: sum of |g_j w_ij| instead (the rounding scale of an uncompensated sum of that row)."""
     g = np.ascontiguousarray(g, dtype=np.float64)
     rows = np.ascontiguousarray(rows, dtype=np.int64)
     y = np.empty(len(rows))
-    lib(cr).orc_history_rows_naive(RULE_CODE[rule], float(alpha), float(h), _dp(g), len(g),
+    fn = lib(cr).orc_history_rows_naive_abs if abs_terms else lib(cr).orc_history_rows_naive
+    fn(RULE_CODE[rule], float(alpha), float(h), _dp(g), len(g),
                                  rows.ctypes.data_as(ctypes.POINTER(ctypes.c_long)), len(rows), _dp(y), n_threads)
     return y
 
 
-def history_full(rule, alpha, h, N, g, n_threads=0, cr=False):
+def history_full(rule, alpha, h, N, g, n_threads=0, cr=False, abs_terms=False):
     """Same values for rows 0..N (row 0 = 0), table-accelerated; g is [n_g] or [n_fields, n_g]."""
     g = np.ascontiguousarray(g, dtype=np.float64)
     g2 = g.reshape(-1, g.shape[-1])
     y = np.empty((g2.shape[0], N + 1))
-    _raise(lib(cr).orc_history_full(RULE_CODE[rule], float(alpha), float(h), N, _dp(g2), g2.shape[1], g2.shape[0],
+    fn = lib(cr).orc_history_full_abs if abs_terms else lib(cr).orc_history_full
+    _raise(fn(RULE_CODE[rule], float(alpha), float(h), N, _dp(g2), g2.shape[1], g2.shape[0],
                                   g2.shape[1], _dp(y), N + 1, n_threads))
     return y.reshape(g.shape[:-1] + (N + 1,))
 

@@ -238,8 +238,8 @@ static inline double nsum_get(const nsum* s) { return s->total + s->comp; }
 /* Growing-history application, the reference's own algorithm (test/integration/test_equation.py:51-57):
  * for every requested row i the stencil of Settings(alpha, i*h, i) is REBUILT FROM SCRATCH
  * (O(i) pow calls) and y_i = sum(g[node] * weight).  g has n_g entries (node 0..n_g-1). */
-int orc_history_rows_naive(int rule, double alpha, double h, const double* g, long n_g,
-                           const long* rows, long n_rows, double* y, int n_threads) {
+static int history_rows_naive_impl(int rule, double alpha, double h, const double* g, long n_g,
+                                   const long* rows, long n_rows, double* y, int n_threads, int abs_terms) {
     if (rule < 0 || rule > 3) return ORC_ERR_RULE;
     int err = 0;
 #ifdef _OPENMP
@@ -255,19 +255,30 @@ int orc_history_rows_naive(int rule, double alpha, double h, const double* g, lo
         double* w = (double*)malloc(sizeof(double) * (size_t)count);
         orc_left_weights(rule, alpha, (double)i * h, (double)i, &first, &count, w);
         nsum s = {0., 0.};
-        for (int k = 0; k < count; ++k) nsum_add(&s, g[i + first + k] * w[k]);
+        for (int k = 0; k < count; ++k) nsum_add(&s, abs_terms ? fabs(g[i + first + k] * w[k]) : g[i + first + k] * w[k]);
         y[r] = nsum_get(&s);
         free(w);
     }
     return err ? ORC_ERR_DOMAIN : ORC_OK;
+}
+int orc_history_rows_naive(int rule, double alpha, double h, const double* g, long n_g,
+                           const long* rows, long n_rows, double* y, int n_threads) {
+    return history_rows_naive_impl(rule, alpha, h, g, n_g, rows, n_rows, y, n_threads, 0);
+}
+/* S_i = sum_j |g_j * w_ij|: the scale of the rounding error of ANY uncompensated FP64 summation of row i (tests use
+ * it for the condition-aware part of the parity tolerance at zero crossings of y) */
+int orc_history_rows_naive_abs(int rule, double alpha, double h, const double* g, long n_g,
+                               const long* rows, long n_rows, double* y, int n_threads) {
+    return history_rows_naive_impl(rule, alpha, h, g, n_g, rows, n_rows, y, n_threads, 1);
 }
 
 /* Same values, table-accelerated (raw weights depend on the distance only, so one O(N) table
  * serves every row; identical floating-point operations per term => bit-identical results,
  * asserted against orc_history_rows_naive in tests/test_oracle_golden.py).  Rows 1..N -> y[1..N]
  * (y[0] = 0; rows outside the rule's domain = NaN). n_fields fields of stride ld_g / ld_y. */
-int orc_history_full(int rule, double alpha, double h, long N, const double* g, long n_g, long n_fields,
-                     long ld_g, double* y, long ld_y, int n_threads) {
+#define ORC_T(x) (abs_terms ? fabs(x) : (x))
+static int history_full_impl(int rule, double alpha, double h, long N, const double* g, long n_g, long n_fields,
+                             long ld_g, double* y, long ld_y, int n_threads, int abs_terms) {
     if (rule < 0 || rule > 3) return ORC_ERR_RULE;
     if (n_g < N + 1 + (rule == 3)) return ORC_ERR_DOMAIN;
     double* cA = (double*)malloc(sizeof(double) * (size_t)(N + 1) * 4);
@@ -285,21 +296,29 @@ int orc_history_full(int rule, double alpha, double h, long N, const double* g, 
             if (check_domain(rule, alpha, (double)i)) { yf[i] = NAN; continue; }
             double m = mult[i];
             nsum s = {0., 0.};
-            if (rule != 1) nsum_add(&s, gf[0] * (m * w0[i]));             /* node number 0 */
+            if (rule != 1) nsum_add(&s, ORC_T(gf[0] * (m * w0[i])));             /* node number 0 */
             if (rule == 3) {
                 for (long d = i - 1; d >= 0; --d) {
                     long j = i - d;
-                    nsum_add(&s, gf[j] * (m * ((j & 1) ? cB[d] : cA[d])));
+                    nsum_add(&s, ORC_T(gf[j] * (m * ((j & 1) ? cB[d] : cA[d]))));
                 }
-                if (i & 1) nsum_add(&s, gf[i + 1] * (m * cm1));
+                if (i & 1) nsum_add(&s, ORC_T(gf[i + 1] * (m * cm1)));
             } else {
-                for (long d = i - 1; d >= 0; --d) nsum_add(&s, gf[i - d] * (m * cA[d]));
+                for (long d = i - 1; d >= 0; --d) nsum_add(&s, ORC_T(gf[i - d] * (m * cA[d])));
             }
             yf[i] = nsum_get(&s);
         }
     }
     free(cA);
     return ORC_OK;
+}
+int orc_history_full(int rule, double alpha, double h, long N, const double* g, long n_g, long n_fields,
+                     long ld_g, double* y, long ld_y, int n_threads) {
+    return history_full_impl(rule, alpha, h, N, g, n_g, n_fields, ld_g, y, ld_y, n_threads, 0);
+}
+int orc_history_full_abs(int rule, double alpha, double h, long N, const double* g, long n_g, long n_fields,
+                         long ld_g, double* y, long ld_y, int n_threads) {
+    return history_full_impl(rule, alpha, h, N, g, n_g, n_fields, ld_g, y, ld_y, n_threads, 1);
 }
 
 /* Inverse of the growing-history operator by forward substitution with the reference's own weights

@@ -51,12 +51,6 @@ def rel_err(got, want):
 #       before the first differing power agree at 1e-12; beyond it the deviation of ANY implementation whose pow differs
 #       from glibc's in one ulp is |cr - glibc|, which is what is allowed there (and not a byte more).
 
-def contract_scale(want):
-    """relative to |y_i|, floored at 1e-3 of max|y| where y crosses zero"""
-    want = np.abs(np.asarray(want))
-    return np.maximum(want, 1e-3 * want.max())
-
-
 def boundary_power_flags(rule, alpha, N):
     """flag[i] (i = 0..N): one of the powers that enter row i NOT as part of a complete (+1,-2,+1) triple -- its first
     column (equation.py:49,90) and its last Toeplitz weight -- differs between glibc pow and the correctly rounded pow."""
@@ -88,19 +82,25 @@ def first_differing_power(rule, alpha, N):
     return first
 
 
-def assert_history_parity(rule, alpha, h, N, rows, got, want_glibc, want_cr):
-    """got / want_*: values at `rows` (ascending).  See the contract above."""
+SUM_EPS = 8 * np.finfo(float).eps
+
+
+def assert_history_parity(rule, alpha, h, N, rows, got, want_glibc, want_cr, abs_sum):
+    """got / want_*: values at `rows` (ascending); abs_sum: S_i = sum_j |g_j w_ij| of those rows (oracle).  See the
+    contract above.  Tolerance of a row: 1e-12 |y_i| + 8 eps S_i -- the second term is the rounding of a plain FP64 sum
+    of the row's terms (the reference adds them with CPython's compensated sum(), the kernel tile by tile); on the
+    BASELINE smooth fields it is < 2e-13 |y_i|, it only matters where y crosses zero."""
     rows = np.asarray(rows)
-    got, want_glibc, want_cr = np.asarray(got), np.asarray(want_glibc), np.asarray(want_cr)
+    got, want_glibc, want_cr, abs_sum = (np.asarray(x) for x in (got, want_glibc, want_cr, abs_sum))
     # (a) summation order only: every row
     err_cr = np.abs(got - want_cr)
-    tol_cr = RTOL * contract_scale(want_cr)
+    tol_cr = RTOL * np.abs(want_cr) + SUM_EPS * abs_sum
     bad = err_cr > tol_cr
-    assert not bad.any(), (rule, alpha, N, 'vs correctly-rounded oracle', rows[bad][:5], (err_cr / contract_scale(want_cr))[bad][:5])
+    assert not bad.any(), (rule, alpha, N, 'vs correctly-rounded oracle', rows[bad][:5], (err_cr / tol_cr)[bad][:5])
     # (b) against the reference's own arithmetic
     err = np.abs(got - want_glibc)
-    scale = contract_scale(want_glibc)
-    outside = err > RTOL * scale
+    tol = RTOL * np.abs(want_glibc) + SUM_EPS * abs_sum
+    outside = err > tol
     if rule == 'simpson':
         x0 = first_differing_power(rule, alpha, N)
         assert not outside[rows < x0 - 2].any(), (rule, alpha, N, rows[outside][:5])
@@ -108,14 +108,15 @@ def assert_history_parity(rule, alpha, h, N, rows, got, want_glibc, want_cr):
         flag = boundary_power_flags(rule, alpha, N)[rows]
         assert not (outside & ~flag).any(), (rule, alpha, N, 'row outside 1e-12 whose boundary powers do not differ',
                                              rows[outside & ~flag][:5])
-        assert flag.mean() < 0.01
     # nowhere more than the pow rounding itself explains
-    assert np.all(err <= RTOL * scale + np.abs(want_cr - want_glibc) + tol_cr), (rule, alpha, N)
+    assert np.all(err <= tol + np.abs(want_cr - want_glibc) + tol_cr), (rule, alpha, N)
     return float(np.mean(~outside))
 
 
 def both_oracles_full(rule, alpha, h, N, g):
-    return clib.history_full(rule, alpha, h, N, g), clib.history_full(rule, alpha, h, N, g, cr=True)
+    """(glibc oracle, correctly-rounded oracle, sum of |terms|) for rows 0..N"""
+    return (clib.history_full(rule, alpha, h, N, g), clib.history_full(rule, alpha, h, N, g, cr=True),
+            clib.history_full(rule, alpha, h, N, g, cr=True, abs_terms=True))
 
 
 def test_tables_vs_c_oracle():
@@ -152,7 +153,8 @@ def test_history_vs_unmodified_reference_rows(golden_history):
         rows = np.array(c['rows'])
         want = np.array(unhex(c['y']))
         want_cr = clib.history_rows_naive(c['rule'], alpha, h, g_h, rows, cr=True)
-        assert_history_parity(c['rule'], alpha, h, N, rows, y[rows], want, want_cr)
+        abs_sum = clib.history_rows_naive(c['rule'], alpha, h, g_h, rows, cr=True, abs_terms=True)
+        assert_history_parity(c['rule'], alpha, h, N, rows, y[rows], want, want_cr, abs_sum)
         assert y[0] == 0.
 
 
@@ -166,10 +168,10 @@ def test_cfg2_full_size_every_row_vs_both_oracles(rule, alpha):
     N, h = 100000, 1e-5
     g = np.array(smooth_field(N + 2, h))
     y = batched.history(rule, alpha, h, dev(g), N=N).cpu().numpy()
-    want, want_cr = both_oracles_full(rule, alpha, h, N, g)
+    want, want_cr, abs_sum = both_oracles_full(rule, alpha, h, N, g)
     lo = FIRST_ROW[rule]
     rows = np.arange(lo, N + 1)
-    strict = assert_history_parity(rule, alpha, h, N, rows, y[rows], want[rows], want_cr[rows])
+    strict = assert_history_parity(rule, alpha, h, N, rows, y[rows], want[rows], want_cr[rows], abs_sum[rows])
     if rule != 'simpson':
         assert strict > 0.995, strict                       # > 99.5 % of the rows are within plain 1e-12 of the reference
 
@@ -201,13 +203,13 @@ def test_history_ragged_sizes_vs_c_oracle(N):
     h = 1. / max(N, 4)
     g = np.array(smooth_field(N + 2, h))
     for rule in RULES:
-        want, want_cr = both_oracles_full(rule, 0.37, h, N, g)
+        want, want_cr, abs_sum = both_oracles_full(rule, 0.37, h, N, g)
         got = batched.history(rule, 0.37, h, dev(g), N=N).cpu().numpy()
         lo = FIRST_ROW[rule]
         assert got[0] == 0.
         assert np.all(np.isnan(got[1:lo])) and np.all(np.isnan(want[1:lo]))
         if N >= lo:
-            assert_history_parity(rule, 0.37, h, N, np.arange(lo, N + 1), got[lo:], want[lo:], want_cr[lo:])
+            assert_history_parity(rule, 0.37, h, N, np.arange(lo, N + 1), got[lo:], want[lo:], want_cr[lo:], abs_sum[lo:])
 
 
 def test_history_alpha_and_field_batches_vs_c_oracle():
@@ -221,9 +223,10 @@ def test_history_alpha_and_field_batches_vs_c_oracle():
         assert got.shape == (5, 3, N + 1)
         lo = FIRST_ROW[rule]
         for ai, a in enumerate(alphas):
-            want, want_cr = both_oracles_full(rule, a, h, N, fields)
+            want, want_cr, abs_sum = both_oracles_full(rule, a, h, N, fields)
             for f in range(3):
-                assert_history_parity(rule, a, h, N, np.arange(lo, N + 1), got[ai][f, lo:], want[f, lo:], want_cr[f, lo:])
+                assert_history_parity(rule, a, h, N, np.arange(lo, N + 1), got[ai][f, lo:], want[f, lo:], want_cr[f, lo:],
+                                      abs_sum[f, lo:])
 
 
 def test_history_host_entry_point_equals_device_entry_point():
@@ -282,10 +285,11 @@ def test_toeplitz_apply_many_fields_vs_c_oracle():
     G = k[:, None] * np.cos(k[:, None] * x[None, :]) + 2. * x[None, :]
     for rule in ('caputo', 'simpson'):
         got = batched.toeplitz_apply(rule, 0.45, h, dev(G), N=N).cpu().numpy()
-        want, want_cr = both_oracles_full(rule, 0.45, h, N, G)
+        want, want_cr, abs_sum = both_oracles_full(rule, 0.45, h, N, G)
         lo = FIRST_ROW[rule]
         for f in range(0, B, 7):
-            assert_history_parity(rule, 0.45, h, N, np.arange(lo, N + 1), got[f, lo:], want[f, lo:], want_cr[f, lo:])
+            assert_history_parity(rule, 0.45, h, N, np.arange(lo, N + 1), got[f, lo:], want[f, lo:], want_cr[f, lo:],
+                                  abs_sum[f, lo:])
         # a field through K3 equals the same field through K2 up to the split-tile summation grouping
         # (results are bitwise reproducible per call shape, the stream-K split points depend on the batch)
         one = batched.history(rule, 0.45, h, dev(G[5]), N=N).cpu().numpy()
@@ -305,8 +309,8 @@ def test_toeplitz_apply_full_size_cfg3_sampled_fields():
     assert torch.max((Y[B - 1] - (Y[0] + Y[1])).abs() / scale).item() < 1e-13
     for f in (0, 1, 777, 2048, 4000, 4094):
         gf = G[f].cpu().numpy()
-        want, want_cr = both_oracles_full('caputo', 0.5, h, N, gf)
-        assert_history_parity('caputo', 0.5, h, N, np.arange(1, N + 1), Y[f, 1:].cpu().numpy(), want[1:], want_cr[1:])
+        want, want_cr, abs_sum = both_oracles_full('caputo', 0.5, h, N, gf)
+        assert_history_parity('caputo', 0.5, h, N, np.arange(1, N + 1), Y[f, 1:].cpu().numpy(), want[1:], want_cr[1:], abs_sum[1:])
 
 
 def _oracle_sided_rows(rule, alpha, h, g, N, rows):
@@ -442,7 +446,8 @@ def test_beyond_baseline_size_sampled_rows():
     rows = np.array([1, 2, 1023, 1024, 1025, 65536, 131071, 131072, 200001, N - 1, N])
     want = clib.history_rows_naive('caputo', 0.35, h, g, rows)
     want_cr = clib.history_rows_naive('caputo', 0.35, h, g, rows, cr=True)
-    assert_history_parity('caputo', 0.35, h, N, rows, y[rows], want, want_cr)
+    abs_sum = clib.history_rows_naive('caputo', 0.35, h, g, rows, cr=True, abs_terms=True)
+    assert_history_parity('caputo', 0.35, h, N, rows, y[rows], want, want_cr, abs_sum)
 
 
 def test_history_solve_inverts_the_operator():

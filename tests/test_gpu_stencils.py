@@ -137,7 +137,9 @@ def test_all_golden_stencils_layout_exact_weights_within_ulps(golden_stencils):
             differing += int(ne.sum())
             if res <= 16:
                 assert not ne.any(), (c['rule'], s, side)
-            assert np.all(np.abs(st.weights_array - ref) <= tol), (c['rule'], s, side)
+            # the Riesz-Caputo constant 1/2 gamma(2 - alpha) (equation.py:23) scales the left weights' differences: > 1 for alpha -> 2
+            tol_side = tol * (max(1., math.gamma(2. - a)) if side == 'riesz_caputo' else 1.)
+            assert np.all(np.abs(st.weights_array - ref) <= tol_side), (c['rule'], s, side)
             if 'nodes' in rec:      # node coordinates: the same Points
                 assert set(st._weights) == {Point(x) for x in unhex(rec['nodes'])}
     assert differing <= 0.005 * total, (differing, total)
