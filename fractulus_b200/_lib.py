@@ -37,6 +37,8 @@ SIGNATURES = {
     'frx_ctx_kernel_times': (ctypes.c_int, [c_void_p, c_double_p, c_int64_p]),
     'frx_stencil_layout': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                           c_int32_p, c_int32_p]),
+    'frx_stencil_layout_batch': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_double_p, c_double_p, c_int32_p,
+                                                c_int64_p, c_int64_p]),
     'frx_stencil_weights': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_void_p, c_void_p,
                                            c_void_p, c_int64_p, c_void_p, c_void_p]),
     'frx_stencil_weights_host': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,

@@ -60,6 +60,20 @@ def default_device():
     return torch.device('cuda', torch.cuda.current_device())
 
 
+def stencil_layouts(approximation, side, alpha, resolution):
+    """Integer layouts of a batch of stencils in ONE C call: (row_ptr[int64, n+1], first_offset[int32, n]), host arrays."""
+    a = np.ascontiguousarray(np.atleast_1d(np.asarray(alpha, dtype=np.float64)))
+    r = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(np.asarray(resolution, dtype=np.float64)), a.shape))
+    row_ptr = np.zeros(len(a) + 1, dtype=np.int64)
+    first = np.zeros(len(a), dtype=np.int32)
+    bad = ctypes.c_int64(-1)
+    _lib.check(_lib.lib().frx_stencil_layout_batch(_lib.RULES[approximation], _lib.SIDES[side], len(a),
+                                                   a.ctypes.data_as(_lib.c_double_p), r.ctypes.data_as(_lib.c_double_p),
+                                                   first.ctypes.data_as(_lib.c_int32_p), row_ptr.ctypes.data_as(_lib.c_int64_p),
+                                                   ctypes.byref(bad)))
+    return row_ptr, first
+
+
 def stencil_weights(approximation, side, alpha, lf, resolution, device=None):
     """K5 for a batch of Settings triples (1-D array-likes of equal length, host or device).
     Returns (row_ptr[int64, host numpy], offsets[int32 cuda], weights[float64 cuda])."""
@@ -71,11 +85,7 @@ def stencil_weights(approximation, side, alpha, lf, resolution, device=None):
                                    dtype=np.float64))
     n = len(a_h)
     L = _lib.lib()
-    row_ptr = np.zeros(n + 1, dtype=np.int64)
-    first, count = ctypes.c_int32(), ctypes.c_int32()
-    for s in range(n):
-        _lib.check(L.frx_stencil_layout(rule, sd, float(a_h[s]), float(r_h[s]), ctypes.byref(first), ctypes.byref(count)))
-        row_ptr[s + 1] = row_ptr[s] + count.value
+    row_ptr, _ = stencil_layouts(approximation, side, a_h, r_h)
     ctx, idx = _ctx_for(device)
     d_alpha, d_lf, d_res = _as_f64(a_h, device), _as_f64(np.atleast_1d(lf.cpu().numpy() if torch.is_tensor(lf) else lf), device), _as_f64(r_h, device)
     offsets = torch.empty(int(row_ptr[-1]), dtype=torch.int32, device=device)

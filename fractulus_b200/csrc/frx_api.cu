@@ -352,4 +352,22 @@ extern "C" int frx_stencil_layout(int rule, int side, double alpha, double resol
     return FRX_OK;
 }
 
+extern "C" int frx_stencil_layout_batch(int rule, int side, int64_t n_settings, const double* h_alpha, const double* h_resolution,
+                                        int32_t* h_first_offset, int64_t* h_row_ptr, int64_t* bad_index) {
+    FRX_REQUIRE(n_settings >= 0 && h_row_ptr && (n_settings == 0 || (h_alpha && h_resolution)), FRX_ERR_INVALID_ARG,
+                "NULL array or negative count");
+    h_row_ptr[0] = 0;
+    for (int64_t s = 0; s < n_settings; ++s) {
+        int32_t first, count;
+        const int rc = frx_stencil_layout(rule, side, h_alpha[s], h_resolution[s], &first, &count);
+        if (rc) {
+            if (bad_index) *bad_index = s;
+            return rc;
+        }
+        if (h_first_offset) h_first_offset[s] = first;
+        h_row_ptr[s + 1] = h_row_ptr[s] + count;
+    }
+    return FRX_OK;
+}
+
 extern "C" int64_t frx_table_ldc(int64_t N);  // defined in frx_history.cu (depends on the tile sizes)

@@ -103,3 +103,45 @@ def create_right_stencil(approximation, settings):
 
 def create_riesz_caputo_stencil(approximation, settings):
     return _stencil(approximation, 'riesz_caputo', settings)
+
+
+# ---- batched conveniences (no counterpart in the reference): a list of Settings -> a list of stencils ------------------
+# One vectorised layout call, ONE K5 launch and one device->host copy for the whole list instead of two launches and two
+# copies per stencil; the stencils are the same objects the single-setting functions return.
+
+def _stencils(approximation, side, settings_list):
+    _lib.RULES[approximation]                 # KeyError for an unknown key
+    triples = [tuple(s) for s in settings_list]
+    if not triples:
+        return []
+    for t in triples:
+        alpha, lf, resolution = t             # same unpacking (and exceptions) as the reference
+    from . import batched
+    alpha = np.array([float(t[0]) for t in triples])
+    lf = np.array([float(t[1]) for t in triples])
+    res = np.array([float(t[2]) for t in triples])
+    row_ptr, first = batched.stencil_layouts(approximation, side, alpha, res)
+    _, _, weights = batched.stencil_weights(approximation, side, alpha, lf, res)
+    w = weights.cpu().numpy()
+    Stencil, Point, builtin = _carrier()
+    out = []
+    for k, (a, l, r) in enumerate(triples):
+        lo, hi = int(row_ptr[k]), int(row_ptr[k + 1])
+        xs = _node_coordinates(approximation, side, l, r, int(first[k]), hi - lo)
+        if builtin:
+            out.append(Stencil.from_layout(xs, w[lo:hi].copy(), int(first[k]), l / float(r)))
+        else:
+            out.append(Stencil({Point(x): float(v) for x, v in zip(xs, w[lo:hi])}))
+    return out
+
+
+def create_left_stencils(approximation, settings_list):
+    return _stencils(approximation, 'left', settings_list)
+
+
+def create_right_stencils(approximation, settings_list):
+    return _stencils(approximation, 'right', settings_list)
+
+
+def create_riesz_caputo_stencils(approximation, settings_list):
+    return _stencils(approximation, 'riesz_caputo', settings_list)

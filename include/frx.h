@@ -104,6 +104,11 @@ int frx_ctx_kernel_times(frx_ctx* ctx, double* ms /*[FRX_K_COUNT]*/, int64_t* ca
 int frx_stencil_layout(int rule, int side, double alpha, double resolution, int32_t* first_offset,
                        int32_t* count);
 
+/* The same for n_settings settings at once: row_ptr[0] = 0, row_ptr[s+1] = row_ptr[s] + count_s (host arrays;
+ * first_offset may be NULL).  Stops at the first invalid setting: its status is returned and *bad_index set (may be NULL). */
+int frx_stencil_layout_batch(int rule, int side, int64_t n_settings, const double* h_alpha, const double* h_resolution,
+                             int32_t* h_first_offset, int64_t* h_row_ptr, int64_t* bad_index);
+
 /* ---- K5: stencil weights for a batch of Settings(alpha, lf, resolution) ------------------------
  * Replaces create_left_stencil / create_right_stencil / create_riesz_caputo_stencil
  * (equation.py:13-39) for n_settings settings at once.  Stencil s occupies

@@ -39,12 +39,17 @@ def main():
             want = clib.history_full(rule, alphas[a], h, N, g, cr=True)
             s = clib.history_full(rule, alphas[a], h, N, g, cr=True, abs_terms=True)
             err = np.abs(got[a, lo:] - want[lo:])
-            assert np.all(err <= 1e-12 * np.abs(want[lo:]) + 8 * eps * s[lo:]), (rank, rule, N, a, err.max())
-        # the fused path gives the bits of the plain single-GPU call
+            slack = np.sqrt(np.arange(lo, N + 1) / 4.) * eps * s[lo:]      # see tests/test_gpu_history.py summation_slack
+            assert np.all(err <= 1e-12 * np.abs(want[lo:]) + slack), (rank, rule, N, a, err.max())
+        # the fused path agrees with the plain single-GPU call up to the split-tile summation grouping (results are bitwise
+        # reproducible per launch shape; the stream-K split points depend on the kernel variant)
         b, e = sweep.partition(n_alpha, world, rank)
         if e > b:
-            mine = batched.history(rule, alphas[b:e], h, torch.as_tensor(g, device=dev), N=N)
-            assert torch.equal(mine.reshape(e - b, N + 1), full[b:e])
+            mine = batched.history(rule, alphas[b:e], h, torch.as_tensor(g, device=dev), N=N).reshape(e - b, N + 1)
+            d = (mine[:, lo:] - full[b:e, lo:]).abs().max().item()
+            assert d <= 1e-13 * mine[:, lo:].abs().max().item(), (rank, rule, N, d)
+        again = sweep.history_sweep(rule, alphas, h, torch.as_tensor(g, device=dev), N=N)      # (collective)
+        assert torch.equal(again[:, lo:], torch.as_tensor(got[:, lo:], device=dev))            # deterministic
         dist.barrier()
         # host field in, shared pinned host result out
         yh = sweep.history_sweep(rule, alphas, h, g, N=N, host_result='all')
@@ -58,7 +63,7 @@ def main():
     Y = sweep.toeplitz_apply_sweep('caputo', 0.45, h, G, N=N)
     want = clib.history_full('caputo', 0.45, h, N, G, cr=True)
     s = clib.history_full('caputo', 0.45, h, N, G, cr=True, abs_terms=True)
-    assert np.all(np.abs(Y[:, 1:] - want[:, 1:]) <= 1e-12 * np.abs(want[:, 1:]) + 8 * eps * s[:, 1:])
+    assert np.all(np.abs(Y[:, 1:] - want[:, 1:]) <= 1e-12 * np.abs(want[:, 1:]) + np.sqrt(np.arange(1, N + 1) / 4.) * eps * s[:, 1:])
     dist.barrier()
     n, n_sys = 48, 5 * world + 2
     rng = np.random.default_rng(11)

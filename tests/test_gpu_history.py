@@ -82,24 +82,30 @@ def first_differing_power(rule, alpha, N):
     return first
 
 
-SUM_EPS = 8 * np.finfo(float).eps
+def summation_slack(rows, abs_sum):
+    """Rounding of a plain FP64 sum of row i's terms: the kernel accumulates them on the FP64 tensor cores, 4 products per
+    DMMA, i.e. a chain of i/4 sequential accumulations -> the probabilistic rounding bound sqrt(i/4) eps S_i with
+    S_i = sum_j |w_ij g_j| (measured: <= 45 eps S_i at i = 39012, 'simpson' alpha = 1.5, next to a zero of y)."""
+    return np.sqrt(np.asarray(rows, dtype=np.float64) / 4.) * np.finfo(float).eps * np.asarray(abs_sum)
 
 
 def assert_history_parity(rule, alpha, h, N, rows, got, want_glibc, want_cr, abs_sum):
     """got / want_*: values at `rows` (ascending); abs_sum: S_i = sum_j |g_j w_ij| of those rows (oracle).  See the
-    contract above.  Tolerance of a row: 1e-12 |y_i| + 8 eps S_i -- the second term is the rounding of a plain FP64 sum
-    of the row's terms (the reference adds them with CPython's compensated sum(), the kernel tile by tile); on the
-    BASELINE smooth fields it is < 2e-13 |y_i|, it only matters where y crosses zero."""
+    contract above.  Tolerance of a row: 1e-12 |y_i| + summation_slack -- the second term is the rounding of a plain FP64
+    sum of the row's terms (the reference adds them with CPython's compensated sum(), the kernel accumulates them on the
+    tensor cores).  For the BASELINE cfg-2 field all terms of a row have one sign, S_i = |y_i| and the slack is
+    <= 3.5e-14 |y_i|: the bound IS 1e-12 relative there; it only matters where y crosses zero (sign-changing fields such
+    as cfg 3's cos(k x) family, or alpha > 1 where the operator differentiates)."""
     rows = np.asarray(rows)
     got, want_glibc, want_cr, abs_sum = (np.asarray(x) for x in (got, want_glibc, want_cr, abs_sum))
     # (a) summation order only: every row
     err_cr = np.abs(got - want_cr)
-    tol_cr = RTOL * np.abs(want_cr) + SUM_EPS * abs_sum
+    tol_cr = RTOL * np.abs(want_cr) + summation_slack(rows, abs_sum)
     bad = err_cr > tol_cr
     assert not bad.any(), (rule, alpha, N, 'vs correctly-rounded oracle', rows[bad][:5], (err_cr / tol_cr)[bad][:5])
     # (b) against the reference's own arithmetic
     err = np.abs(got - want_glibc)
-    tol = RTOL * np.abs(want_glibc) + SUM_EPS * abs_sum
+    tol = RTOL * np.abs(want_glibc) + summation_slack(rows, abs_sum)
     outside = err > tol
     if rule == 'simpson':
         x0 = first_differing_power(rule, alpha, N)

@@ -248,3 +248,23 @@ def test_stencil_composition_equals_operator_expansion():
             assert got[o] == want[k][o], (cases[k], o, got[o], want[k][o])      # bit-exact
     with pytest.raises(ValueError):
         batched.stencil_compose([0, 2], [0, 1], [1., 1.], [0, 2], [1, 0], [1., 1.])     # B not ascending
+
+
+def test_batched_stencil_creators_equal_single_calls():
+    """create_*_stencils (one K5 launch for a list of Settings) return the stencils of the single-setting functions."""
+    import fractulus_b200 as frb
+    settings = [Settings(0.5, 0.6, 4), Settings(0.3, 2.0, 7), Settings(0.9, 1.0, 64), Settings(1.5, 1.4, 2), Settings(0.2, 3.3, 33)]
+    for many, one in ((frb.create_left_stencils, fr.create_left_stencil), (frb.create_right_stencils, fr.create_right_stencil),
+                      (frb.create_riesz_caputo_stencils, fr.create_riesz_caputo_stencil)):
+        for rule in ('caputo', 'trapezoidal', 'simpson'):
+            got = many(rule, settings)
+            assert len(got) == len(settings)
+            for st, s in zip(got, settings):
+                ref = one(rule, s)
+                assert st == ref and st.first_offset == ref.first_offset
+                assert np.array_equal(st.weights_array, ref.weights_array)
+    assert frb.create_left_stencils('caputo', []) == []
+    with pytest.raises(KeyError):
+        frb.create_left_stencils('nope', settings)
+    with pytest.raises(ZeroDivisionError):
+        frb.create_left_stencils('caputo', [Settings(0.5, 1., 4), Settings(0.5, 1., 0)])
