@@ -283,7 +283,7 @@ def _solve_params(alpha, h, res, n_sys=None):
     return a, hh, rr
 
 
-def assemble_solve(approximation, alpha, h, res, rhs, return_info=False):
+def assemble_solve(approximation, alpha, h, res, rhs, return_info=False, out=None):
     """K4: for every system s assemble the matrix of d/dx o D^alpha_RC(lf = res*h) o d/dx on n interior nodes
     (u = 0 outside) in shared memory and solve A x = rhs[s] by in-kernel LU with partial pivoting.
 
@@ -295,7 +295,11 @@ def assemble_solve(approximation, alpha, h, res, rhs, return_info=False):
     n_sys, n = rhs.shape
     a, hh, rr = _solve_params(alpha, h, res, n_sys)
     ctx, idx = _ctx_for(rhs.device)
-    x = torch.empty_like(rhs)
+    if out is None:
+        x = torch.empty_like(rhs)
+    else:
+        x = out
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and tuple(x.shape) == (n_sys, n)
     info = torch.empty((n_sys,), dtype=torch.int32, device=rhs.device)
     _lib.check(_lib.lib().frx_assemble_solve(ctx.handle, rule, n_sys, n, a.ctypes.data_as(_lib.c_double_p),
                                              hh.ctypes.data_as(_lib.c_double_p), rr.ctypes.data_as(_lib.c_double_p),

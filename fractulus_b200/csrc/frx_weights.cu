@@ -143,6 +143,45 @@ __global__ void __launch_bounds__(128) frx_k5b_stencil_nodes(int rule, int side,
     if (offsets) offsets[e] = (int32_t)o;
 }
 
+// One Settings triple passed BY VALUE (the drop-in's create_*_stencil call): no parameter upload, one launch.  Every CTA
+// re-evaluates the scalars (a few microseconds) and then one node per thread -- the operations of k5a + k5b, same bits.
+__global__ void __launch_bounds__(128) frx_k5_single(int rule, int side, double alpha, double lf, double resolution,
+                                                     long long first, long long count, double* __restrict__ weights) {
+    __shared__ frx_k5_scalars S;
+    if (threadIdx.x == 0) {
+        S.P = frx_par_init(rule, alpha);
+        S.mult = frx_multiplier(S.P, lf, resolution);
+        S.K = FRX_DIV(FRX_MUL(0.5, frx_gamma_py(FRX_SUB(2.0, alpha))), 1.0);
+        S.sgn = (((long long)S.P.n) & 1) ? -1.0 : 1.0;
+    }
+    __syncthreads();
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const frx_par P = S.P;
+    const long long p = (long long)resolution;
+    long long lfirst, lcount;
+    frx_left_layout(rule, p, &lfirst, &lcount);
+    const long long llast = lfirst + lcount - 1;
+    const long long o = first + k;
+    const double mult = S.mult;
+    double w;
+    if (side == FRX_SIDE_LEFT) {
+        w = FRX_MUL(mult, frx_raw_at_offset(P, p, o));
+    } else if (side == FRX_SIDE_RIGHT) {
+        w = FRX_MUL(FRX_MUL(mult, frx_raw_at_offset(P, p, -o)), -1.0);
+    } else {
+        const bool in_left = (o >= lfirst && o <= llast), in_mirror = (-o >= lfirst && -o <= llast);
+        double acc = 0.0;
+        if (in_left) acc = FRX_MUL(mult, frx_raw_at_offset(P, p, o));
+        if (in_mirror) {
+            double r = FRX_MUL(S.sgn, FRX_MUL(FRX_MUL(mult, frx_raw_at_offset(P, p, -o)), -1.0));
+            acc = in_left ? FRX_ADD(acc, r) : r;
+        }
+        w = FRX_MUL(S.K, acc);
+    }
+    weights[k] = w;
+}
+
 size_t frx_k5_scratch_bytes(int64_t n_settings) { return sizeof(frx_k5_scalars) * (size_t)n_settings; }
 
 // K5 launch with the row pointer already on the device (also used by frx_assemble_solve).  d_scratch:
@@ -196,6 +235,20 @@ extern "C" int frx_stencil_weights_host(frx_ctx* ctx, int rule, int side, double
     *count = cnt;
     FRX_REQUIRE(capacity >= cnt, FRX_ERR_INVALID_ARG, "capacity smaller than the stencil length");
     FRX_ON_DEVICE(ctx);
+    if (rule != FRX_RULE_GRUNWALD_LETNIKOV) {
+        // one launch with the triple by value, one copy back; the offsets are first .. first + count - 1
+        int rc2 = frx_ws_reserve(ctx, sizeof(double) * (size_t)cnt);
+        if (rc2) return rc2;
+        FRX_LAUNCH(ctx, FRX_K_STENCIL,
+                   frx_k5_single<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(rule, side, alpha, lf, resolution,
+                                                                                       (long long)first, (long long)cnt,
+                                                                                       (double*)ctx->ws));
+        FRX_CUDA(cudaMemcpyAsync(h_weights, ctx->ws, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_offsets)
+            for (int32_t k = 0; k < cnt; ++k) h_offsets[k] = first + k;
+        FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+        return FRX_OK;
+    }
     // workspace: [row_ptr (2 x i64) + scalars, written by frx_stencil_weights] [3 doubles] [weights] [offsets]
     size_t off_par = 256 + frx_align_up(frx_k5_scratch_bytes(1), 256), off_w = off_par + 64,
            off_o = off_w + frx_align_up(sizeof(double) * cnt, 64);

@@ -70,26 +70,34 @@ def _node_coordinates(approximation, side, lf, resolution, first, count):
     return xs
 
 
+def _lazy_nodes(approximation, side, lf, resolution, first, count):
+    return lambda: _node_coordinates(approximation, side, lf, resolution, first, count)
+
+
 def _stencil(approximation, side, settings):
     rule = _lib.RULES[approximation]          # KeyError for an unknown key, like _factory[approximation]
     alpha, lf, resolution = settings          # same unpacking (and exceptions) as the reference
     L = _lib.lib()
-    first, count = ctypes.c_int32(), ctypes.c_int32()
-    _lib.check(L.frx_stencil_layout(rule, _lib.SIDES[side], float(alpha), float(resolution),
-                                    ctypes.byref(first), ctypes.byref(count)))
-    n = count.value
-    weights = np.empty(n, dtype=np.float64)
-    offsets = np.empty(n, dtype=np.int32)
+    alpha_f, lf_f, res_f = float(alpha), float(lf), float(resolution)
+    first_c, count_c = ctypes.c_int32(), ctypes.c_int32()
+    # the domain checks (KeyError / ZeroDivisionError / ValueError like the reference) need no GPU
+    _lib.check(L.frx_stencil_layout(rule, _lib.SIDES[side], alpha_f, res_f, ctypes.byref(first_c), ctypes.byref(count_c)))
+    cap = count_c.value
+    weights = np.empty(cap, dtype=np.float64)
+    offsets = np.empty(cap, dtype=np.int32)
     got = ctypes.c_int32()
     ctx = _lib.context()
-    _lib.check(L.frx_stencil_weights_host(ctx.handle, rule, _lib.SIDES[side], float(alpha), float(lf),
-                                          float(resolution), n, offsets.ctypes.data_as(_lib.c_int32_p),
-                                          weights.ctypes.data_as(_lib.c_double_p), ctypes.byref(got)))
-    assert got.value == n and offsets[0] == first.value
-    xs = _node_coordinates(approximation, side, lf, resolution, first.value, n)
+    _lib.check(L.frx_stencil_weights_host(ctx.handle, rule, _lib.SIDES[side], alpha_f, lf_f, res_f, cap,
+                                          offsets.ctypes.data_as(_lib.c_int32_p), weights.ctypes.data_as(_lib.c_double_p),
+                                          ctypes.byref(got)))
+    n = got.value
+    first = int(offsets[0])
+    weights = weights[:n]
     Stencil, Point, builtin = _carrier()
-    if builtin:
-        return Stencil.from_layout(xs, weights, first.value, lf / float(resolution))
+    if builtin:       # node coordinates and the {Point: weight} dictionary are produced when first asked for
+        return Stencil.from_layout(lambda: _node_coordinates(approximation, side, lf, resolution, first, n), weights, first,
+                                   lf / float(resolution))
+    xs = _node_coordinates(approximation, side, lf, resolution, first, n)
     return Stencil({Point(x): float(w) for x, w in zip(xs, weights)})
 
 
@@ -127,9 +135,10 @@ def _stencils(approximation, side, settings_list):
     out = []
     for k, (a, l, r) in enumerate(triples):
         lo, hi = int(row_ptr[k]), int(row_ptr[k + 1])
-        xs = _node_coordinates(approximation, side, l, r, int(first[k]), hi - lo)
+        xs = None if builtin else _node_coordinates(approximation, side, l, r, int(first[k]), hi - lo)
         if builtin:
-            out.append(Stencil.from_layout(xs, w[lo:hi].copy(), int(first[k]), l / float(r)))
+            out.append(Stencil.from_layout(_lazy_nodes(approximation, side, l, r, int(first[k]), hi - lo), w[lo:hi].copy(),
+                                           int(first[k]), l / float(r)))
         else:
             out.append(Stencil({Point(x): float(v) for x, v in zip(xs, w[lo:hi])}))
     return out

@@ -85,16 +85,28 @@ class Element(object):
 
 class Stencil(Element):
     def __init__(self, weights, first_offset=None, step=None, weights_array=None):
-        self._weights = dict(weights)
+        self._dict = dict(weights) if weights is not None else None
+        self._nodes = None
         self.first_offset = first_offset
         self.step = step
         self.weights_array = weights_array
 
+    @property
+    def _weights(self):
+        """{Point: weight} -- what the reference's call sites read (test/unit/test_equation.py:18).  A stencil built from
+        kernel output keeps its weights as an array and materialises the dictionary on first use."""
+        if self._dict is None:
+            xs = self._nodes() if callable(self._nodes) else self._nodes
+            self._dict = {Point(float(x)): float(v) for x, v in zip(xs, self.weights_array)}
+        return self._dict
+
     @classmethod
     def from_layout(cls, nodes_x, weights, first_offset, step):
-        """nodes_x: node coordinates; weights: float64 array (kept); integer layout remembered."""
-        w = np.asarray(weights, dtype=np.float64)
-        return cls({Point(float(x)): float(v) for x, v in zip(nodes_x, w)}, first_offset, step, w)
+        """nodes_x: node coordinates, or a callable producing them on demand; weights: float64 array (kept); integer
+        layout remembered.  The {Point: weight} dictionary is built lazily."""
+        st = cls(None, first_offset, step, np.asarray(weights, dtype=np.float64))
+        st._nodes = nodes_x
+        return st
 
     @classmethod
     def uniform(cls, left, right, resolution, weights_provider):
