@@ -606,15 +606,13 @@ def sub_cfg3(env, steps=5):
     Gh = batched.pinned_empty((B, N + 2))      # page-locked host fields (the e2e contract: inputs come from pinned host memory)
     torch.as_tensor(Gh).copy_(G)
     torch.cuda.synchronize()
+    Yh_pinned = batched.pinned_empty((B, N + 1))
     if world == 1:
         def e2e_step():
             return sweep.toeplitz_apply_sweep(RULE, 0.5, h, Gh, N=N)
-    else:
-        Gall = None     # every rank holds only its own block in this bench: the sweep API takes the full batch, so time the block path
+    else:      # weak scaling: every rank holds its own 4096 fields -- the per-rank host call the sweep API is made of
         def e2e_step():
-            Gd = torch.as_tensor(Gh).to(dev, non_blocking=True)
-            Yb = batched.toeplitz_apply(RULE, 0.5, h, Gd, N=N)
-            return Yb.cpu().numpy()
+            return batched.toeplitz_apply_host(RULE, 0.5, h, Gh, N=N, out=Yh_pinned)
     Yh = e2e_step()
     env['barrier']()
     t0 = time.perf_counter()
@@ -628,8 +626,9 @@ def sub_cfg3(env, steps=5):
         e2e_s = t.item()
     out['e2e'] = {'value': world * B * N / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3, 'h2d_bytes_per_step': 8 * B * (N + 2) * world,
                   'd2h_bytes_per_step': 8 * B * (N + 1) * world,
-                  'api': 'sweep.toeplitz_apply_sweep (NumPy fields in, shared pinned host result out)' if world == 1 else
-                         'per-rank block: NumPy fields -> device -> batched.toeplitz_apply -> NumPy',
+                  'api': 'sweep.toeplitz_apply_sweep (pinned NumPy fields in, shared pinned host result out; 512-field chunks, copies '
+                         'overlapped with the kernel)' if world == 1 else
+                         'batched.toeplitz_apply_host on every rank (its own block of fields; pinned NumPy in and out, chunked, overlapped)',
                   'note': 'PCIe-bound: %.0f MB each way per GPU' % (8 * B * (N + 1) / 1e6)}
     if rank == 0:
         f = 777
@@ -720,13 +719,13 @@ def sub_cfg4(env, n, steps=5):
     rhs_h = batched.pinned_empty((n_sys, n))    # page-locked host right-hand sides
     torch.as_tensor(rhs_h).copy_(rhs)
     torch.cuda.synchronize()
+    x_pinned = batched.pinned_empty((n_sys, n))
     if world == 1:
         def e2e_step():
             return sweep.assemble_solve_sweep(RULE, alpha, h, res, rhs_h)
     else:
         def e2e_step():
-            b = torch.as_tensor(rhs_h).to(dev, non_blocking=True)
-            return batched.assemble_solve(RULE, alpha, h, res, b).cpu().numpy()
+            return batched.assemble_solve_host(RULE, alpha, h, res, rhs_h, out=x_pinned)
     e2e_step()
     env['barrier']()
     t0 = time.perf_counter()
@@ -740,8 +739,9 @@ def sub_cfg4(env, n, steps=5):
         e2e_s = t.item()
     out['e2e'] = {'value': world * n_sys / e2e_s, 'unit': 'solves/s', 'ms_per_step': e2e_s * 1e3,
                   'h2d_bytes_per_step': (8 * n_sys * n + 24 * n_sys) * world, 'd2h_bytes_per_step': 8 * n_sys * n * world,
-                  'api': 'sweep.assemble_solve_sweep (NumPy rhs in, shared pinned host result out)' if world == 1 else
-                         'per-rank block: NumPy rhs -> device -> batched.assemble_solve -> NumPy'}
+                  'api': 'sweep.assemble_solve_sweep (pinned NumPy rhs in, shared pinned host result out; chunks of 16384 systems, copies '
+                         'overlapped with the solves)' if world == 1 else
+                         'batched.assemble_solve_host on every rank (its own systems; pinned NumPy in and out, chunked, overlapped)'}
     if rank == 0:
         from oracle import assemble
         k = 6

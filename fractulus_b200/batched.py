@@ -363,3 +363,77 @@ def history_host(approximation, alpha, h, g, N=None, device=None, out=None):
     if np.ndim(alpha) == 0:
         y = y[0]
     return y
+
+
+# ---- host-buffer forms of the many-fields / many-systems calls: chunked, copies overlapped with the kernels -----------------
+
+def _host_tensor(a):
+    """torch view of a host array without a copy (pinned / registered memory stays pinned: async copies)."""
+    return torch.as_tensor(a) if a.flags.c_contiguous and a.dtype == np.float64 else \
+        torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
+
+
+def _pipelined(host_in, host_out, chunk, width_in, width_out, run, dev):
+    """Rows of host_in -> run(device block) -> rows of host_out in chunks on three streams: chunk k+1 is uploaded while
+    chunk k computes and chunk k-1 is downloaded (double-buffered device blocks).  run(d_in, d_out) works on the CURRENT
+    stream.  With page-locked host arrays both copies are asynchronous DMA; pageable ones are staged by the driver."""
+    n = host_in.shape[0]
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    t_in, t_out = _host_tensor(host_in), torch.as_tensor(host_out)
+    d_in = [torch.empty((chunk, width_in), dtype=torch.float64, device=dev) for _ in range(2)]
+    d_out = [torch.empty((chunk, width_out), dtype=torch.float64, device=dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_cmp = [torch.cuda.Event() for _ in range(2)]
+    free_in = [torch.cuda.Event() for _ in range(2)]
+    free_out = [torch.cuda.Event() for _ in range(2)]
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    for k, b in enumerate(range(0, n, chunk)):
+        e, slot = min(n, b + chunk), k % 2
+        with torch.cuda.stream(s_in):
+            if k >= 2:
+                s_in.wait_event(free_in[slot])
+            d_in[slot][:e - b].copy_(t_in[b:e], non_blocking=True)
+            ev_in[slot].record(s_in)
+        cur.wait_event(ev_in[slot])
+        if k >= 2:
+            cur.wait_event(free_out[slot])
+        run(d_in[slot][:e - b], d_out[slot][:e - b], b, e)
+        free_in[slot].record(cur)
+        ev_cmp[slot].record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp[slot])
+            t_out[b:e].copy_(d_out[slot][:e - b], non_blocking=True)
+            free_out[slot].record(s_out)
+    cur.wait_stream(s_out)
+    cur.synchronize()
+
+
+def toeplitz_apply_host(approximation, alpha, h, G, N=None, out=None, chunk=512, device=None):
+    """K3 with host buffers: G NumPy [n_fields, n_g] in, Y NumPy [n_fields, N+1] out (`out`: e.g. a pinned or CUDA-registered
+    array, written in place).  Fields travel in chunks of `chunk`: upload, kernel and download of consecutive chunks overlap."""
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    n_fields, n_g = G.shape
+    if N is None:
+        N = n_g - 1 - (1 if approximation == 'simpson' else 0)
+    if out is None:
+        out = pinned_empty((n_fields, N + 1))
+    if n_fields:
+        _pipelined(G, out, max(1, min(n_fields, chunk)), n_g, N + 1,
+                   lambda d_in, d_out, b, e: toeplitz_apply(approximation, alpha, h, d_in, N=N, out=d_out), dev)
+    return out
+
+
+def assemble_solve_host(approximation, alpha, h, res, rhs, out=None, chunk=16384, device=None):
+    """K4 with host buffers: rhs NumPy [n_sys, n] in, x NumPy [n_sys, n] out, in chunks of `chunk` systems with the copies
+    overlapped with the solves."""
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    n_sys, n = rhs.shape
+    a, hh, rr = _solve_params(alpha, h, res, n_sys)
+    if out is None:
+        out = pinned_empty((n_sys, n))
+    if n_sys:
+        _pipelined(rhs, out, max(1, min(n_sys, chunk)), n, n,
+                   lambda d_in, d_out, b, e: assemble_solve(approximation, a[b:e], hh[b:e], rr[b:e], d_in, out=d_out), dev)
+    return out

@@ -249,49 +249,6 @@ def history_sweep(approximation, alphas, h, g, N=None, group=None, compute=None,
     return peer.buffer
 
 
-def _host_tensor(a):
-    """torch view of a host array without a copy (pinned / registered memory stays pinned: async copies)."""
-    return torch.as_tensor(a) if a.flags.c_contiguous and a.dtype == np.float64 else \
-        torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
-
-
-def _pipelined(host_in, host_out, chunk, width_in, width_out, run, dev):
-    """Rows of host_in -> run(device block) -> rows of host_out in chunks on three streams: chunk k+1 is uploaded while
-    chunk k computes and chunk k-1 is downloaded (double-buffered device blocks).  run(d_in, d_out) works on the CURRENT
-    stream.  With page-locked host arrays both copies are asynchronous DMA; pageable ones are staged by the driver."""
-    n = host_in.shape[0]
-    cur = torch.cuda.current_stream(dev)
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    t_in, t_out = _host_tensor(host_in), torch.as_tensor(host_out)
-    d_in = [torch.empty((chunk, width_in), dtype=torch.float64, device=dev) for _ in range(2)]
-    d_out = [torch.empty((chunk, width_out), dtype=torch.float64, device=dev) for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_cmp = [torch.cuda.Event() for _ in range(2)]
-    free_in = [torch.cuda.Event() for _ in range(2)]
-    free_out = [torch.cuda.Event() for _ in range(2)]
-    s_in.wait_stream(cur)
-    s_out.wait_stream(cur)
-    for k, b in enumerate(range(0, n, chunk)):
-        e, slot = min(n, b + chunk), k % 2
-        with torch.cuda.stream(s_in):
-            if k >= 2:
-                s_in.wait_event(free_in[slot])
-            d_in[slot][:e - b].copy_(t_in[b:e], non_blocking=True)
-            ev_in[slot].record(s_in)
-        cur.wait_event(ev_in[slot])
-        if k >= 2:
-            cur.wait_event(free_out[slot])
-        run(d_in[slot][:e - b], d_out[slot][:e - b], b, e)
-        free_in[slot].record(cur)
-        ev_cmp[slot].record(cur)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_cmp[slot])
-            t_out[b:e].copy_(d_out[slot][:e - b], non_blocking=True)
-            free_out[slot].record(s_out)
-    cur.wait_stream(s_out)
-    cur.synchronize()
-
-
 def toeplitz_apply_sweep(approximation, alpha, h, G, N=None, group=None, compute=None, host_result='all'):
     """ONE alpha applied to many fields (BASELINE cfg 3: the DMMA dense-contraction path), the FIELDS dealt to the ranks
     in contiguous blocks (the weight table is replicated: 128 KB).
@@ -316,10 +273,7 @@ def toeplitz_apply_sweep(approximation, alpha, h, G, N=None, group=None, compute
                    lambda: SharedHostArray((n_fields, N + 1), group, register=compute is None))
     if end > begin:
         if compute is None:
-            dev = torch.device('cuda', torch.cuda.current_device())
-            chunk = max(1, min(end - begin, 512))
-            _pipelined(G[begin:end], shared.array[begin:end], chunk, n_g, N + 1,
-                       lambda d_in, d_out, b, e: batched.toeplitz_apply(approximation, alpha, h, d_in, N=N, out=d_out), dev)
+            batched.toeplitz_apply_host(approximation, alpha, h, G[begin:end], N=N, out=shared.array[begin:end])
         else:
             shared.array[begin:end] = np.asarray(compute(alpha, G[begin:end]))
     _host_barrier(group, world)
@@ -353,12 +307,7 @@ def assemble_solve_sweep(approximation, alpha, h, res, rhs, group=None, compute=
     shared = _plan('host', (n_sys, n, id(group)), lambda: SharedHostArray((n_sys, n), group, register=compute is None))
     if end > begin:
         if compute is None:
-            dev = torch.device('cuda', torch.cuda.current_device())
-            chunk = max(1, min(end - begin, 16384))
-            a_l, h_l, r_l = a[sl], hh[sl], rr[sl]
-            _pipelined(rhs[sl], shared.array[sl], chunk, n, n,
-                       lambda d_in, d_out, b, e: batched.assemble_solve(approximation, a_l[b:e], h_l[b:e], r_l[b:e], d_in, out=d_out),
-                       dev)
+            batched.assemble_solve_host(approximation, a[sl], hh[sl], rr[sl], rhs[sl], out=shared.array[sl])
         else:
             shared.array[sl] = np.asarray(compute(a[sl], hh[sl], rr[sl], rhs[sl]))
     _host_barrier(group, world)

@@ -81,3 +81,27 @@ def test_solve_errors():
         batched.assemble_solve('nope', [0.5], 0.1, 2, rhs)
     with pytest.raises(ValueError):
         batched.assemble_solve('simpson', [0.5], 0.1, 3, rhs)     # odd Simpson stencil is not symmetric-closed
+
+
+def test_host_buffer_forms_equal_device_calls():
+    """batched.assemble_solve_host / toeplitz_apply_host (chunked, copies overlapped with the kernels) = the device calls."""
+    n, n_sys = 64, 5000
+    rng = np.random.default_rng(2)
+    alpha = rng.uniform(0.1, 0.9, n_sys)
+    res = rng.integers(1, 31, n_sys).astype(np.float64)
+    h = 1. / (n + 1)
+    rhs = rng.standard_normal((n_sys, n))
+    want = batched.assemble_solve('caputo', alpha, h, res, torch.as_tensor(rhs, device='cuda')).cpu().numpy()
+    got = batched.assemble_solve_host('caputo', alpha, h, res, rhs, chunk=1024)            # pageable in, pinned out
+    rhs_pin = batched.pinned_empty(rhs.shape)
+    rhs_pin[:] = rhs
+    out = batched.pinned_empty(rhs.shape)
+    got2 = batched.assemble_solve_host('caputo', alpha, h, res, rhs_pin, out=out, chunk=700)
+    assert np.shares_memory(got2, out)
+    # (per-chunk batches bin the systems differently, the arithmetic per system is the same)
+    assert np.array_equal(got, want) and np.array_equal(got2, want)
+    N, B = 1500, 37
+    G = rng.standard_normal((B, N + 2))
+    Yd = batched.toeplitz_apply('caputo', 0.4, 1. / N, torch.as_tensor(G, device='cuda'), N=N).cpu().numpy()
+    Yh = batched.toeplitz_apply_host('caputo', 0.4, 1. / N, G, N=N, chunk=8)
+    assert np.allclose(Yh[:, 1:], Yd[:, 1:], rtol=1e-12, atol=1e-12 * np.abs(Yd[:, 1:]).max())
