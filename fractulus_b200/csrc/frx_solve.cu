@@ -203,6 +203,7 @@ constexpr int kStreamWarps = 1;   // one-warp CTAs pack shared memory best
 constexpr int kStreamMaxNb = 31;
 constexpr int kStreamMaxN = 256;
 constexpr int kStreamBins = 4;    // bins by nb = res + 1: <= 7, <= 15, <= 23, <= 31
+constexpr int kDefaultTwoWarpBins = 0x0;  // FRX_K4_TWO_WARP bits 2,3: two warps per system in the wide-band bins (measured slower: DESIGN.md section 6)
 constexpr int kDefaultDmmaBins = 0xF;   // bins that run the blocked tensor-core kernel (frx_solve_dmma.cuh)
 __host__ __device__ inline int stream_c(int nb_max) { return 2 * nb_max + 1; }
 __host__ __device__ inline int stream_rs(int nb_max) { return ((stream_c(nb_max) + 7) & ~7) + 1; }   // ring padded to 8, +1 -> odd
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
 struct BinLaunch {
     int64_t grid;
     size_t dyn, scratch;
-    int kind;   // 0: frx_k4_band_stream, 1..4: frx_k4_band_dmma<1,3> / <2,5> / <3,7> / <4,9>
+    int kind;   // 0: frx_k4_band_stream, 1..4: frx_k4_band_dmma<1,3> / <2,5> / <3,7> / <4,9>, 5..6: frx_k4_band_dmma2<3,7> / <4,9>
 };
 
 template <int RT, int CT>
@@ -392,6 +393,26 @@ static int band_dmma_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, Bi
     out->grid = (int64_t)ctx->sm_count * per_sm;
     if (out->grid > count) out->grid = count;
     out->scratch = sizeof(double) * (size_t)out->grid * n * (2 * nb_bin + 1);
+    return FRX_OK;
+}
+
+template <int RT, int CT>
+static int band_dmma2_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, BinLaunch* out) {
+    using G = frx_k4::BandGeo<RT, CT>;
+    out->dyn = sizeof(double) * (size_t)G::smem_doubles2(n);
+    FRX_CUDA(cudaFuncSetAttribute(frx_k4::frx_k4_band_dmma2<RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->dyn));
+    int per_sm = 1;
+    FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4::frx_k4_band_dmma2<RT, CT>, 64, out->dyn));
+    if (per_sm < 1) per_sm = 1;
+    out->grid = (int64_t)ctx->sm_count * per_sm;
+    if (out->grid > count) out->grid = count;
+    out->scratch = sizeof(double) * (size_t)out->grid * n * (2 * nb_bin + 1);
+    return FRX_OK;
+}
+
+template <int RT, int CT>
+static int band_dmma2_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
+    FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_dmma2<RT, CT><<<(unsigned)L.grid, 64, L.dyn, ctx->stream>>>(q));
     return FRX_OK;
 }
 
@@ -481,6 +502,8 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     // FRX_K4_DMMA_BINS: bit b set = bin b runs the blocked tensor-core kernel (default: see kDefaultDmmaBins)
     static const int variant = getenv("FRX_K4_VARIANT") ? atoi(getenv("FRX_K4_VARIANT")) : 0;
     static const int dmma_bins = variant == 2 ? 0 : (getenv("FRX_K4_DMMA_BINS") ? atoi(getenv("FRX_K4_DMMA_BINS")) : kDefaultDmmaBins);
+    // FRX_K4_TWO_WARP: bit b set = bin b (2 or 3) runs the two-warps-per-system form of the blocked kernel
+    static const int two_warp_bins = getenv("FRX_K4_TWO_WARP") ? atoi(getenv("FRX_K4_TWO_WARP")) : kDefaultTwoWarpBins;
     if (!d_dense && variant != 1 && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
         frx_k4::BandParams q;
         q.n = n;
@@ -497,7 +520,12 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         for (int b = 0; b < kStreamBins; ++b) {
             L[b].grid = 0;
             if (!bin_count[b]) continue;
-            if (dmma_bins & (1 << b)) {
+            if ((two_warp_bins & (1 << b)) && b >= 2 && (dmma_bins & (1 << b))) {
+                L[b].kind = 3 + b;     // 5, 6: the two-warp kernel for the bins <3,7> and <4,9>
+                rc = b == 2 ? band_dmma2_geometry<3, 7>(ctx, n, bin_count[b], bin_nb[b], &L[b])
+                            : band_dmma2_geometry<4, 9>(ctx, n, bin_count[b], bin_nb[b], &L[b]);
+                if (rc) return rc;
+            } else if (dmma_bins & (1 << b)) {
                 L[b].kind = 1 + b;
                 rc = b == 0 ? band_dmma_geometry<1, 3>(ctx, n, bin_count[b], bin_nb[b], &L[b])
                    : b == 1 ? band_dmma_geometry<2, 5>(ctx, n, bin_count[b], bin_nb[b], &L[b])
@@ -533,6 +561,9 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                 FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L[b].dyn));
                 FRX_LAUNCH(ctx, FRX_K_SOLVE,
                            frx_k4_band_stream<<<(unsigned)L[b].grid, kStreamWarps * 32, L[b].dyn, ctx->stream>>>(sp));
+            } else if (L[b].kind >= 5) {
+                rc = L[b].kind == 5 ? band_dmma2_launch<3, 7>(ctx, q, L[b]) : band_dmma2_launch<4, 9>(ctx, q, L[b]);
+                if (rc) return rc;
             } else {
                 rc = L[b].kind == 1 ? band_dmma_launch<1, 3>(ctx, q, L[b])
                    : L[b].kind == 2 ? band_dmma_launch<2, 5>(ctx, q, L[b])

@@ -50,6 +50,9 @@ struct BandGeo {
     __host__ __device__ static inline int smem_doubles(int n) {
         return S * RS + S * 8 + 8 * TS + 64 + APAD + ((n + 1) & ~1);
     }
+    __host__ __device__ static inline int smem_doubles2(int n) {      // frx_k4_band_dmma2: REC (80) instead of L11 (64), + PS
+        return S * RS + S * 8 + 8 * TS + 80 + APAD + ((n + 1) & ~1) + 4;
+    }
 };
 
 __device__ inline void dmma884(double& d0, double& d1, double a, double b) {
@@ -73,6 +76,84 @@ struct BandParams {
     const int32_t* order;    // the systems of this launch (one band-width bin)
     int nb_max;              // widest band (res + 1) among them
 };
+
+// Back substitution in blocks of 8 rows, one warp.  xs[k] = transformed rhs on entry, the solution on exit;
+// U[k][0] = 1 / pivot; U[k][c], c >= 1, multiplies x_{k+c}.
+template <class G>
+__device__ __forceinline__ void band_back_substitution(const int lane, const int n, const int n_panels, const int us,
+                                                       const double* __restrict__ U, double* xs) {
+    constexpr int TW = G::TW, TPL = G::TPL;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int gq = lane >> 2;
+    auto load_block = [&](int kb, double (&uu)[TPL][8], double (&dd)[8]) {
+#pragma unroll
+        for (int jj = 0; jj < TPL; ++jj) {
+            const int t = lane + 32 * jj;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int rel = 8 - q + t;
+                uu[jj][q] = (kb >= 0 && t < TW && kb + 8 + t < n && rel < us) ? __ldcg(U + (int64_t)(kb + q) * us + rel) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+            dd[cc] = (kb >= 0 && cc >= gq && cc - gq < us && kb + cc < n) ? __ldcg(U + (int64_t)(kb + gq) * us + cc - gq) : 0.0;
+    };
+    double un[TPL][8], dn[8];
+    load_block((n_panels - 1) * 8, un, dn);
+    for (int kb = (n_panels - 1) * 8; kb >= 0; kb -= 8) {
+        double uc[TPL][8], d[8];
+#pragma unroll
+        for (int jj = 0; jj < TPL; ++jj)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) uc[jj][q] = un[jj][q];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) d[cc] = dn[cc];
+        load_block(kb - 8, un, dn);
+        double sacc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sacc[q] = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < TPL; ++jj) {
+            const int t = lane + 32 * jj, j = kb + 8 + t;
+            const double xj = (t < TW && j < n) ? xs[j] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sacc[q] = fma(uc[jj][q], xj, sacc[q]);
+        }
+        // transpose-reduce: 8 sums over 32 lanes -> lane group gq holds the sum of row kb + gq
+        double v4[4], v2[2], v1;
+        {
+            const bool up = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double keep = up ? sacc[4 + i] : sacc[i], send = up ? sacc[i] : sacc[4 + i];
+                v4[i] = keep + __shfl_xor_sync(FULL, send, 16);
+            }
+            const bool up8 = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double keep = up8 ? v4[2 + i] : v4[i], send = up8 ? v4[i] : v4[2 + i];
+                v2[i] = keep + __shfl_xor_sync(FULL, send, 8);
+            }
+            const bool up4 = lane & 4;
+            const double keep = up4 ? v2[1] : v2[0], send = up4 ? v2[0] : v2[1];
+            v1 = keep + __shfl_xor_sync(FULL, send, 4);
+            v1 += __shfl_xor_sync(FULL, v1, 2);
+            v1 += __shfl_xor_sync(FULL, v1, 1);
+        }
+        double rhsq = (kb + gq < n) ? xs[kb + gq] - v1 : 0.0;
+        double rinvq = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) rinvq = cc == gq ? d[cc] : rinvq;
+        __syncwarp();
+#pragma unroll
+        for (int qq = 7; qq >= 0; --qq) {
+            const double xv = __shfl_sync(FULL, rhsq * rinvq, qq * 4);
+            if (gq < qq) rhsq = fma(-d[qq], xv, rhsq);
+            if (lane == qq * 4 && kb + qq < n) xs[kb + qq] = xv;
+        }
+        __syncwarp();
+    }}
 
 template <int RT, int CT>
 __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
@@ -130,19 +211,14 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
             }
         }
         int info = 0, pm = 0;                                // pm = panel index mod CT
+        double areg[7];                                      // a_{-nb} .. a_{-nb+6}: the panel entries of a row entering the band
+#pragma unroll
+        for (int e = 0; e < 7; ++e) areg[e] = apad[e];
         __syncwarp();
         for (int pnl = 0; pnl < n_panels; ++pnl) {
             const int k0 = pnl * 8;
-            // shared-memory offsets of this lane's window columns in the ring: refill (window column jj) and copy-out
-            // (trailing column t = window column 8 + t)
-            int doff[WCL], colidx[TPL];
-#pragma unroll
-            for (int i = 0; i < WCL; ++i) {
-                const int jj = lane + 32 * i;
-                int tile = pm + (jj >> 3);
-                if (tile >= CT) tile -= CT;
-                doff[i] = tile * 8 + (jj & 7);
-            }
+            // shared-memory offsets of this lane's trailing columns (trailing column t = window column 8 + t) in the ring
+            int colidx[TPL];
 #pragma unroll
             for (int i = 0; i < TPL; ++i) {
                 const int t = lane + 32 * i;
@@ -199,9 +275,20 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
                     }
                     // the pivot row leaves the window: trailing entries to the registers of their columns' lanes,
                     // multipliers w.r.t. the earlier pivots to L11, panel entries to row k of U
-                    const double* wrow = W + P * RS;
+                    // (every lane OWNS its trailing columns: it reads the retiring row's entry and writes the entering row's
+                    // coefficient in its place itself, so no warp barrier is needed between the two, nor before the next pivot)
+                    double* wrow = W + P * RS;
+                    const int inew = k + nb + 1;
 #pragma unroll
-                    for (int i = 0; i < TPL; ++i) u[i][c] = (lane + 32 * i < TW) ? wrow[colidx[i]] : 0.0;
+                    for (int i = 0; i < TPL; ++i) {
+                        const int t = lane + 32 * i;
+                        if (t < TW) {
+                            u[i][c] = wrow[colidx[i]];
+                            if (inew < n) wrow[colidx[i]] = (k0 + 8 + t < n) ? apad[t + 7 - c] : 0.0;   // window column 8 + t of row inew
+                        } else {
+                            u[i][c] = 0.0;
+                        }
+                    }
                     if (is_pivot) {
 #pragma unroll
                         for (int cc = 0; cc < c; ++cc) L11[c * 8 + cc] = -r[cc];
@@ -211,35 +298,21 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
                         for (int cc = c + 1; cc < 8; ++cc)
                             if (cc - c < us && k0 + cc < n) urow[cc - c] = r[cc];
                         xs[k] = r[8];                          // transformed right-hand side of row k of U
-                    }
-                    __syncwarp();
-                    // ... and the matrix row that enters the band at this column takes its slot
-                    const int inew = k + nb + 1;
-                    if (inew < n) {                            // warp-uniform
-                        double* nrow = W + P * RS;
+                        // ... and the matrix row that enters the band at this column takes its slot
+                        if (inew < n) {
 #pragma unroll
-                        for (int i = 0; i < WCL; ++i) {
-                            const int jj = lane + 32 * i;
-                            if (jj >= 8 && jj < WC) nrow[doff[i]] = (k0 + jj < n) ? apad[jj - c - 1] : 0.0;
-                        }
-                        const double nbv = xs[inew];
-                        double nv[8];
-#pragma unroll
-                        for (int cc = 0; cc < 8; ++cc) nv[cc] = (cc > c && k0 + cc < n) ? apad[cc - c - 1] : 0.0;
-                        if (is_pivot) {
-#pragma unroll
-                            for (int cc = 0; cc < 8; ++cc) r[cc] = nv[cc];
-                            r[8] = nbv;
+                            for (int cc = 0; cc < 8; ++cc) r[cc] = (cc > c && k0 + cc < n) ? areg[cc > c ? cc - c - 1 : 0] : 0.0;
+                            r[8] = xs[inew];
                             label = inew;
-                        }
-                    } else if (is_pivot) {
-                        label = -1;
+                        } else {
+                            label = -1;
 #pragma unroll
-                        for (int cc = 0; cc < 9; ++cc) r[cc] = 0.0;
+                            for (int cc = 0; cc < 9; ++cc) r[cc] = 0.0;
+                        }
                     }
-                    __syncwarp();
                 }
             }
+            __syncwarp();
             // multipliers (negated) to PB: the A operand of the trailing update
             if (lane < S) {
                 const bool alive = label >= 0;
@@ -325,81 +398,269 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
             pm = pm + 1 == CT ? 0 : pm + 1;
             __syncwarp();
         }
-        // ---- back substitution in blocks of 8 rows ------------------------------------------------------------
-        // xs[k] = transformed rhs; U[k][0] = 1 / pivot; U[k][c], c >= 1, multiplies x_{k+c}
-        const int gq = lane >> 2;
-        auto load_block = [&](int kb, double (&uu)[TPL][8], double (&dd)[8]) {
-#pragma unroll
-            for (int jj = 0; jj < TPL; ++jj) {
-                const int t = lane + 32 * jj;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int rel = 8 - q + t;
-                    uu[jj][q] = (kb >= 0 && t < TW && kb + 8 + t < n && rel < us) ? __ldcg(U + (int64_t)(kb + q) * us + rel) : 0.0;
-                }
-            }
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc)
-                dd[cc] = (kb >= 0 && cc >= gq && cc - gq < us && kb + cc < n) ? __ldcg(U + (int64_t)(kb + gq) * us + cc - gq) : 0.0;
-        };
-        double un[TPL][8], dn[8];
-        load_block((n_panels - 1) * 8, un, dn);
-        for (int kb = (n_panels - 1) * 8; kb >= 0; kb -= 8) {
-            double uc[TPL][8], d[8];
-#pragma unroll
-            for (int jj = 0; jj < TPL; ++jj)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) uc[jj][q] = un[jj][q];
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) d[cc] = dn[cc];
-            load_block(kb - 8, un, dn);
-            double sacc[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) sacc[q] = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < TPL; ++jj) {
-                const int t = lane + 32 * jj, j = kb + 8 + t;
-                const double xj = (t < TW && j < n) ? xs[j] : 0.0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) sacc[q] = fma(uc[jj][q], xj, sacc[q]);
-            }
-            // transpose-reduce: 8 sums over 32 lanes -> lane group gq holds the sum of row kb + gq
-            double v4[4], v2[2], v1;
-            {
-                const bool up = lane & 16;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double keep = up ? sacc[4 + i] : sacc[i], send = up ? sacc[i] : sacc[4 + i];
-                    v4[i] = keep + __shfl_xor_sync(FULL, send, 16);
-                }
-                const bool up8 = lane & 8;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const double keep = up8 ? v4[2 + i] : v4[i], send = up8 ? v4[i] : v4[2 + i];
-                    v2[i] = keep + __shfl_xor_sync(FULL, send, 8);
-                }
-                const bool up4 = lane & 4;
-                const double keep = up4 ? v2[1] : v2[0], send = up4 ? v2[0] : v2[1];
-                v1 = keep + __shfl_xor_sync(FULL, send, 4);
-                v1 += __shfl_xor_sync(FULL, v1, 2);
-                v1 += __shfl_xor_sync(FULL, v1, 1);
-            }
-            double rhsq = (kb + gq < n) ? xs[kb + gq] - v1 : 0.0;
-            double rinvq = 0.0;
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) rinvq = cc == gq ? d[cc] : rinvq;
-            __syncwarp();
-#pragma unroll
-            for (int qq = 7; qq >= 0; --qq) {
-                const double xv = __shfl_sync(FULL, rhsq * rinvq, qq * 4);
-                if (gq < qq) rhsq = fma(-d[qq], xv, rhsq);
-                if (lane == qq * 4 && kb + qq < n) xs[kb + qq] = xv;
-            }
-            __syncwarp();
-        }
+        band_back_substitution<G>(lane, n, n_panels, us, U, xs);
         for (int i = lane; i < n; i += 32) xo[i] = xs[i];
         if (lane == 0 && p.info) p.info[s] = info;
         __syncwarp();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Two warps per system (one CTA of 64 threads): the wide-band bins.  Shared memory, not registers, limits how many systems
+// an SM holds (27 KB each at nb = 31 -> 8), and one warp running the dependent chain of a panel issues ~0.2 instructions
+// per cycle (profiles/r02_k4_band_dmma_*): the SM idles.  Here warp 0 keeps the chain -- and nothing else: per column it
+// publishes the retired row's registers (REC) and the pivot slot (PS) in shared memory -- and everything that is
+// per-COLUMN work is done by all 64 threads after a block barrier: every thread owns ONE trailing column of the window
+// (lifts the 8 retired rows' entries out, drops the entering rows' coefficients in, forms its column of U12, stores it to
+// the U scratch), the 8x8 panel part of U goes out one element per thread, and the two warps split the column tiles of the
+// tensor-core update.  Four block barriers per panel.
+// ----------------------------------------------------------------------------------------------------------------
+template <int RT, int CT>
+__global__ void __launch_bounds__(64, 8) frx_k4_band_dmma2(const BandParams p) {
+    using G = BandGeo<RT, CT>;
+    constexpr int S = G::S, WC = G::WC, RS = G::RS, TW = G::TW, TS = G::TS, WCL = G::WCL;
+    constexpr int H = (CT - 1) / 2;                 // column tiles per warp in the update
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(TW <= 64, "one trailing column per thread");
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, cp = lane & 3, n = p.n;
+    double* W = sm;
+    double* PB = W + S * RS;
+    double* Ub = PB + S * 8;
+    double* REC = Ub + 8 * TS;              // REC[c * 10 + i]: registers r[0..8] of the row that retired at panel step c
+    double* apad = REC + 80;
+    double* xs = apad + G::APAD;
+    int* PS = reinterpret_cast<int*>(xs + ((n + 1) & ~1));      // PS[c]: pivot slot of step c, -1 beyond the matrix
+    double* U = p.uscratch + (int64_t)blockIdx.x * n * (2 * p.nb_max + 1);
+    const int n_panels = (n + 7) >> 3;
+    for (int64_t si = blockIdx.x; si < p.n_sys; si += gridDim.x) {
+        const int64_t s = p.order[si];
+        const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
+        const int nb_a = res + 1;
+        const int nb = nb_a > n - 1 ? n - 1 : nb_a;
+        const int us = 2 * nb + 1;
+        const double ih = 1.0 / p.h[s];
+        const double* rc = p.rcw + p.wptr[s] + res;
+        const double* rhs = p.rhs + s * p.ldb;
+        double* xo = p.x + s * p.ldx;
+        __syncthreads();
+        for (int e = tid; e < G::APAD; e += 64) apad[e] = 0.0;
+        for (int i = tid; i < n; i += 64) xs[i] = rhs[i];
+        __syncthreads();
+        for (int k = -nb_a + tid; k <= nb_a; k += 64) {      // band coefficients: terms and order of the dict-merging expansion
+            double acc = 0.0;
+            bool any = false;
+            auto add = [&](double t) { acc = any ? __dadd_rn(acc, t) : t; any = true; };
+            if (k >= -res && k <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k], ih)));
+            if (k + 1 >= -res && k + 1 <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k + 1], -ih)));
+            if (k - 1 >= -res && k - 1 <= res) add(__dmul_rn(ih, __dmul_rn(rc[k - 1], ih)));
+            if (k >= -res && k <= res) add(__dmul_rn(ih, __dmul_rn(rc[k], -ih)));
+            if (k >= -nb && k <= nb) apad[k + nb] = acc;
+        }
+        __syncthreads();
+        const int rows0 = n < nb + 1 ? n : nb + 1;
+        int label = (warp == 0 && lane < rows0) ? lane : -1;
+        double bval = (warp == 0 && lane < rows0) ? xs[lane] : 0.0;
+        for (int r0 = warp; r0 < rows0; r0 += 2) {
+#pragma unroll
+            for (int i = 0; i < WCL; ++i) {
+                const int jj = lane + 32 * i;
+                if (jj < WC) {
+                    const double v = jj < n ? apad[jj - r0 + nb] : 0.0;
+                    W[r0 * RS + jj] = v;
+                    if (i == 0 && lane < 8) PB[r0 * 8 + lane] = v;
+                }
+            }
+        }
+        int info = 0, pm = 0;
+        double areg[7];
+#pragma unroll
+        for (int e = 0; e < 7; ++e) areg[e] = apad[e];
+        __syncthreads();
+        for (int pnl = 0; pnl < n_panels; ++pnl) {
+            const int k0 = pnl * 8;
+            const bool interior = k0 + 8 + TW <= n && us >= 8;
+            // ================= phase A (warp 0): the dependent chain of the panel, lane = row slot =================
+            if (warp == 0) {
+                double r[9];
+                if (lane < S) {
+                    const double2* src = reinterpret_cast<const double2*>(PB + lane * 8);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double2 v = src[q];
+                        r[2 * q] = v.x;
+                        r[2 * q + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) r[q] = 0.0;
+                }
+                r[8] = bval;
+                int centered = -1;                           // panel step at which this lane's row entered the window
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (interior || k0 + c < n) {            // warp-uniform
+                        const int k = k0 + c;
+                        const bool act = label >= 0;
+                        const unsigned long long bits = act ? (unsigned long long)__double_as_longlong(fabs(r[c])) : 0ull;
+                        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+                        const unsigned mh = __reduce_max_sync(FULL, hi);
+                        const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+                        const int code = __reduce_min_sync(FULL, (act && hi == mh && lo == ml) ? ((label << 5) | lane) : 0x7fffffff);
+                        const int P = code & 31, blog = code >> 5;
+                        double prow[9];
+#pragma unroll
+                        for (int cc = c; cc < 9; ++cc) prow[cc] = __shfl_sync(FULL, r[cc], P);
+                        const double pval = prow[c];
+                        if (pval == 0.0 && info == 0) info = k + 1;
+                        const double rinv = 1.0 / pval;
+                        if (lane == P) {
+                            // the retired row's registers as they are (its multipliers w.r.t. earlier pivots, reciprocal pivot, panel part of
+                            // the U row, transformed rhs): the consumers know which entries belong to this row
+                            r[c] = rinv;
+                            double2* rec = reinterpret_cast<double2*>(REC + c * 10);
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq) rec[qq] = make_double2(r[2 * qq], r[2 * qq + 1]);
+                            REC[c * 10 + 8] = r[8];
+                            xs[k] = r[8];
+                            const int inew = k + nb + 1;
+                            if (inew < n) {
+#pragma unroll
+                                for (int cc = c + 1; cc < 8; ++cc) r[cc] = (interior || k0 + cc < n) ? areg[cc - c - 1] : 0.0;
+                                r[8] = xs[inew];
+                                label = inew;
+                                centered = c;
+                            } else {
+                                label = -1;
+                            }
+                        } else if (act) {
+                            const double l = r[c] * rinv;
+                            r[c] = l;
+#pragma unroll
+                            for (int cc = c + 1; cc < 9; ++cc) r[cc] = fma(-l, prow[cc], r[cc]);
+                            if (label == k) label = blog;
+                        }
+                        if (lane == 0) PS[c] = P;
+                    } else if (lane == 0) {
+                        PS[c] = -1;
+                    }
+                }
+                if (lane < S) {
+                    const bool alive = label >= 0;
+                    double m[8];
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) m[cc] = (alive && cc > centered && (interior || k0 + cc < n)) ? -r[cc] : 0.0;
+                    double2* dst = reinterpret_cast<double2*>(PB + lane * 8);
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) dst[qq] = make_double2(m[2 * qq], m[2 * qq + 1]);
+                }
+                bval = r[8];
+            }
+            __syncthreads();
+            // ================= phase B (64 threads): one trailing column per thread ===============================
+            {
+                int ps[8];
+                {
+                    const int4 a4 = *reinterpret_cast<const int4*>(PS), b4 = *reinterpret_cast<const int4*>(PS + 4);
+                    ps[0] = a4.x; ps[1] = a4.y; ps[2] = a4.z; ps[3] = a4.w;
+                    ps[4] = b4.x; ps[5] = b4.y; ps[6] = b4.z; ps[7] = b4.w;
+                }
+                const int t = tid;
+                if (t < TW) {
+                    int tile = pm + 1 + (t >> 3);
+                    if (tile >= CT) tile -= CT;
+                    const int col = tile * 8 + (t & 7);
+                    const bool col_in = interior || k0 + 8 + t < n;
+                    double u[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        u[c] = 0.0;
+                        if (ps[c] >= 0) {
+                            double* w = W + ps[c] * RS + col;
+                            u[c] = *w;
+                            if (interior || k0 + c + nb + 1 < n) *w = col_in ? apad[t + 7 - c] : 0.0;   // window column 8 + t of row k + nb + 1
+                        }
+                    }
+#pragma unroll
+                    for (int q = 1; q < 8; ++q) {
+                        if (ps[q] >= 0) {
+                            int cent = -1;                   // step at which the row that retired at step q had entered this panel
+#pragma unroll
+                            for (int c1 = 0; c1 < q; ++c1) cent = ps[c1] == ps[q] ? c1 : cent;
+                            const double2* mrow = reinterpret_cast<const double2*>(REC + q * 10);
+#pragma unroll
+                            for (int qq = 0; qq < (q + 1) / 2; ++qq) {
+                                const double2 v = mrow[qq];
+                                if (2 * qq < q && 2 * qq > cent) u[q] = fma(-v.x, u[2 * qq], u[q]);
+                                if (2 * qq + 1 < q && 2 * qq + 1 > cent) u[q] = fma(-v.y, u[2 * qq + 1], u[q]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        *reinterpret_cast<double2*>(Ub + (m * TS + t) * 2) = make_double2(u[2 * m], u[2 * m + 1]);
+                    if (col_in) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int rel = 8 - q + t;
+                            if (ps[q] >= 0 && rel < us) U[(int64_t)(k0 + q) * us + rel] = u[q];
+                        }
+                    }
+                }
+                {   // the 8 x 8 panel part of U (reciprocal pivots on the diagonal): one element per thread
+                    const int q = tid >> 3, j = tid & 7;
+                    if (j >= q && ps[q] >= 0 && j - q < us && (interior || k0 + j < n))
+                        U[(int64_t)(k0 + q) * us + (j - q)] = REC[q * 10 + j];
+                }
+            }
+            __syncthreads();
+            // ================= phase C (both warps): trailing update on the tensor cores ========================
+            double2 am[RT];
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) am[rt] = *reinterpret_cast<const double2*>(PB + (8 * rt + g) * 8 + 2 * cp);
+            __syncthreads();                                // PB may now take the next panel
+            {
+                double2 cf[RT], cfn[RT];
+                int tile = pm + 1 + warp * H;
+                if (tile >= CT) tile -= CT;
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt) cf[rt] = *reinterpret_cast<const double2*>(W + (8 * rt + g) * RS + tile * 8 + 2 * cp);
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const int ct = warp * H + i;
+                    const int tile_next = tile + 1 == CT ? 0 : tile + 1;
+                    if (i + 1 < H) {
+#pragma unroll
+                        for (int rt = 0; rt < RT; ++rt)
+                            cfn[rt] = *reinterpret_cast<const double2*>(W + (8 * rt + g) * RS + tile_next * 8 + 2 * cp);
+                    }
+                    const double2 bb = *reinterpret_cast<const double2*>(Ub + (cp * TS + 8 * ct + g) * 2);
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) {
+                        dmma884(cf[rt].x, cf[rt].y, am[rt].x, bb.x);
+                        dmma884(cf[rt].x, cf[rt].y, am[rt].y, bb.y);
+                    }
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) {
+                        if (ct == 0) *reinterpret_cast<double2*>(PB + (8 * rt + g) * 8 + 2 * cp) = cf[rt];   // the next panel
+                        else *reinterpret_cast<double2*>(W + (8 * rt + g) * RS + tile * 8 + 2 * cp) = cf[rt];
+                        cf[rt] = cfn[rt];
+                    }
+                    tile = tile_next;
+                }
+            }
+            if (warp == 1) {
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt)             // the freed column tile: zero, it becomes the right-most one
+                    *reinterpret_cast<double2*>(W + (8 * rt + g) * RS + pm * 8 + 2 * cp) = make_double2(0.0, 0.0);
+            }
+            pm = pm + 1 == CT ? 0 : pm + 1;
+            __syncthreads();
+        }
+        if (warp == 0) band_back_substitution<G>(lane, n, n_panels, us, U, xs);
+        __syncthreads();
+        for (int i = tid; i < n; i += 64) xo[i] = xs[i];
+        if (tid == 0 && p.info) p.info[s] = info;
     }
 }
 

@@ -148,12 +148,20 @@ __global__ void __launch_bounds__(128) frx_k5b_stencil_nodes(int rule, int side,
 __global__ void __launch_bounds__(128) frx_k5_single(int rule, int side, double alpha, double lf, double resolution,
                                                      long long first, long long count, double* __restrict__ weights) {
     __shared__ frx_k5_scalars S;
+    __shared__ double s_pm;
+    // the scalars are three independent ~5 us chains (the rule's gammas, the power of the step, the Riesz-Caputo gamma):
+    // one warp each -- the same operations as frx_par_init / frx_multiplier, evaluated side by side
     if (threadIdx.x == 0) {
         S.P = frx_par_init(rule, alpha);
-        S.mult = frx_multiplier(S.P, lf, resolution);
-        S.K = FRX_DIV(FRX_MUL(0.5, frx_gamma_py(FRX_SUB(2.0, alpha))), 1.0);
         S.sgn = (((long long)S.P.n) & 1) ? -1.0 : 1.0;
+    } else if (threadIdx.x == 32) {
+        const frx_par E = frx_par_exponents(rule, alpha);
+        s_pm = frx_pow_cr(FRX_DIV(lf, resolution), E.e_mult);
+    } else if (threadIdx.x == 64) {
+        S.K = side == FRX_SIDE_RIESZ_CAPUTO ? FRX_DIV(FRX_MUL(0.5, frx_gamma_py(FRX_SUB(2.0, alpha))), 1.0) : 0.0;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) S.mult = (rule == FRX_R_SIMPSON || rule == FRX_R_GL) ? s_pm : FRX_DIV(s_pm, S.P.g_mult);   // = frx_multiplier
     __syncthreads();
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;

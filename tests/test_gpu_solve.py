@@ -52,25 +52,32 @@ def test_solve_other_rules_and_dense_storage_path():
             assert np.abs(x[s] - want).max() / np.abs(want).max() <= 1e-12 + 20 * np.finfo(float).eps * np.linalg.cond(A)
 
 
-def test_full_batch_cfg4_properties():
-    """BASELINE cfg 4: 1e5 systems, alpha x length-scale sweep, n = 64: residual of every system and
-    bitwise reproducibility."""
-    n, n_alpha, n_ls = 64, 400, 250
+@pytest.mark.parametrize('n', [64, 128, 256])
+def test_full_batch_cfg4_properties(n):
+    """BASELINE cfg 4 at full size: 1e5 systems, 400 alpha x 250 length scales (resolution 1..30 -> every band-width bin of
+    the blocked kernel), n = 64 / 128 / 256: residual of a sample of systems from EVERY bin through the kernel's own dense
+    assembly (checked against the oracle above), finiteness of all solutions, bitwise reproducibility."""
+    n_alpha, n_ls = 400, 250
     h = 1. / (n + 1)
     alpha = np.repeat(np.linspace(0.05, 0.95, n_alpha), n_ls)
-    res = np.tile(1. + (np.arange(n_ls) % 16), n_alpha)
+    res = np.tile(1. + (np.arange(n_ls) % 30), n_alpha)
     xg = torch.arange(1, n + 1, dtype=torch.float64, device='cuda') * h
     rhs = torch.sin(np.pi * xg).repeat(n_alpha * n_ls, 1).contiguous()
-    x1 = batched.assemble_solve('caputo', alpha, h, res, rhs)
+    x1, info = batched.assemble_solve('caputo', alpha, h, res, rhs, return_info=True)
     x2 = batched.assemble_solve('caputo', alpha, h, res, rhs)
     assert torch.equal(x1, x2)
-    # residual through the dense matrices of a sample of systems (the kernel's own assembly, checked above)
-    idx = np.arange(0, n_alpha * n_ls, 997)
+    assert int(info.abs().sum()) == 0 and torch.isfinite(x1).all()
+    idx = np.arange(0, n_alpha * n_ls, 331 if n <= 128 else 997)        # 331 is coprime to 30: every resolution is sampled
+    assert set(res[idx]) == set(range(1, 31))
     A = batched.assemble_dense('caputo', alpha[idx], h, res[idx], n)
     r = torch.bmm(A, x1[idx].unsqueeze(-1)).squeeze(-1) - rhs[idx]
     scale = (A.abs().amax(dim=(1, 2)) * x1[idx].abs().amax(dim=1)).unsqueeze(-1)
     assert (r.abs() / scale).max().item() < 1e-13
-    assert torch.isfinite(x1).all()
+    # a few systems per bin against the oracle's assembly + LAPACK
+    for s in (0, 7, 15, 23, 29, 99999 - 5):
+        want, Amat = assemble.solve('caputo', alpha[s], h, int(res[s]), n, rhs[s].cpu().numpy())
+        err = np.abs(x1[s].cpu().numpy() - want).max() / np.abs(want).max()
+        assert err <= 1e-12 + 20 * np.finfo(float).eps * np.linalg.cond(Amat), (n, s, err)
 
 
 def test_solve_errors():

@@ -54,7 +54,7 @@ nb = np.minimum(res + 1, n - 1)
 flop = float(np.sum(n * (2.0 * nb * (2 * nb + 1) + 3 * nb) + n * (4 * nb + 1)))
 solve_ms = kt['solve'][0] / a.steps
 print(json.dumps({'n': n, 'n_sys': n_sys, 'res': [a.res_lo, a.res_hi], 'variant': os.environ.get('FRX_K4_VARIANT', '0'),
-                  'dmma_bins': os.environ.get('FRX_K4_DMMA_BINS', 'default'), 'ms_per_batch': ms,
+                  'dmma_bins': os.environ.get('FRX_K4_DMMA_BINS', 'default'), 'two_warp': os.environ.get('FRX_K4_TWO_WARP', 'default'), 'ms_per_batch': ms,
                   'solves_per_s': n_sys / (ms * 1e-3), 'solve_kernels_ms': solve_ms, 'stencil_kernels_ms': kt['stencil'][0] / a.steps,
                   'band_tflops': flop / (solve_ms * 1e-3) / 1e12, 'max_rel_residual': resid, 'info_nonzero': int((info != 0).sum()),
                   'finite': bool(torch.isfinite(x).all())}))
