@@ -104,7 +104,7 @@ class PeerGather(object):
 
 class SharedHostArray(object):
     """float64 host array of `shape` in ONE POSIX shared-memory segment mapped by every rank of `group` and page-locked /
-    mapped for CUDA in every process (frx_host_register): any rank's kernels can store into it in place, every rank
+    mapped for CUDA rank by rank (pin_rows: every rank registers the rows its own kernels store into), every rank
     reads the whole of it as an ordinary NumPy array.  Collective constructor (rank 0 creates, the others attach).
     register=False (CPU tests with the gloo backend) skips the CUDA registration."""
 
@@ -134,21 +134,38 @@ class SharedHostArray(object):
         if rank == 0:
             os.unlink(path[0])
         self.array = np.frombuffer(self._mm, dtype=np.float64, count=int(np.prod(self.shape))).reshape(self.shape)
-        self._ptr, self._registered = self.array.ctypes.data if self.array.size else 0, False
-        if register and self._ptr:
-            _lib.check(_lib.lib().frx_host_register(self._ptr, nbytes))
-            self._registered = True
+        self._ptr = self.array.ctypes.data if self.array.size else 0
+        self._nbytes, self._register, self._registered = nbytes, bool(register), []
         atexit.register(self.close)
+
+    def pin_rows(self, begin, end):
+        """Page-lock and map for CUDA the rows [begin, end) -- the part THIS rank's kernels store into (every rank pins only
+        its own share: 8 ranks x the whole of an 8 GB result would exceed what the OS lets processes lock).  Returns False
+        when the OS refuses; the host entry points then stage the rows through a device buffer instead of writing in place."""
+        if not self._register or not self._ptr or end <= begin:
+            return False
+        import mmap
+        row_bytes = int(np.prod(self.shape[1:])) * 8
+        lo = (begin * row_bytes) // mmap.PAGESIZE * mmap.PAGESIZE
+        hi = min(self._nbytes, -(-(end * row_bytes) // mmap.PAGESIZE) * mmap.PAGESIZE)
+        if any(a <= lo and hi <= b for a, b in self._registered):
+            return True
+        try:
+            _lib.check(_lib.lib().frx_host_register(self._ptr + lo, hi - lo))
+        except Exception:      # noqa: BLE001 -- locked-memory limit: fall back to staged copies
+            return False
+        self._registered.append((lo, hi))
+        return True
 
     def close(self):
         if getattr(self, '_mm', None) is None:
             return
-        if self._registered:
+        for lo, hi in self._registered:
             try:
-                _lib.lib().frx_host_unregister(self._ptr)
+                _lib.lib().frx_host_unregister(self._ptr + lo)
             except Exception:
                 pass
-            self._registered = False
+        self._registered = []
         self.array = None
         mm, self._mm = self._mm, None
         try:
@@ -227,6 +244,7 @@ def history_sweep(approximation, alphas, h, g, N=None, group=None, compute=None,
                        lambda: SharedHostArray((n_total, N + 1), group, register=compute is None))
         if end > begin:
             if compute is None:
+                shared.pin_rows(begin, end)
                 batched.history_host(approximation, mine, h, g, N=N, out=shared.array[begin:end])
             else:
                 shared.array[begin:end] = np.asarray(compute(mine, g))
@@ -273,6 +291,7 @@ def toeplitz_apply_sweep(approximation, alpha, h, G, N=None, group=None, compute
                    lambda: SharedHostArray((n_fields, N + 1), group, register=compute is None))
     if end > begin:
         if compute is None:
+            shared.pin_rows(begin, end)
             batched.toeplitz_apply_host(approximation, alpha, h, G[begin:end], N=N, out=shared.array[begin:end])
         else:
             shared.array[begin:end] = np.asarray(compute(alpha, G[begin:end]))
@@ -307,6 +326,7 @@ def assemble_solve_sweep(approximation, alpha, h, res, rhs, group=None, compute=
     shared = _plan('host', (n_sys, n, id(group)), lambda: SharedHostArray((n_sys, n), group, register=compute is None))
     if end > begin:
         if compute is None:
+            shared.pin_rows(begin, end)
             batched.assemble_solve_host(approximation, a[sl], hh[sl], rr[sl], rhs[sl], out=shared.array[sl])
         else:
             shared.array[sl] = np.asarray(compute(a[sl], hh[sl], rr[sl], rhs[sl]))
