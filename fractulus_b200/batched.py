@@ -243,35 +243,66 @@ def toeplitz_product(c, g, paired=False, scale=1.0, n_cols=0, out=None):
     return out
 
 
+def _compose_structure(d_ptr_a, d_off_a, d_ptr_b, d_off_b):
+    """(ptr_c, off_c) of a batched composition with tensor ops on the inputs' device: the distinct offset sums of every item,
+    ascending -- every (a, b) pair of every item, then one sort/unique over (item, sum) keys."""
+    dev = d_ptr_a.device
+    n = d_ptr_a.numel() - 1
+    na, nb = d_ptr_a[1:] - d_ptr_a[:-1], d_ptr_b[1:] - d_ptr_b[:-1]
+    item_b = torch.repeat_interleave(torch.arange(n, device=dev), nb)
+    if d_off_b.numel() > 1:
+        same = item_b[1:] == item_b[:-1]
+        if bool((same & (d_off_b[1:] <= d_off_b[:-1])).any()):
+            raise ValueError("B's offsets must ascend within an item")
+    item_a = torch.repeat_interleave(torch.arange(n, device=dev), na)     # entry e of A (item k) meets the nb_k entries of B's item k
+    cnt = nb[item_a]
+    pair_a = torch.repeat_interleave(torch.arange(item_a.numel(), device=dev), cnt)
+    start = torch.cumsum(cnt, 0) - cnt
+    pair_b = d_ptr_b[item_a][pair_a] + (torch.arange(pair_a.numel(), device=dev) - start[pair_a])
+    sums = d_off_a[pair_a].to(torch.int64) + d_off_b[pair_b].to(torch.int64)
+    if sums.numel() == 0:
+        return torch.zeros(n + 1, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
+    lo = sums.min()
+    span = sums.max() - lo + 1
+    keys = torch.unique(item_a[pair_a] * span + (sums - lo))              # sorted: by item, then by offset sum
+    item_c = torch.div(keys, span, rounding_mode='floor')
+    d_off_c = (keys - item_c * span + lo).to(torch.int32)
+    d_ptr_c = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_ptr_c[1:] = torch.cumsum(torch.bincount(item_c, minlength=n), 0)
+    return d_ptr_c, d_off_c
+
+
 def stencil_compose(ptr_a, off_a, w_a, ptr_b, off_b, w_b, device=None):
     """(f)(1): batched stencil o stencil composition, the expansion of fdm.Operator(A, fdm.Operator(B)) with the dict-merge's
-    own term order (bit-identical to it).  Ragged NumPy inputs: item k owns entries ptr[k]:ptr[k+1] of (off, w); offsets
-    are integers on a common grid; B's offsets ascend within an item.  -> (ptr_c, off_c) NumPy (distinct sums, ascending)
-    and the composed weights as a CUDA tensor."""
-    ptr_a = np.ascontiguousarray(ptr_a, dtype=np.int64)
-    ptr_b = np.ascontiguousarray(ptr_b, dtype=np.int64)
-    off_a = np.ascontiguousarray(off_a, dtype=np.int32)
-    off_b = np.ascontiguousarray(off_b, dtype=np.int32)
-    n = len(ptr_a) - 1
-    if len(ptr_b) - 1 != n:
+    own term order (bit-identical to it).  Ragged inputs (NumPy or CUDA tensors): item k owns entries ptr[k]:ptr[k+1] of
+    (off, w); offsets are integers on a common grid; B's offsets ascend within an item.  The output structure -- the distinct
+    offset sums of every item, ascending -- is built on the device (pair sums, one sort/unique over (item, sum) keys).
+    -> (ptr_c, off_c) NumPy and the composed weights as a CUDA tensor."""
+    if len(ptr_a) != len(ptr_b):
         raise ValueError('A and B must hold the same number of items')
-    outs = []
-    for k in range(n):                      # host-side structure: the distinct offset sums of every pair
-        oa, ob = off_a[ptr_a[k]:ptr_a[k + 1]], off_b[ptr_b[k]:ptr_b[k + 1]]
-        if len(ob) > 1 and np.any(np.diff(ob) <= 0):
+    if not torch.is_tensor(off_b) and len(off_b) > 1:      # host inputs: argument errors before any device work
+        ob, pb = np.asarray(off_b), np.asarray(ptr_b, dtype=np.int64)
+        first = np.zeros(len(ob), dtype=bool)
+        first[pb[:-1][pb[:-1] < len(ob)]] = True
+        if np.any((np.diff(ob) <= 0) & ~first[1:]):
             raise ValueError("B's offsets must ascend within an item")
-        outs.append(np.unique(oa[:, None].astype(np.int64) + ob[None, :]).astype(np.int32))
-    ptr_c = np.zeros(n + 1, dtype=np.int64)
-    ptr_c[1:] = np.cumsum([len(o) for o in outs])
-    off_c = np.concatenate(outs) if outs else np.zeros(0, dtype=np.int32)
     dev = default_device() if device is None else torch.device(device)
+    t = lambda x, dt: x.to(device=dev, dtype=dt).contiguous() if torch.is_tensor(x) else \
+        torch.as_tensor(np.ascontiguousarray(x), dtype=dt, device=dev)
+    d_ptr_a, d_ptr_b = t(ptr_a, torch.int64), t(ptr_b, torch.int64)
+    d_off_a, d_off_b = t(off_a, torch.int32), t(off_b, torch.int32)
+    d_w_a, d_w_b = t(w_a, torch.float64), t(w_b, torch.float64)
+    n = d_ptr_a.numel() - 1
+    if d_ptr_b.numel() - 1 != n:
+        raise ValueError('A and B must hold the same number of items')
+    if n <= 0:
+        return np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32), torch.empty((0,), dtype=torch.float64, device=dev)
+    d_ptr_c, d_off_c = _compose_structure(d_ptr_a, d_off_a, d_ptr_b, d_off_b)
     ctx, idx = _ctx_for(dev)
-    t = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x), dtype=dt, device=dev)
-    d = [t(ptr_a, torch.int64), t(off_a, torch.int32), t(w_a, torch.float64), t(ptr_b, torch.int64), t(off_b, torch.int32),
-         t(w_b, torch.float64), t(ptr_c, torch.int64), t(off_c, torch.int32)]
-    w_c = torch.empty((len(off_c),), dtype=torch.float64, device=dev)
-    _lib.check(_lib.lib().frx_stencil_compose(ctx.handle, n, *[_ptr(x) for x in d], len(off_c), _ptr(w_c)))
-    return ptr_c, off_c, w_c
+    w_c = torch.empty((d_off_c.numel(),), dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().frx_stencil_compose(ctx.handle, n, _ptr(d_ptr_a), _ptr(d_off_a), _ptr(d_w_a), _ptr(d_ptr_b), _ptr(d_off_b),
+                                              _ptr(d_w_b), _ptr(d_ptr_c), _ptr(d_off_c), d_off_c.numel(), _ptr(w_c)))
+    return d_ptr_c.cpu().numpy(), d_off_c.cpu().numpy(), w_c
 
 
 def _solve_params(alpha, h, res, n_sys=None):

@@ -211,3 +211,24 @@ def test_host_side_argument_handling_without_gpu():
         batched.stencil_compose([0, 1], [0], [1.], [0, 1, 2], [0, 1], [1., 1.])
     with pytest.raises(ValueError):                                      # B's offsets must ascend
         batched.stencil_compose([0, 2], [0, 1], [1., 1.], [0, 2], [1, 0], [1., 1.])
+
+
+def test_compose_structure_matches_per_item_unique():
+    """batched._compose_structure (tensor ops; runs on the device in production) against the per-item np.unique it replaced."""
+    import torch
+    from fractulus_b200 import batched
+    rng = np.random.default_rng(4)
+    n = 50
+    na, nb = rng.integers(0, 9, n), rng.integers(0, 7, n)
+    ptr_a, ptr_b = np.concatenate([[0], np.cumsum(na)]), np.concatenate([[0], np.cumsum(nb)])
+    off_a = rng.integers(-20, 20, ptr_a[-1]).astype(np.int32)
+    off_b = np.concatenate([np.sort(rng.choice(np.arange(-15, 15), k, replace=False)) for k in nb] + [np.zeros(0)]).astype(np.int32)
+    t = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x), dtype=dt)
+    ptr_c, off_c = batched._compose_structure(t(ptr_a, torch.int64), t(off_a, torch.int32), t(ptr_b, torch.int64), t(off_b, torch.int32))
+    ptr_c, off_c = ptr_c.numpy(), off_c.numpy()
+    for k in range(n):
+        oa, ob = off_a[ptr_a[k]:ptr_a[k + 1]], off_b[ptr_b[k]:ptr_b[k + 1]]
+        want = np.unique(oa[:, None].astype(np.int64) + ob[None, :]) if len(oa) and len(ob) else np.zeros(0)
+        assert np.array_equal(off_c[ptr_c[k]:ptr_c[k + 1]], want), k
+    with pytest.raises(ValueError):
+        batched._compose_structure(t([0, 1], torch.int64), t([0], torch.int32), t([0, 2], torch.int64), t([3, 3], torch.int32))
