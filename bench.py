@@ -39,6 +39,7 @@ RULE = 'caputo'
 METRIC = 'fractional_history_node_evals_per_sec'
 UNIT = 'node-evals/s'
 FLUSH_BYTES = 256 << 20      # > 126 MB L2
+FUSED_GATHER = 'fused P2P stores from the kernel epilogue + symmetric-memory barrier'
 
 
 def smooth_field_np(n, h):
@@ -204,7 +205,10 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warmup, 'ms_per_step': 1e3 * sum(secs) / len(secs), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(1, 1, gather='none'),
+        # the same config dict as the B200 arm prints for this --gpus (the CPU arm itself always samples the single-field job:
+        # every alpha of the sweep costs the same)
+        'config': workload_config(args.gpus, 1 if args.gpus == 1 else CFG5_ALPHAS_PER_GPU,
+                                  gather='none' if args.gpus == 1 else FUSED_GATHER),
         'cpu_baseline': last,
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'CPU arm: each step is a bounded sample of the cfg-2 job (evenly spaced rows), timed on the host cores; '
@@ -272,7 +276,7 @@ def bench_history(env, A, steps, warmup, kernel_pass=True, e2e=True, warm_second
         if not env['args'].nccl_gather:
             peer = sweep._peer_plan(world * A, N_NODES + 1, None, world)
         if peer is not None:
-            gather_mode = 'fused P2P stores from the kernel epilogue + symmetric-memory barrier'
+            gather_mode = FUSED_GATHER
         else:
             y = torch.empty((A, 1, N_NODES + 1), dtype=torch.float64, device=dev)
             gathered = torch.empty((world * A, N_NODES + 1), dtype=torch.float64, device=dev)
