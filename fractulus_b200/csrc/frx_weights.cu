@@ -143,6 +143,57 @@ __global__ void __launch_bounds__(128) frx_k5b_stencil_nodes(int rule, int side,
     if (offsets) offsets[e] = (int32_t)o;
 }
 
+// Riesz-Caputo batches: K (left + (-1.)**n * mirror) is symmetric (n odd) or antisymmetric (n even) in the offset, and its two
+// halves are built from the SAME left weights -- one thread per node of the LEFT half (offsets <= 0) evaluates its left weight
+// once and writes both the node and its mirror image, with the operations (and their order) of k5b: same bits, half the pow().
+// Every Riesz-Caputo stencil has an odd node count, so the left half of stencil s starts at (row_ptr[s] + s) / 2.
+__global__ void __launch_bounds__(128) frx_k5b_riesz_half(int rule, int64_t n, int64_t total_half,
+                                                          const double* __restrict__ resolution,
+                                                          const int64_t* __restrict__ row_ptr,
+                                                          const frx_k5_scalars* __restrict__ scal,
+                                                          int32_t* __restrict__ offsets, double* __restrict__ weights) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total_half) return;
+    int64_t lo = 0, hi = n;                   // half_ptr(lo) <= e < half_ptr(hi), half_ptr(s) = (row_ptr[s] + s) / 2
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (((row_ptr[mid] + mid) >> 1) <= e) lo = mid; else hi = mid;
+    }
+    const int64_t s = lo, k = e - ((row_ptr[s] + s) >> 1), base = row_ptr[s], count = row_ptr[s + 1] - base;
+    const frx_k5_scalars& S = scal[s];
+    const frx_par P = S.P;
+    const long long p = (long long)resolution[s];
+    long long lfirst, lcount;
+    frx_left_layout(rule, p, &lfirst, &lcount);
+    const long long llast = lfirst + lcount - 1;
+    const long long first = lfirst < -llast ? lfirst : -llast;
+    const long long o = first + k;            // <= 0
+    const double mult = S.mult;
+    const bool in_left = (o >= lfirst && o <= llast), in_left_m = (-o >= lfirst && -o <= llast);
+    const double Lo = in_left ? FRX_MUL(mult, frx_raw_at_offset(P, p, o)) : 0.0;
+    const double Lm = (in_left_m && o != 0) ? FRX_MUL(mult, frx_raw_at_offset(P, p, -o)) : Lo;
+    {   // node o:  acc = left(o); if (-o in left) acc += sgn * (left(-o) * -1.)
+        double acc = 0.0;
+        if (in_left) acc = Lo;
+        if (in_left_m) {
+            const double r = FRX_MUL(S.sgn, FRX_MUL(Lm, -1.0));
+            acc = in_left ? FRX_ADD(acc, r) : r;
+        }
+        weights[base + k] = FRX_MUL(S.K, acc);
+        if (offsets) offsets[base + k] = (int32_t)o;
+    }
+    if (o != 0) {   // node -o: left(-o) if it exists, then + sgn * (left(o) * -1.)
+        double acc = 0.0;
+        if (in_left_m) acc = Lm;
+        if (in_left) {
+            const double r = FRX_MUL(S.sgn, FRX_MUL(Lo, -1.0));
+            acc = in_left_m ? FRX_ADD(acc, r) : r;
+        }
+        weights[base + (count - 1 - k)] = FRX_MUL(S.K, acc);
+        if (offsets) offsets[base + (count - 1 - k)] = (int32_t)(-o);
+    }
+}
+
 // One Settings triple passed BY VALUE (the drop-in's create_*_stencil call): no parameter upload, one launch.  Every CTA
 // re-evaluates the scalars (a few microseconds) and then one node per thread -- the operations of k5a + k5b, same bits.
 __global__ void __launch_bounds__(128) frx_k5_single(int rule, int side, double alpha, double lf, double resolution,
@@ -207,6 +258,14 @@ int frx_launch_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_setti
     FRX_LAUNCH(ctx, FRX_K_STENCIL,
                frx_k5a_settings_scalars<<<(unsigned)((n_settings + 127) / 128), 128, 0, ctx->stream>>>(
                    rule, n_settings, d_alpha, d_lf, d_resolution, (frx_k5_scalars*)d_scratch));
+    if (side == FRX_SIDE_RIESZ_CAPUTO) {
+        const int64_t total_half = (total + n_settings) / 2;
+        FRX_LAUNCH(ctx, FRX_K_STENCIL,
+                   frx_k5b_riesz_half<<<(unsigned)((total_half + 127) / 128), 128, 0, ctx->stream>>>(
+                       rule, n_settings, total_half, d_resolution, d_row_ptr, (const frx_k5_scalars*)d_scratch, d_offsets,
+                       d_weights));
+        return FRX_OK;
+    }
     FRX_LAUNCH(ctx, FRX_K_STENCIL,
                frx_k5b_stencil_nodes<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
                    rule, side, n_settings, total, d_resolution, d_row_ptr, (const frx_k5_scalars*)d_scratch, d_offsets,

@@ -67,7 +67,7 @@ def test_full_batch_cfg4_properties(n):
     x2 = batched.assemble_solve('caputo', alpha, h, res, rhs)
     assert torch.equal(x1, x2)
     assert int(info.abs().sum()) == 0 and torch.isfinite(x1).all()
-    idx = np.arange(0, n_alpha * n_ls, 331 if n <= 128 else 997)        # 331 is coprime to 30: every resolution is sampled
+    idx = np.arange(0, n_alpha * n_ls, 331)        # 302 systems; every resolution 1..30 is among them
     assert set(res[idx]) == set(range(1, 31))
     A = batched.assemble_dense('caputo', alpha[idx], h, res[idx], n)
     r = torch.bmm(A, x1[idx].unsqueeze(-1)).squeeze(-1) - rhs[idx]
