@@ -382,6 +382,9 @@ struct BinLaunch {
     int kind;   // 0: frx_k4_band_stream, 1..4: frx_k4_band_dmma<1,3> / <2,5> / <3,7> / <4,9>, 5..6: frx_k4_band_dmma2<3,7> / <4,9>
 };
 
+// U scratch of one CTA in doubles: a multiple of 128 bytes so that every CTA's slab is line-aligned (discard.global.L2)
+static inline int64_t band_ustride_cta(int n, int nb_bin) { return ((int64_t)n * (2 * nb_bin + 1) + 15) / 16 * 16; }
+
 template <int RT, int CT>
 static int band_dmma_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, BinLaunch* out) {
     using G = frx_k4::BandGeo<RT, CT>;
@@ -392,7 +395,7 @@ static int band_dmma_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, Bi
     if (per_sm < 1) per_sm = 1;
     out->grid = (int64_t)ctx->sm_count * per_sm;
     if (out->grid > count) out->grid = count;
-    out->scratch = sizeof(double) * (size_t)out->grid * n * (2 * nb_bin + 1);
+    out->scratch = sizeof(double) * (size_t)out->grid * band_ustride_cta(n, nb_bin);
     return FRX_OK;
 }
 
@@ -406,7 +409,7 @@ static int band_dmma2_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, B
     if (per_sm < 1) per_sm = 1;
     out->grid = (int64_t)ctx->sm_count * per_sm;
     if (out->grid > count) out->grid = count;
-    out->scratch = sizeof(double) * (size_t)out->grid * n * (2 * nb_bin + 1);
+    out->scratch = sizeof(double) * (size_t)out->grid * band_ustride_cta(n, nb_bin);
     return FRX_OK;
 }
 
@@ -553,6 +556,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             q.n_sys = bin_count[b];
             q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
             q.nb_max = bin_nb[b];
+            q.ustride_cta = band_ustride_cta(n, bin_nb[b]);
             if (L[b].kind == 0) {
                 StreamParams sp;
                 sp.n_sys = q.n_sys; sp.n = n; sp.rcw = q.rcw; sp.wptr = q.wptr; sp.h = q.h; sp.rhs = q.rhs; sp.ldb = ldb;

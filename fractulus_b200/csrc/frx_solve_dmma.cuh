@@ -61,6 +61,14 @@ __device__ inline void dmma884(double& d0, double& d1, double a, double b) {
                  : "d"(a), "d"(b));
 }
 
+// The U rows of a finished system are dead: tell L2 not to write the scratch lines back (they would otherwise reach DRAM
+// when they are evicted: 70-90 MB per launch against 11 MB of algorithmic bytes, profiles/r02_k4_band_dmma_v2_ncu_full.txt).
+__device__ __forceinline__ void discard_l2(const double* base, int64_t bytes, int tid, int nthreads) {
+    const char* b = reinterpret_cast<const char*>(base);
+    for (int64_t off = (int64_t)tid * 128; off + 128 <= bytes; off += (int64_t)nthreads * 128)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(b + off) : "memory");
+}
+
 struct BandParams {
     int64_t n_sys;
     int n;
@@ -72,7 +80,8 @@ struct BandParams {
     double* x;
     int64_t ldx;
     int32_t* info;
-    double* uscratch;        // [grid][n * (2 * nb_max + 1)]
+    double* uscratch;        // [grid][ustride_cta]
+    int64_t ustride_cta;     // doubles per CTA: n * (2 * nb_max + 1) rounded up to a multiple of 16 (128 bytes)
     const int32_t* order;    // the systems of this launch (one band-width bin)
     int nb_max;              // widest band (res + 1) among them
 };
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
     double* L11 = Ub + 8 * TS;              // L11[q * 8 + c], c < q: multiplier (negated) of pivot row q w.r.t. pivot c
     double* apad = L11 + 64;                // apad[e] = a_{e - nb} for e <= 2nb, 0 beyond
     double* xs = apad + G::APAD;            // rhs, then transformed rhs, then the solution
-    double* U = p.uscratch + (int64_t)blockIdx.x * n * (2 * p.nb_max + 1);
+    double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
     const int n_panels = (n + 7) >> 3;
     for (int64_t si = blockIdx.x; si < p.n_sys; si += gridDim.x) {
         const int64_t s = p.order[si];
@@ -402,6 +411,8 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
         for (int i = lane; i < n; i += 32) xo[i] = xs[i];
         if (lane == 0 && p.info) p.info[s] = info;
         __syncwarp();
+        discard_l2(U, (int64_t)n * us * 8, lane, 32);
+        __syncwarp();
     }
 }
 
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(64, 8) frx_k4_band_dmma2(const BandParams p) {
     double* apad = REC + 80;
     double* xs = apad + G::APAD;
     int* PS = reinterpret_cast<int*>(xs + ((n + 1) & ~1));      // PS[c]: pivot slot of step c, -1 beyond the matrix
-    double* U = p.uscratch + (int64_t)blockIdx.x * n * (2 * p.nb_max + 1);
+    double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
     const int n_panels = (n + 7) >> 3;
     for (int64_t si = blockIdx.x; si < p.n_sys; si += gridDim.x) {
         const int64_t s = p.order[si];
@@ -661,6 +672,7 @@ __global__ void __launch_bounds__(64, 8) frx_k4_band_dmma2(const BandParams p) {
         __syncthreads();
         for (int i = tid; i < n; i += 64) xo[i] = xs[i];
         if (tid == 0 && p.info) p.info[s] = info;
+        discard_l2(U, (int64_t)n * us * 8, tid, 64);
     }
 }
 
