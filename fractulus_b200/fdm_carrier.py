@@ -156,6 +156,9 @@ class Operator(Element):
         self._element = element
 
     def expand(self, point):
+        fast = self._expand_from_arrays(point)
+        if fast is not None:
+            return fast
         outer = self._stencil.expand(point)
         if self._element is None:
             return outer
@@ -164,6 +167,40 @@ class Operator(Element):
             for inner, wi in self._element.expand(node).items():
                 _accumulate(out, inner, w * wi)
         return out
+
+    def _expand_from_arrays(self, point):
+        """Operator(kernel-built stencil, Operator(small stencil)) on the x axis -- the reference's call pattern
+        (test/integration/test_equation.py:61-66) -- without materialising a Point per intermediate node: the same
+        floating-point operations in the same order as the generic path below (node coordinates point + a + b, products
+        wa * wb, first term assigned and later ones added in the outer stencil's node order, nodes identified after the
+        same rounding), so the result is the same dictionary, in the same order.  None: not this pattern."""
+        st, el = self._stencil, self._element
+        if type(st) is not Stencil or st.weights_array is None or st._dict is not None or st._nodes is None:
+            return None
+        if type(el) is Operator and el._element is None:
+            el = el._stencil
+        if type(el) is not Stencil or point.y != 0. or point.z != 0.:
+            return None
+        inner = list(el._weights.items())
+        if not 0 < len(inner) <= 16 or any(p.y != 0. or p.z != 0. for p, _ in inner):
+            return None
+        if callable(st._nodes):
+            st._nodes = st._nodes()
+        xs = np.asarray(st._nodes, dtype=np.float64)
+        if xs.shape != st.weights_array.shape:
+            return None
+        X = point.x + xs                                                  # point + node
+        Y = X[:, None] + np.array([p.x for p, _ in inner])[None, :]        # node + inner node
+        Wt = st.weights_array[:, None] * np.array([float(w) for _, w in inner])[None, :]
+        acc = {}
+        for y, w in zip(Y.reshape(-1).tolist(), Wt.reshape(-1).tolist()):
+            k = round(y, _ROUND) + 0.
+            e = acc.get(k)
+            if e is None:
+                acc[k] = [y, w]
+            else:
+                e[1] = e[1] + w
+        return {Point(y): w for y, w in acc.values()}
 
 
 class LazyOperation(Element):

@@ -232,3 +232,25 @@ def test_compose_structure_matches_per_item_unique():
         assert np.array_equal(off_c[ptr_c[k]:ptr_c[k + 1]], want), k
     with pytest.raises(ValueError):
         batched._compose_structure(t([0, 1], torch.int64), t([0], torch.int32), t([0, 2], torch.int64), t([3, 3], torch.int32))
+
+
+def test_operator_array_fast_path_equals_generic_expansion():
+    """fdm_carrier.Operator._expand_from_arrays (kernel-built stencil o small stencil, the reference's call pattern of
+    test/integration/test_equation.py:61-66) gives the generic dict-merging expansion: same nodes, same order, same bits."""
+    P, St, Op = fdm_carrier.Point, fdm_carrier.Stencil, fdm_carrier.Operator
+    rng = np.random.default_rng(0)
+    for p in (1, 2, 5, 40, 333):
+        h = 0.001
+        lf = p * h
+        xs = [-lf + (lf / p) * j for j in range(p + 1)]
+        w = rng.standard_normal(p + 1)
+        eager = St({P(x): float(v) for x, v in zip(xs, w)})
+        for inner in (St.central(h), St.central(2 * h), St({P(-h): 1., P(0.): -2., P(h): 1.})):
+            lazy = St.from_layout(lambda xs=xs: list(xs), w, -p, h)
+            assert lazy._dict is None
+            a = Op(lazy, Op(inner)).expand(P(p * h))
+            assert lazy._dict is None                                   # no Point per stencil node was built
+            b = Op(eager, Op(inner)).expand(P(p * h))
+            assert [q.x for q in a] == [q.x for q in b] and list(a.values()) == list(b.values())
+    lazy = St.from_layout(lambda: [0., 1.], np.array([1., 2.]), 0, 1.)
+    assert Op(lazy, fdm_carrier.Number(3.)).expand(P(0.)) == {P(0.): 3., P(1.): 6.}      # other elements: generic path
