@@ -254,3 +254,24 @@ def test_operator_array_fast_path_equals_generic_expansion():
             assert [q.x for q in a] == [q.x for q in b] and list(a.values()) == list(b.values())
     lazy = St.from_layout(lambda: [0., 1.], np.array([1., 2.]), 0, 1.)
     assert Op(lazy, fdm_carrier.Number(3.)).expand(P(0.)) == {P(0.): 3., P(1.): 6.}      # other elements: generic path
+
+
+def test_cr_oracle_tables_equal_the_kernel_rule_functions(hostmath):
+    """The correctly-rounded-pow build of the C oracle and the product's rule functions (host build of csrc/frx_rules.cuh, the
+    source kernel K1 compiles) give bit-identical Toeplitz tables: GPU vs that oracle therefore isolates summation order."""
+    from oracle import clib
+    dp = ctypes.POINTER(ctypes.c_double)
+    hostmath.t_tables.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long, dp, dp, dp, dp, dp]
+    N, h = 20000, 5e-5
+    for rule, code, alphas in (('caputo', 0, (0.1, 0.5, 0.9, 1.5)), ('rectangle', 1, (0.5,)), ('trapezoidal', 2, (0.5, 1.25)),
+                               ('simpson', 3, (0.5, 1.5))):
+        for alpha in alphas:
+            cA, cB, w0, mult = np.zeros(N), np.zeros(N), np.zeros(N + 1), np.zeros(N + 1)
+            cm1 = ctypes.c_double()
+            hostmath.t_tables(code, alpha, h, N, cA.ctypes.data_as(dp), cB.ctypes.data_as(dp), w0.ctypes.data_as(dp),
+                              mult.ctypes.data_as(dp), ctypes.byref(cm1))
+            o = clib.tables(rule, alpha, h, N, cr=True)
+            lo = 2 if rule == 'simpson' else 1          # (row 1 of 'simpson' does not exist: (m-2)**x with m = 1)
+            assert np.array_equal(cA, o[0]) and np.array_equal(w0[lo:], o[2][lo:]) and np.array_equal(mult[1:], o[3][1:]), (rule, alpha)
+            if rule == 'simpson':
+                assert np.array_equal(cB, o[1]) and cm1.value == o[4]
