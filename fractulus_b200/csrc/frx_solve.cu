@@ -204,6 +204,7 @@ constexpr int kStreamMaxNb = 31;
 constexpr int kStreamMaxN = 256;
 constexpr int kStreamBins = 4;    // bins by nb = res + 1: <= 7, <= 15, <= 23, <= 31
 constexpr int kDefaultTwoWarpBins = 0x0;  // FRX_K4_TWO_WARP bits 2,3: two warps per system in the wide-band bins (measured slower: DESIGN.md section 6)
+constexpr int kDefaultPackedBins = 0x1;   // nb <= 7: four systems per warp (measured 1.38x; two per warp at nb <= 15 is slower: bit 1 off)
 constexpr int kDefaultDmmaBins = 0xF;   // bins that run the blocked tensor-core kernel (frx_solve_dmma.cuh)
 __host__ __device__ inline int stream_c(int nb_max) { return 2 * nb_max + 1; }
 __host__ __device__ inline int stream_rs(int nb_max) { return ((stream_c(nb_max) + 7) & ~7) + 1; }   // ring padded to 8, +1 -> odd
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32) frx_k4_band_stream(const St
 struct BinLaunch {
     int64_t grid;
     size_t dyn, scratch;
-    int kind;   // 0: frx_k4_band_stream, 1..4: frx_k4_band_dmma<1,3> / <2,5> / <3,7> / <4,9>, 5..6: frx_k4_band_dmma2<3,7> / <4,9>
+    int kind;   // 0: frx_k4_band_stream, 1..4: frx_k4_band_dmma<1,3> / <2,5> / <3,7> / <4,9>, 5..6: frx_k4_band_dmma2<3,7> / <4,9>, 7..8: frx_k4_band_dmma_packed<1,3,8> / <2,5,16>
 };
 
 // U scratch of one CTA in doubles: a multiple of 128 bytes so that every CTA's slab is line-aligned (discard.global.L2)
@@ -396,6 +397,29 @@ static int band_dmma_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, Bi
     out->grid = (int64_t)ctx->sm_count * per_sm;
     if (out->grid > count) out->grid = count;
     out->scratch = sizeof(double) * (size_t)out->grid * band_ustride_cta(n, nb_bin);
+    return FRX_OK;
+}
+
+template <int RT, int CT, int GS>
+static int band_packed_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, BinLaunch* out) {
+    using G = frx_k4::BandGeo<RT, CT>;
+    constexpr int NG = 32 / GS;
+    out->dyn = sizeof(double) * (size_t)NG * G::smem_doubles(n);
+    FRX_CUDA(cudaFuncSetAttribute(frx_k4::frx_k4_band_dmma_packed<RT, CT, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)out->dyn));
+    int per_sm = 1;
+    FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4::frx_k4_band_dmma_packed<RT, CT, GS>, 32, out->dyn));
+    if (per_sm < 1) per_sm = 1;
+    out->grid = (int64_t)ctx->sm_count * per_sm;
+    const int64_t warps_needed = (count + NG - 1) / NG;
+    if (out->grid > warps_needed) out->grid = warps_needed;
+    out->scratch = sizeof(double) * (size_t)out->grid * NG * band_ustride_cta(n, nb_bin);
+    return FRX_OK;
+}
+
+template <int RT, int CT, int GS>
+static int band_packed_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
+    FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_dmma_packed<RT, CT, GS><<<(unsigned)L.grid, 32, L.dyn, ctx->stream>>>(q));
     return FRX_OK;
 }
 
@@ -506,6 +530,8 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     static const int variant = getenv("FRX_K4_VARIANT") ? atoi(getenv("FRX_K4_VARIANT")) : 0;
     static const int dmma_bins = variant == 2 ? 0 : (getenv("FRX_K4_DMMA_BINS") ? atoi(getenv("FRX_K4_DMMA_BINS")) : kDefaultDmmaBins);
     // FRX_K4_TWO_WARP: bit b set = bin b (2 or 3) runs the two-warps-per-system form of the blocked kernel
+    // FRX_K4_PACKED: bit b set = bin b (0 or 1) runs several systems per warp (frx_k4_band_dmma_packed)
+    static const int packed_bins = getenv("FRX_K4_PACKED") ? atoi(getenv("FRX_K4_PACKED")) : kDefaultPackedBins;
     static const int two_warp_bins = getenv("FRX_K4_TWO_WARP") ? atoi(getenv("FRX_K4_TWO_WARP")) : kDefaultTwoWarpBins;
     if (!d_dense && variant != 1 && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
         frx_k4::BandParams q;
@@ -523,7 +549,12 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         for (int b = 0; b < kStreamBins; ++b) {
             L[b].grid = 0;
             if (!bin_count[b]) continue;
-            if ((two_warp_bins & (1 << b)) && b >= 2 && (dmma_bins & (1 << b))) {
+            if ((packed_bins & (1 << b)) && b <= 1 && (dmma_bins & (1 << b))) {
+                L[b].kind = 7 + b;     // 7, 8: several systems per warp, bins <1,3> (4 systems) and <2,5> (2 systems)
+                rc = b == 0 ? band_packed_geometry<1, 3, 8>(ctx, n, bin_count[b], bin_nb[b], &L[b])
+                            : band_packed_geometry<2, 5, 16>(ctx, n, bin_count[b], bin_nb[b], &L[b]);
+                if (rc) return rc;
+            } else if ((two_warp_bins & (1 << b)) && b >= 2 && (dmma_bins & (1 << b))) {
                 L[b].kind = 3 + b;     // 5, 6: the two-warp kernel for the bins <3,7> and <4,9>
                 rc = b == 2 ? band_dmma2_geometry<3, 7>(ctx, n, bin_count[b], bin_nb[b], &L[b])
                             : band_dmma2_geometry<4, 9>(ctx, n, bin_count[b], bin_nb[b], &L[b]);
@@ -565,6 +596,9 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                 FRX_CUDA(cudaFuncSetAttribute(frx_k4_band_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L[b].dyn));
                 FRX_LAUNCH(ctx, FRX_K_SOLVE,
                            frx_k4_band_stream<<<(unsigned)L[b].grid, kStreamWarps * 32, L[b].dyn, ctx->stream>>>(sp));
+            } else if (L[b].kind >= 7) {
+                rc = L[b].kind == 7 ? band_packed_launch<1, 3, 8>(ctx, q, L[b]) : band_packed_launch<2, 5, 16>(ctx, q, L[b]);
+                if (rc) return rc;
             } else if (L[b].kind >= 5) {
                 rc = L[b].kind == 5 ? band_dmma2_launch<3, 7>(ctx, q, L[b]) : band_dmma2_launch<4, 9>(ctx, q, L[b]);
                 if (rc) return rc;

@@ -417,6 +417,339 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// Narrow bands: SEVERAL systems per warp.  A band with nb <= 7 (<= 15) needs 8 (16) row slots, so one warp holds 4 (2)
+// systems -- lane groups of GS = 8 (16) lanes, each group its own system, window and U scratch.  The pivot chain of a
+// column (three reductions, broadcast, reciprocal, update) is issued ONCE for all groups of the warp (reductions and
+// shuffles confined to the group), the tensor-core phase walks through the groups with the whole warp.  These bins are
+// instruction-issue bound with one system per warp (issue slots 54-59 %, profiles/r02_k4_band_dmma_final_ncu_full.txt).
+// All systems of a launch share n, so the panel loop is uniform; band widths may differ from group to group.
+// ----------------------------------------------------------------------------------------------------------------
+template <class G, int GS>
+__device__ __forceinline__ void band_back_substitution_group(const int gl, const int n, const int n_panels, const int us,
+                                                             const double* __restrict__ U, double* xs) {
+    constexpr int TW = G::TW, TPL = (TW + GS - 1) / GS;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int gq = gl & 7;                           // row of the block this lane solves (GS = 16: lanes 8..15 duplicate 0..7)
+    auto load_block = [&](int kb, double (&uu)[TPL][8], double (&dd)[8]) {
+#pragma unroll
+        for (int jj = 0; jj < TPL; ++jj) {
+            const int t = gl + GS * jj;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int rel = 8 - q + t;
+                uu[jj][q] = (kb >= 0 && t < TW && kb + 8 + t < n && rel < us) ? __ldcg(U + (int64_t)(kb + q) * us + rel) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+            dd[cc] = (kb >= 0 && cc >= gq && cc - gq < us && kb + cc < n) ? __ldcg(U + (int64_t)(kb + gq) * us + cc - gq) : 0.0;
+    };
+    double un[TPL][8], dn[8];
+    load_block((n_panels - 1) * 8, un, dn);
+    for (int kb = (n_panels - 1) * 8; kb >= 0; kb -= 8) {
+        double uc[TPL][8], d[8];
+#pragma unroll
+        for (int jj = 0; jj < TPL; ++jj)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) uc[jj][q] = un[jj][q];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) d[cc] = dn[cc];
+        load_block(kb - 8, un, dn);
+        double sacc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sacc[q] = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < TPL; ++jj) {
+            const int t = gl + GS * jj, j = kb + 8 + t;
+            const double xj = (t < TW && j < n) ? xs[j] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sacc[q] = fma(uc[jj][q], xj, sacc[q]);
+        }
+        if (GS == 16) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sacc[q] += __shfl_xor_sync(FULL, sacc[q], 8);
+        }
+        // transpose-reduce over 8 lanes: lane gq ends with the sum of row kb + gq
+        double v4[4], v2[2], v1;
+        {
+            const bool up = gl & 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double keep = up ? sacc[4 + i] : sacc[i], send = up ? sacc[i] : sacc[4 + i];
+                v4[i] = keep + __shfl_xor_sync(FULL, send, 4);
+            }
+            const bool up2 = gl & 2;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double keep = up2 ? v4[2 + i] : v4[i], send = up2 ? v4[i] : v4[2 + i];
+                v2[i] = keep + __shfl_xor_sync(FULL, send, 2);
+            }
+            const bool up1 = gl & 1;
+            const double keep = up1 ? v2[1] : v2[0], send = up1 ? v2[0] : v2[1];
+            v1 = keep + __shfl_xor_sync(FULL, send, 1);
+        }
+        double rhsq = (kb + gq < n) ? xs[kb + gq] - v1 : 0.0;
+        double rinvq = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) rinvq = cc == gq ? d[cc] : rinvq;
+        __syncwarp();
+#pragma unroll
+        for (int qq = 7; qq >= 0; --qq) {
+            const double xv = __shfl_sync(FULL, rhsq * rinvq, qq, GS);
+            if (gq < qq) rhsq = fma(-d[qq], xv, rhsq);
+            if (gl == qq && kb + qq < n) xs[kb + qq] = xv;
+        }
+        __syncwarp();
+    }
+}
+
+template <int RT, int CT, int GS>
+__global__ void __launch_bounds__(32) frx_k4_band_dmma_packed(const BandParams p) {
+    using G = BandGeo<RT, CT>;
+    constexpr int S = G::S, WC = G::WC, RS = G::RS, TW = G::TW, TS = G::TS;
+    constexpr int NG = 32 / GS, TPL = (TW + GS - 1) / GS, WCL = (WC + GS - 1) / GS;
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(S <= GS && (GS == 8 || GS == 16), "one row slot per lane of a group");
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x, g = lane >> 2, cp = lane & 3, n = p.n;
+    const int gl = lane & (GS - 1), gi = lane / GS;
+    const unsigned gmask = ((1u << GS) - 1u) << (gi * GS);
+    const int gsm = G::smem_doubles(n);                      // doubles of shared memory per system
+    double* W = sm + gi * gsm;
+    double* PB = W + S * RS;
+    double* Ub = PB + S * 8;
+    double* L11 = Ub + 8 * TS;
+    double* apad = L11 + 64;
+    double* xs = apad + G::APAD;
+    double* U = p.uscratch + ((int64_t)blockIdx.x * NG + gi) * p.ustride_cta;
+    const int n_panels = (n + 7) >> 3;
+    for (int64_t base = (int64_t)blockIdx.x * NG; base < p.n_sys; base += (int64_t)gridDim.x * NG) {
+        // a group without a system of its own repeats the launch's last one (same values written twice: harmless)
+        const int64_t sidx = base + gi < p.n_sys ? base + gi : p.n_sys - 1;
+        const int64_t s = p.order[sidx];
+        const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
+        const int nb_a = res + 1;
+        const int nb = nb_a > n - 1 ? n - 1 : nb_a;
+        const int us = 2 * nb + 1;
+        const double ih = 1.0 / p.h[s];
+        const double* rc = p.rcw + p.wptr[s] + res;
+        const double* rhs = p.rhs + s * p.ldb;
+        double* xo = p.x + s * p.ldx;
+        __syncwarp();
+        for (int e = gl; e < G::APAD; e += GS) apad[e] = 0.0;
+        for (int i = gl; i < n; i += GS) xs[i] = rhs[i];
+        __syncwarp();
+        for (int k = -nb_a + gl; k <= nb_a; k += GS) {       // band coefficients: terms and order of the dict-merging expansion
+            double acc = 0.0;
+            bool any = false;
+            auto add = [&](double t) { acc = any ? __dadd_rn(acc, t) : t; any = true; };
+            if (k >= -res && k <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k], ih)));
+            if (k + 1 >= -res && k + 1 <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k + 1], -ih)));
+            if (k - 1 >= -res && k - 1 <= res) add(__dmul_rn(ih, __dmul_rn(rc[k - 1], ih)));
+            if (k >= -res && k <= res) add(__dmul_rn(ih, __dmul_rn(rc[k], -ih)));
+            if (k >= -nb && k <= nb) apad[k + nb] = acc;
+        }
+        __syncwarp();
+        const int rows0 = n < nb + 1 ? n : nb + 1;
+        int label = gl < rows0 ? gl : -1;
+        double bval = gl < rows0 ? xs[gl] : 0.0;
+#pragma unroll 1
+        for (int r0 = 0; r0 < S; ++r0) {
+            if (r0 < rows0) {
+#pragma unroll
+                for (int i = 0; i < WCL; ++i) {
+                    const int jj = gl + GS * i;
+                    if (jj < WC) {
+                        const double v = jj < n ? apad[jj - r0 + nb] : 0.0;
+                        W[r0 * RS + jj] = v;
+                        if (jj < 8) PB[r0 * 8 + jj] = v;
+                    }
+                }
+            }
+        }
+        int info = 0, pm = 0;
+        double areg[7];
+#pragma unroll
+        for (int e = 0; e < 7; ++e) areg[e] = apad[e];
+        __syncwarp();
+        for (int pnl = 0; pnl < n_panels; ++pnl) {
+            const int k0 = pnl * 8;
+            int colidx[TPL];
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                const int t = gl + GS * i;
+                int tile = pm + 1 + (t >> 3);
+                if (tile >= CT) tile -= CT;
+                colidx[i] = tile * 8 + (t & 7);
+            }
+            // ================= phase A: the pivot chain, issued once for all groups of the warp ==================
+            double r[9], u[TPL][8];
+            if (gl < S) {
+                const double2* src = reinterpret_cast<const double2*>(PB + gl * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 v = src[q];
+                    r[2 * q] = v.x;
+                    r[2 * q + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) r[q] = 0.0;
+            }
+            r[8] = bval;
+#pragma unroll
+            for (int i = 0; i < TPL; ++i)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) u[i][q] = 0.0;
+            int ps_valid = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (k0 + c < n) {                            // warp-uniform: every system of the launch has n unknowns
+                    const int k = k0 + c;
+                    ps_valid |= 1 << c;
+                    const bool act = label >= 0;
+                    const unsigned long long bits = act ? (unsigned long long)__double_as_longlong(fabs(r[c])) : 0ull;
+                    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+                    const unsigned mh = __reduce_max_sync(gmask, hi);
+                    const unsigned ml = __reduce_max_sync(gmask, hi == mh ? lo : 0u);
+                    const int code = __reduce_min_sync(gmask, (act && hi == mh && lo == ml) ? ((label << 5) | gl) : 0x7fffffff);
+                    const int P = code & 31, blog = code >> 5;       // P: lane within the group
+                    double prow[9];
+#pragma unroll
+                    for (int cc = c; cc < 9; ++cc) prow[cc] = __shfl_sync(FULL, r[cc], P, GS);
+                    const double pval = prow[c];
+                    if (pval == 0.0 && info == 0) info = k + 1;
+                    const double rinv = 1.0 / pval;
+                    const bool is_pivot = gl == P;
+                    if (act && !is_pivot) {
+                        const double l = r[c] * rinv;
+                        r[c] = l;
+#pragma unroll
+                        for (int cc = c + 1; cc < 9; ++cc) r[cc] = fma(-l, prow[cc], r[cc]);
+                        if (label == k) label = blog;
+                    }
+                    double* wrow = W + P * RS;
+                    const int inew = k + nb + 1;
+#pragma unroll
+                    for (int i = 0; i < TPL; ++i) {
+                        const int t = gl + GS * i;
+                        if (t < TW) {
+                            u[i][c] = wrow[colidx[i]];
+                            if (inew < n) wrow[colidx[i]] = (k0 + 8 + t < n) ? apad[t + 7 - c] : 0.0;
+                        } else {
+                            u[i][c] = 0.0;
+                        }
+                    }
+                    if (is_pivot) {
+#pragma unroll
+                        for (int cc = 0; cc < c; ++cc) L11[c * 8 + cc] = -r[cc];
+                        double* urow = U + (int64_t)k * us;
+                        urow[0] = rinv;
+#pragma unroll
+                        for (int cc = c + 1; cc < 8; ++cc)
+                            if (cc - c < us && k0 + cc < n) urow[cc - c] = r[cc];
+                        xs[k] = r[8];
+                        if (inew < n) {
+#pragma unroll
+                            for (int cc = 0; cc < 8; ++cc) r[cc] = (cc > c && k0 + cc < n) ? areg[cc > c ? cc - c - 1 : 0] : 0.0;
+                            r[8] = xs[inew];
+                            label = inew;
+                        } else {
+                            label = -1;
+#pragma unroll
+                            for (int cc = 0; cc < 9; ++cc) r[cc] = 0.0;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (gl < S) {
+                const bool alive = label >= 0;
+                double m[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) m[cc] = (alive && k0 + cc < n) ? -r[cc] : 0.0;
+                double2* dst = reinterpret_cast<double2*>(PB + gl * 8);
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) dst[qq] = make_double2(m[2 * qq], m[2 * qq + 1]);
+            }
+            bval = r[8];
+            // ================= phase B: U12 = L11^-1 (retired rows), lane of the group = trailing column =========
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                if (ps_valid & (1 << q)) {
+                    const double2* mrow = reinterpret_cast<const double2*>(L11 + q * 8);
+                    double mq[8];
+#pragma unroll
+                    for (int qq = 0; qq < (q + 1) / 2; ++qq) {
+                        const double2 v = mrow[qq];
+                        mq[2 * qq] = v.x;
+                        mq[2 * qq + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < TPL; ++i)
+#pragma unroll
+                        for (int c = 0; c < q; ++c) u[i][q] = fma(mq[c], u[i][c], u[i][q]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                const int t = gl + GS * i;
+                if (t < TW) {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        *reinterpret_cast<double2*>(Ub + (m * TS + t) * 2) = make_double2(u[i][2 * m], u[i][2 * m + 1]);
+                    if (k0 + 8 + t < n) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int rel = 8 - q + t;
+                            if ((ps_valid & (1 << q)) && rel < us) U[(int64_t)(k0 + q) * us + rel] = u[i][q];
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ================= phase C: trailing update, the whole warp on one group after the other ===========
+#pragma unroll
+            for (int g2 = 0; g2 < NG; ++g2) {
+                double* W2 = sm + g2 * gsm;
+                double* PB2 = W2 + S * RS;
+                const double* Ub2 = PB2 + S * 8;
+                double2 am[RT];
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt) am[rt] = *reinterpret_cast<const double2*>(PB2 + (8 * rt + g) * 8 + 2 * cp);
+                __syncwarp();                               // PB of this group may now take its next panel
+                int tile = pm + 1 == CT ? 0 : pm + 1;
+#pragma unroll
+                for (int ct = 0; ct < CT - 1; ++ct) {
+                    const double2 bb = *reinterpret_cast<const double2*>(Ub2 + (cp * TS + 8 * ct + g) * 2);
+#pragma unroll
+                    for (int rt = 0; rt < RT; ++rt) {
+                        double2* cptr = reinterpret_cast<double2*>(W2 + (8 * rt + g) * RS + tile * 8 + 2 * cp);
+                        double2 cf = *cptr;
+                        dmma884(cf.x, cf.y, am[rt].x, bb.x);
+                        dmma884(cf.x, cf.y, am[rt].y, bb.y);
+                        if (ct == 0) *reinterpret_cast<double2*>(PB2 + (8 * rt + g) * 8 + 2 * cp) = cf;
+                        else *cptr = cf;
+                    }
+                    tile = tile + 1 == CT ? 0 : tile + 1;
+                }
+#pragma unroll
+                for (int rt = 0; rt < RT; ++rt)             // the freed column tile: zero, it becomes the right-most one
+                    *reinterpret_cast<double2*>(W2 + (8 * rt + g) * RS + pm * 8 + 2 * cp) = make_double2(0.0, 0.0);
+            }
+            pm = pm + 1 == CT ? 0 : pm + 1;
+            __syncwarp();
+        }
+        band_back_substitution_group<G, GS>(gl, n, n_panels, us, U, xs);
+        for (int i = gl; i < n; i += GS) xo[i] = xs[i];
+        if (gl == 0 && p.info) p.info[s] = info;
+        __syncwarp();
+        discard_l2(U, (int64_t)n * us * 8, gl, GS);
+        __syncwarp();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // Two warps per system (one CTA of 64 threads): the wide-band bins.  Shared memory, not registers, limits how many systems
 // an SM holds (27 KB each at nb = 31 -> 8), and one warp running the dependent chain of a panel issues ~0.2 instructions
 // per cycle (profiles/r02_k4_band_dmma_*): the SM idles.  Here warp 0 keeps the chain -- and nothing else: per column it
