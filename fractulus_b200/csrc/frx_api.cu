@@ -44,10 +44,11 @@ extern "C" int frx_ctx_create(int device, frx_ctx** out) {
     FRX_REQUIRE(c != nullptr, FRX_ERR_ALLOC, "host allocation failed");
     c->device = device;
     c->stream = 0;
+    c->k4_n_sys = -1;
     frx_device_guard guard(device);
     cudaError_t e = guard.err;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&c->scalars, 256);
+    if (e == cudaSuccess) e = cudaMalloc(&c->scalars, 512);   // [0, 256): by-value scalars; [256, 512): K4's fail counters
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->hstage_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->switch_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -156,6 +157,19 @@ extern "C" int frx_ctx_synchronize(frx_ctx* ctx) {
 extern "C" int frx_ctx_launch_count(frx_ctx* ctx, int64_t* n) {
     FRX_REQUIRE(ctx != nullptr && n != nullptr, FRX_ERR_INVALID_ARG, "NULL argument");
     *n = ctx->launches;
+    return FRX_OK;
+}
+
+extern "C" int frx_solve_stats(frx_ctx* ctx, int64_t* n_systems, int64_t* n_pivoted) {
+    FRX_REQUIRE(ctx != nullptr && n_systems && n_pivoted, FRX_ERR_INVALID_ARG, "NULL argument");
+    FRX_ON_DEVICE(ctx);
+    *n_systems = ctx->k4_n_sys < 0 ? 0 : ctx->k4_n_sys;
+    *n_pivoted = *n_systems;
+    if (ctx->k4_n_sys < 0 || !ctx->k4_ldl) return FRX_OK;
+    int32_t cnt[4] = {0, 0, 0, 0};
+    FRX_CUDA(cudaMemcpyAsync(cnt, (const char*)ctx->scalars + 256, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    FRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_pivoted = (int64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3];
     return FRX_OK;
 }
 

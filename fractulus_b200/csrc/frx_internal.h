@@ -18,7 +18,9 @@ struct frx_ctx {
     // grow-only device buffers behind the *_host entry points (caller-facing inputs / outputs)
     void* io;
     size_t io_bytes;
-    void* scalars;         // 256 bytes of device memory for by-value scalar arguments
+    void* scalars;         // 256 bytes of device memory for by-value scalar arguments, then K4's four fail counters
+    int64_t k4_n_sys;      // systems of the last frx_assemble_solve (-1: none yet), k4_ldl: it went through the pivot-free attempt
+    int k4_ldl;
     // grow-only pinned host staging block for batches of host-side parameters (frx_hstage_reserve / _release):
     // filled by the host, uploaded with one async copy, reused only after the event behind that copy has fired
     void* hstage;

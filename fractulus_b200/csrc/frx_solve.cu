@@ -24,6 +24,7 @@
 
 #include "frx_internal.h"
 #include "frx_solve_dmma.cuh"
+#include "frx_solve_ldl.cuh"
 
 namespace {
 
@@ -443,6 +444,27 @@ static int band_dmma2_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const Bi
     return FRX_OK;
 }
 
+
+template <int T>
+static int band_ldl_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, BinLaunch* out) {
+    using G = frx_k4::LdlGeo<T>;
+    out->dyn = sizeof(double) * (size_t)G::smem_doubles(n);
+    FRX_CUDA(cudaFuncSetAttribute(frx_k4::frx_k4_band_ldl<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->dyn));
+    int per_sm = 1;
+    FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4::frx_k4_band_ldl<T>, 32, out->dyn));
+    if (per_sm < 1) per_sm = 1;
+    out->grid = (int64_t)ctx->sm_count * per_sm;
+    if (out->grid > count) out->grid = count;
+    out->scratch = sizeof(double) * (size_t)out->grid * (size_t)G::ustride(n);
+    return FRX_OK;
+}
+
+template <int T>
+static int band_ldl_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
+    FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_ldl<T><<<(unsigned)L.grid, 32, L.dyn, ctx->stream>>>(q));
+    return FRX_OK;
+}
+
 template <int RT, int CT>
 static int band_dmma_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
     FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_dmma<RT, CT><<<(unsigned)L.grid, 32, L.dyn, ctx->stream>>>(q));
@@ -458,6 +480,10 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     FRX_REQUIRE(h_alpha && h_h && h_res, FRX_ERR_INVALID_ARG, "NULL parameter array");
     FRX_REQUIRE(d_dense || (d_rhs && d_x && ldb >= n && ldx >= n), FRX_ERR_INVALID_ARG, "NULL buffer or bad leading dimension");
     FRX_ON_DEVICE(ctx);
+    if (!d_dense) {
+        ctx->k4_n_sys = n_sys;
+        ctx->k4_ldl = 0;
+    }
     // One host pass (domain checks, stencil row pointers, band-width bins) into the context's pinned staging block,
     // laid out like its device image:  [alpha | lf | res | h : 4 n_sys doubles][wptr : n_sys + 1][order : n_sys int32]
     const size_t o_par = 0;
@@ -512,6 +538,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     const size_t o_w = carve(sizeof(double) * (size_t)total_w);
     extern size_t frx_k5_scratch_bytes(int64_t);
     const size_t o_k5 = carve(frx_k5_scratch_bytes(n_sys));
+    const size_t o_fail = carve(sizeof(int32_t) * (size_t)n_sys);       // fail lists of the pivot-free attempt, bin by bin
     rc = frx_ws_reserve(ctx, off);
     if (rc) return rc;
     char* ws = (char*)ctx->ws;
@@ -533,6 +560,10 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     // FRX_K4_PACKED: bit b set = bin b (0 or 1) runs several systems per warp (frx_k4_band_dmma_packed)
     static const int packed_bins = getenv("FRX_K4_PACKED") ? atoi(getenv("FRX_K4_PACKED")) : kDefaultPackedBins;
     static const int two_warp_bins = getenv("FRX_K4_TWO_WARP") ? atoi(getenv("FRX_K4_TWO_WARP")) : kDefaultTwoWarpBins;
+    // FRX_K4_LDL: 1 (default) = every system is first tried without pivoting (frx_k4_band_ldl: definite systems end there),
+    // the pivoted kernels work through what that attempt rejects; 0 = pivoted kernels for everything
+    static const int use_ldl_env = getenv("FRX_K4_LDL") ? atoi(getenv("FRX_K4_LDL")) : 1;
+    const bool use_ldl = use_ldl_env && variant == 0 && dmma_bins == 0xF && two_warp_bins == 0;
     if (!d_dense && variant != 1 && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
         frx_k4::BandParams q;
         q.n = n;
@@ -544,11 +575,23 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.x = d_x;
         q.ldx = ldx;
         q.info = d_info;
-        BinLaunch L[kStreamBins];
+        q.n_sys_dev = nullptr;
+        q.fail_list = nullptr;
+        q.fail_count = nullptr;
+        BinLaunch L[kStreamBins], Lf[kStreamBins];
         size_t scratch = 0;
         for (int b = 0; b < kStreamBins; ++b) {
             L[b].grid = 0;
+            Lf[b].grid = 0;
             if (!bin_count[b]) continue;
+            if (use_ldl) {
+                rc = b == 0 ? band_ldl_geometry<1>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                   : b == 1 ? band_ldl_geometry<2>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                   : b == 2 ? band_ldl_geometry<3>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                            : band_ldl_geometry<4>(ctx, n, bin_count[b], bin_nb[b], &Lf[b]);
+                if (rc) return rc;
+                if (Lf[b].scratch > scratch) scratch = Lf[b].scratch;
+            }
             if ((packed_bins & (1 << b)) && b <= 1 && (dmma_bins & (1 << b))) {
                 L[b].kind = 7 + b;     // 7, 8: several systems per warp, bins <1,3> (4 systems) and <2,5> (2 systems)
                 rc = b == 0 ? band_packed_geometry<1, 3, 8>(ctx, n, bin_count[b], bin_nb[b], &L[b])
@@ -582,10 +625,33 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         rc = frx_io_reserve(ctx, scratch);     // U rows of the resident systems (L2-resident: each warp reuses its slab)
         if (rc) return rc;
         q.uscratch = (double*)ctx->io;
+        ctx->k4_ldl = use_ldl ? 1 : 0;
+        if (use_ldl) {
+            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * kStreamBins, ctx->stream));
+            for (int b = kStreamBins - 1; b >= 0; --b) {
+                if (!bin_count[b]) continue;
+                q.n_sys = bin_count[b];
+                q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
+                q.nb_max = bin_nb[b];
+                q.ustride_cta = b == 0 ? frx_k4::LdlGeo<1>::ustride(n) : b == 1 ? frx_k4::LdlGeo<2>::ustride(n)
+                              : b == 2 ? frx_k4::LdlGeo<3>::ustride(n) : frx_k4::LdlGeo<4>::ustride(n);
+                q.fail_list = (int32_t*)(ws + o_fail) + bin_begin[b];
+                q.fail_count = (int32_t*)((char*)ctx->scalars + 256) + b;
+                rc = b == 0 ? band_ldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_ldl_launch<2>(ctx, q, Lf[b])
+                   : b == 2 ? band_ldl_launch<3>(ctx, q, Lf[b]) : band_ldl_launch<4>(ctx, q, Lf[b]);
+                if (rc) return rc;
+            }
+            q.fail_list = nullptr;
+            q.fail_count = nullptr;
+        }
         for (int b = kStreamBins - 1; b >= 0; --b) {    // widest bands first: the longest-running CTAs start first
             if (!bin_count[b]) continue;
             q.n_sys = bin_count[b];
             q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
+            if (use_ldl) {                                // what the pivot-free attempt rejected, counted on the device
+                q.order = (const int32_t*)(ws + o_fail) + bin_begin[b];
+                q.n_sys_dev = (const int32_t*)((char*)ctx->scalars + 256) + b;
+            }
             q.nb_max = bin_nb[b];
             q.ustride_cta = band_ustride_cta(n, bin_nb[b]);
             if (L[b].kind == 0) {

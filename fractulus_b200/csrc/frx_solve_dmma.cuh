@@ -84,6 +84,9 @@ struct BandParams {
     int64_t ustride_cta;     // doubles per CTA: n * (2 * nb_max + 1) rounded up to a multiple of 16 (128 bytes)
     const int32_t* order;    // the systems of this launch (one band-width bin)
     int nb_max;              // widest band (res + 1) among them
+    const int32_t* n_sys_dev;   // if not NULL: the number of systems in `order` is read from here (a fail list of frx_k4_band_ldl)
+    int32_t* fail_list;      // frx_k4_band_ldl: systems that turned out indefinite, appended at fail_list[atomicAdd(fail_count, 1)]
+    int32_t* fail_count;
 };
 
 // Back substitution in blocks of 8 rows, one warp.  xs[k] = transformed rhs on entry, the solution on exit;
@@ -179,7 +182,8 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma(const BandParams p) {
     double* xs = apad + G::APAD;            // rhs, then transformed rhs, then the solution
     double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
     const int n_panels = (n + 7) >> 3;
-    for (int64_t si = blockIdx.x; si < p.n_sys; si += gridDim.x) {
+    const int64_t n_sys = p.n_sys_dev ? (int64_t)*p.n_sys_dev : p.n_sys;
+    for (int64_t si = blockIdx.x; si < n_sys; si += gridDim.x) {
         const int64_t s = p.order[si];
         const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
         const int nb_a = res + 1;
@@ -523,9 +527,10 @@ __global__ void __launch_bounds__(32) frx_k4_band_dmma_packed(const BandParams p
     double* xs = apad + G::APAD;
     double* U = p.uscratch + ((int64_t)blockIdx.x * NG + gi) * p.ustride_cta;
     const int n_panels = (n + 7) >> 3;
-    for (int64_t base = (int64_t)blockIdx.x * NG; base < p.n_sys; base += (int64_t)gridDim.x * NG) {
+    const int64_t n_sys = p.n_sys_dev ? (int64_t)*p.n_sys_dev : p.n_sys;
+    for (int64_t base = (int64_t)blockIdx.x * NG; base < n_sys; base += (int64_t)gridDim.x * NG) {
         // a group without a system of its own repeats the launch's last one (same values written twice: harmless)
-        const int64_t sidx = base + gi < p.n_sys ? base + gi : p.n_sys - 1;
+        const int64_t sidx = base + gi < n_sys ? base + gi : n_sys - 1;
         const int64_t s = p.order[sidx];
         const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
         const int nb_a = res + 1;
@@ -777,7 +782,8 @@ __global__ void __launch_bounds__(64, 8) frx_k4_band_dmma2(const BandParams p) {
     int* PS = reinterpret_cast<int*>(xs + ((n + 1) & ~1));      // PS[c]: pivot slot of step c, -1 beyond the matrix
     double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
     const int n_panels = (n + 7) >> 3;
-    for (int64_t si = blockIdx.x; si < p.n_sys; si += gridDim.x) {
+    const int64_t n_sys = p.n_sys_dev ? (int64_t)*p.n_sys_dev : p.n_sys;
+    for (int64_t si = blockIdx.x; si < n_sys; si += gridDim.x) {
         const int64_t s = p.order[si];
         const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
         const int nb_a = res + 1;

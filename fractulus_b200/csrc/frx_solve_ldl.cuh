@@ -1,0 +1,314 @@
+// K4, definite systems: blocked band LDL^T without pivoting -- sm_100a.
+//
+// The assembled operator (central o Riesz-Caputo o central) is a SYMMETRIC banded Toeplitz matrix;
+// about three quarters of the (alpha, resolution) pairs of the cfg-4 sweep give a DEFINITE one.  For a definite matrix
+// elimination without row interchanges is unconditionally backward stable (it is the Cholesky / LDL^T factorisation), and
+// definiteness shows in the factorisation itself (Sylvester: the matrix is definite iff every pivot has the sign of the
+// first).  So every system is first tried here; the first pivot of the wrong sign (or a zero / NaN one) ends the attempt and
+// the system is appended to the launch's fail list, which the pivoted kernels of frx_solve_dmma.cuh then work through
+// (device-side count, no host round trip).  Like LAPACK's dpbtrf(uplo='L') the routine reads ONE triangle: the lower band
+// a_m = A[i+m][i], m = 0..nb, mirrored where a diagonal tile needs its upper part.
+//
+// Without interchanges nothing fills in beyond the band and no row ever moves, which removes what the pivoted kernel
+// spends its time on (ncu: 62 % of its instructions are the pivot search / row retirement chain):
+//   * state = the T x T trailing block behind the current panel of 8 columns, lower tiles only: T(T+1)/2 tiles of 8 x 8
+//     in shared memory (5 KB at nb <= 32 against 18 KB of pivoted window), every tile stored as its DMMA C fragment reads it;
+//   * panel: lanes 0..7 hold the rows of the diagonal tile (+ rhs), lane l < 8T the row 8 + l below it.  Per column: the
+//     pivot row is broadcast from a FIXED lane (shuffles), one reciprocal, one multiply, <= 8 FMAs -- the sub-diagonal rows
+//     leave the loop as L21 (multipliers) and, one step earlier, as U12^T (the values before the division): both operands of
+//     the trailing update come out of the same registers, the forward substitution rides along as a ninth column;
+//   * trailing update C(i,j) -= L21(i) U12(j), i >= j: 2 mma.sync.m8n8k4.f64 per tile; the A fragment of row tile i and the
+//     B fragment of column tile j have the SAME lane mapping (lane (g,cp) holds M[8t+g][2cp..2cp+1]), so 4T doubles per
+//     lane feed all T(T+1)/2 tiles.  Tile (i,j) is written where the NEXT panel expects it (one tile up and left), tiles
+//     that enter the band are built from the coefficient vector in the C fragment layout -- no ring, no copies;
+//   * rows >= n: the system is padded with identity rows up to the next multiple of 8;
+//   * U rows (reciprocal pivot at [0]) go to the per-warp scratch in L2, back substitution as in the pivoted kernel.
+//
+// Index bookkeeping prototyped in NumPy first: tools/proto_band_ldl.py.
+#pragma once
+#include "frx_solve_dmma.cuh"
+
+namespace frx_k4 {
+
+template <int T_>
+struct LdlGeo {
+    static constexpr int T = T_;
+    static constexpr int TW = 8 * T, TPL = 1;           // what band_back_substitution reads: columns right of a block
+    static constexpr int NT = T * (T + 1) / 2;          // lower tiles of the trailing block
+    static constexpr int OFF = 8 * T + 8;               // apad[OFF + k] = a_|k|, zero for nb < |k| <= OFF
+    static constexpr int APAD = 2 * OFF + 2;
+    static constexpr int NB_MAX = 8 * T;
+    static constexpr int UBLK = (8 * T + 8) * 8;        // doubles of U scratch per panel: U11 rows, then the rows of U12^T
+    __host__ __device__ static inline int xs_doubles(int n) { return ((n + 7) & ~7) + 8 * T + 2; }   // zero beyond n
+    __host__ __device__ static inline int smem_doubles(int n) { return NT * 64 + 2 * 64 * T + APAD + xs_doubles(n); }
+    __host__ __device__ static inline int64_t ustride(int n) { return (int64_t)((n + 7) >> 3) * UBLK; }
+    __host__ __device__ static constexpr int tile(int i, int j) { return i * (i + 1) / 2 + j; }
+};
+
+// a_k of the assembled operator, k = column - row: the terms and the order of the dict-merging expansion
+// (same expression as in frx_k4_band_dmma)
+__device__ __forceinline__ double band_coefficient(const int k, const int res, const double ih, const double* rc) {
+    double acc = 0.0;
+    bool any = false;
+    auto add = [&](double t) { acc = any ? __dadd_rn(acc, t) : t; any = true; };
+    if (k >= -res && k <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k], ih)));
+    if (k + 1 >= -res && k + 1 <= res) add(__dmul_rn(-ih, __dmul_rn(rc[k + 1], -ih)));
+    if (k - 1 >= -res && k - 1 <= res) add(__dmul_rn(ih, __dmul_rn(rc[k - 1], ih)));
+    if (k >= -res && k <= res) add(__dmul_rn(ih, __dmul_rn(rc[k], -ih)));
+    return acc;
+}
+
+// Back substitution on the panel blocks the factorisation left in the scratch: block of panel kb/8 =
+// [U11: 8 rows of 8, reciprocal pivot on the diagonal][U12^T: 8T rows l of 8, entry q = U[kb + q][kb + 8 + l]].
+// xs = transformed rhs on entry, the solution on exit (zero beyond n, allocated up to 8 * n_panels + 8T).
+template <int T>
+__device__ __forceinline__ void ldl_back_substitution(const int lane, const int n_panels, const double* __restrict__ U, double* xs) {
+    using G = LdlGeo<T>;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int gq = lane >> 2;
+    auto load_block = [&](int pnl, double (&uu)[8], double (&dd)[8]) {
+        if (pnl >= 0) {
+            const double* blk = U + (int64_t)pnl * G::UBLK;
+            const double2* dsrc = reinterpret_cast<const double2*>(blk + gq * 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 v = __ldcg(dsrc + q);
+                dd[2 * q] = v.x;
+                dd[2 * q + 1] = v.y;
+            }
+            if (lane < 8 * T) {
+                const double2* usrc = reinterpret_cast<const double2*>(blk + 64 + lane * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 v = __ldcg(usrc + q);
+                    uu[2 * q] = v.x;
+                    uu[2 * q + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) uu[q] = 0.0;
+            }
+        }
+    };
+    double un[8], dn[8];
+    load_block(n_panels - 1, un, dn);
+    for (int pnl = n_panels - 1; pnl >= 0; --pnl) {
+        const int kb = pnl * 8;
+        double sacc[8], d[8];
+        const double xl = lane < 8 * T ? xs[kb + 8 + lane] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            sacc[q] = un[q] * xl;
+            d[q] = dn[q];
+        }
+        load_block(pnl - 1, un, dn);
+        // transpose-reduce: 8 sums over 32 lanes -> lane group gq holds the sum of row kb + gq
+        double v4[4], v2[2], v1;
+        {
+            const bool up = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double keep = up ? sacc[4 + i] : sacc[i], send = up ? sacc[i] : sacc[4 + i];
+                v4[i] = keep + __shfl_xor_sync(FULL, send, 16);
+            }
+            const bool up8 = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double keep = up8 ? v4[2 + i] : v4[i], send = up8 ? v4[i] : v4[2 + i];
+                v2[i] = keep + __shfl_xor_sync(FULL, send, 8);
+            }
+            const bool up4 = lane & 4;
+            const double keep = up4 ? v2[1] : v2[0], send = up4 ? v2[0] : v2[1];
+            v1 = keep + __shfl_xor_sync(FULL, send, 4);
+            v1 += __shfl_xor_sync(FULL, v1, 2);
+            v1 += __shfl_xor_sync(FULL, v1, 1);
+        }
+        double rhsq = xs[kb + gq] - v1;
+        double rinvq = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) rinvq = cc == gq ? d[cc] : rinvq;
+        __syncwarp();
+#pragma unroll
+        for (int qq = 7; qq >= 0; --qq) {
+            const double xv = __shfl_sync(FULL, rhsq * rinvq, qq * 4);
+            if (gq < qq) rhsq = fma(-d[qq], xv, rhsq);
+            if (lane == qq * 4) xs[kb + qq] = xv;
+        }
+        __syncwarp();
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(32) frx_k4_band_ldl(const BandParams p) {
+    using G = LdlGeo<T>;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int OFF = G::OFF;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x, g = lane >> 2, cp = lane & 3, n = p.n;
+    double* SL = sm;                        // SL[tile(i,j) * 64 + row * 8 + col], i >= j: trailing block behind the panel
+    double* XS = SL + G::NT * 64;           // XS[l * 8 + c] = -L21[l][c]   (A operand)
+    double* YS = XS + 64 * T;               // YS[l * 8 + c] = U12[c][l]    (B operand)
+    double* apad = YS + 64 * T;
+    double* xs = apad + G::APAD;            // rhs, then transformed rhs, then the solution
+    double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
+    const int n_panels = (n + 7) >> 3;
+    const int64_t n_sys = p.n_sys_dev ? (int64_t)*p.n_sys_dev : p.n_sys;
+    for (int64_t si = blockIdx.x; si < n_sys; si += gridDim.x) {
+        const int64_t s = p.order[si];
+        const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
+        const int nb_a = res + 1;
+        const int nb = nb_a > n - 1 ? n - 1 : nb_a;
+        const double ih = 1.0 / p.h[s];
+        const double* rc = p.rcw + p.wptr[s] + res;
+        const double* rhs = p.rhs + s * p.ldb;
+        double* xo = p.x + s * p.ldx;
+        __syncwarp();
+        for (int e = lane; e < G::APAD; e += 32) apad[e] = 0.0;
+        for (int i = lane; i < G::xs_doubles(n); i += 32) xs[i] = i < n ? rhs[i] : 0.0;
+        __syncwarp();
+        for (int m = lane; m <= nb; m += 32) {               // the lower band, mirrored
+            const double a = band_coefficient(-m, res, ih, rc);
+            apad[OFF + m] = a;
+            apad[OFF - m] = a;
+        }
+        __syncwarp();
+        // entries (R, C), (R, C + 1) of the padded matrix, |R - C| <= OFF - 1
+        auto fresh2 = [&](const int R, const int C, const bool edge) -> double2 {
+            double2 v;
+            v.x = apad[OFF + R - C];
+            v.y = apad[OFF + R - C - 1];
+            if (edge) {
+                if (R >= n || C >= n) v.x = R == C ? 1.0 : 0.0;
+                if (R >= n || C + 1 >= n) v.y = R == C + 1 ? 1.0 : 0.0;
+            }
+            return v;
+        };
+#pragma unroll
+        for (int i = 0; i < T; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+                *reinterpret_cast<double2*>(SL + G::tile(i, j) * 64 + g * 8 + 2 * cp) = fresh2(8 * i + g, 8 * j + 2 * cp, 8 * T > n);
+        const double sgn = apad[OFF] < 0.0 ? -1.0 : 1.0;
+        bool bad = false;
+        __syncwarp();
+        for (int pnl = 0; pnl < n_panels; ++pnl) {
+            const int k0 = pnl * 8;
+            const bool edge = k0 + 8 * T + 8 > n;
+            // ================= panel: lanes 0..7 = rows of the diagonal tile, lane l < 8T = row k0 + 8 + l ==========
+            double d[9], r[9], x[8];
+            if (lane < 8) {
+                const double2* src = reinterpret_cast<const double2*>(SL + lane * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 v = src[q];
+                    d[2 * q] = v.x;
+                    d[2 * q + 1] = v.y;
+                }
+                d[8] = xs[k0 + lane];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) d[q] = 0.0;
+            }
+            const int R = k0 + 8 + lane;
+            if (lane < 8 * T) {
+                const int t = lane >> 3;
+                if (t + 1 <= T - 1) {
+                    const double2* src = reinterpret_cast<const double2*>(SL + ((t + 1) * (t + 2) / 2) * 64 + (lane & 7) * 8);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double2 v = src[q];
+                        r[2 * q] = v.x;
+                        r[2 * q + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) r[c] = (!edge || (R < n && k0 + c < n)) ? apad[OFF + 8 + lane - c] : 0.0;
+                }
+                r[8] = xs[R];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) r[q] = 0.0;
+            }
+            double myrinv = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double pv[9];
+#pragma unroll
+                for (int cc = c; cc < 9; ++cc) pv[cc] = __shfl_sync(FULL, d[cc], c);
+                const double pval = pv[c];
+                if (k0 + c < n && !(pval * sgn > 0.0)) bad = true;      // warp-uniform
+                const double rinv = 1.0 / pval;
+                if (lane == c) myrinv = rinv;
+                if (lane > c) {                                          // rows below the pivot inside the diagonal tile
+                    const double l = d[c] * rinv;
+#pragma unroll
+                    for (int cc = c + 1; cc < 9; ++cc) d[cc] = fma(-l, pv[cc], d[cc]);
+                }
+                const double l = r[c] * rinv;                            // r[c] stays: it is U12[c][this row]
+                x[c] = -l;
+#pragma unroll
+                for (int cc = c + 1; cc < 9; ++cc) r[cc] = fma(-l, pv[cc], r[cc]);
+            }
+            if (bad) break;
+            // this panel's block of the U scratch: the rows of the diagonal tile (reciprocal pivot on the diagonal; what is
+            // left of it are multipliers, never read), then the rows of U12^T; the transformed right-hand side stays in xs
+            double* ublk = U + (int64_t)pnl * G::UBLK;
+            if (lane < 8) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                    if (lane == cc) d[cc] = myrinv;
+                double2* ud = reinterpret_cast<double2*>(ublk + lane * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ud[q] = make_double2(d[2 * q], d[2 * q + 1]);
+                xs[k0 + lane] = d[8];
+            }
+            if (lane < 8 * T) {
+                xs[R] = r[8];
+                double2* ud = reinterpret_cast<double2*>(ublk + 64 + lane * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ud[q] = make_double2(r[2 * q], r[2 * q + 1]);
+                double2* xd = reinterpret_cast<double2*>(XS + lane * 8);
+                double2* yd = reinterpret_cast<double2*>(YS + lane * 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    xd[q] = make_double2(x[2 * q], x[2 * q + 1]);
+                    yd[q] = make_double2(r[2 * q], r[2 * q + 1]);
+                }
+            }
+            __syncwarp();
+            // ================= trailing update on the tensor cores, written one tile up and left ====================
+            double2 xa[T], yb[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                xa[t] = *reinterpret_cast<const double2*>(XS + (8 * t + g) * 8 + 2 * cp);
+                yb[t] = *reinterpret_cast<const double2*>(YS + (8 * t + g) * 8 + 2 * cp);
+            }
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    double2 cf;
+                    if (i + 1 <= T - 1) cf = *reinterpret_cast<const double2*>(SL + G::tile(i + 1, j + 1) * 64 + g * 8 + 2 * cp);
+                    else cf = fresh2(k0 + 8 + 8 * i + g, k0 + 8 + 8 * j + 2 * cp, edge);
+                    dmma884(cf.x, cf.y, xa[i].x, yb[j].x);
+                    dmma884(cf.x, cf.y, xa[i].y, yb[j].y);
+                    *reinterpret_cast<double2*>(SL + G::tile(i, j) * 64 + g * 8 + 2 * cp) = cf;
+                }
+            }
+            __syncwarp();
+        }
+        if (!bad) {
+            __syncwarp();
+            ldl_back_substitution<T>(lane, n_panels, U, xs);
+            for (int i = lane; i < n; i += 32) xo[i] = xs[i];
+            if (lane == 0 && p.info) p.info[s] = 0;
+            __syncwarp();
+            discard_l2(U, G::ustride(n) * 8, lane, 32);
+        } else if (lane == 0) {
+            p.fail_list[atomicAdd(p.fail_count, 1)] = (int32_t)s;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace frx_k4
