@@ -460,6 +460,26 @@ static int band_ldl_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, Bin
 }
 
 template <int T>
+static int band_bldl_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, BinLaunch* out) {
+    using G = frx_k4::BldlGeo<T>;
+    (void)nb_bin;
+    out->dyn = sizeof(double) * (size_t)G::smem_doubles(n);
+    int per_sm = 1;
+    FRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frx_k4::frx_k4_band_bldl<T>, 32, out->dyn));
+    if (per_sm < 1) per_sm = 1;
+    out->grid = (int64_t)ctx->sm_count * per_sm;
+    if (out->grid > count) out->grid = count;
+    out->scratch = sizeof(double) * (size_t)out->grid * (size_t)G::ustride(n);
+    return FRX_OK;
+}
+
+template <int T>
+static int band_bldl_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
+    FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_bldl<T><<<(unsigned)L.grid, 32, L.dyn, ctx->stream>>>(q));
+    return FRX_OK;
+}
+
+template <int T>
 static int band_ldl_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
     FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_ldl<T><<<(unsigned)L.grid, 32, L.dyn, ctx->stream>>>(q));
     return FRX_OK;
@@ -560,8 +580,9 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     // FRX_K4_PACKED: bit b set = bin b (0 or 1) runs several systems per warp (frx_k4_band_dmma_packed)
     static const int packed_bins = getenv("FRX_K4_PACKED") ? atoi(getenv("FRX_K4_PACKED")) : kDefaultPackedBins;
     static const int two_warp_bins = getenv("FRX_K4_TWO_WARP") ? atoi(getenv("FRX_K4_TWO_WARP")) : kDefaultTwoWarpBins;
-    // FRX_K4_LDL: 1 (default) = every system is first tried without pivoting (frx_k4_band_ldl: definite systems end there),
-    // the pivoted kernels work through what that attempt rejects; 0 = pivoted kernels for everything
+    // FRX_K4_LDL: 1 (default) = every system is first tried without pivoting (frx_k4_band_bldl: definite systems end there),
+    // the pivoted kernels work through what that attempt rejects; 2 = the same with the first form of the attempt
+    // (frx_k4_band_ldl, scalar pivots, tiles in shared memory); 0 = pivoted kernels for everything
     static const int use_ldl_env = getenv("FRX_K4_LDL") ? atoi(getenv("FRX_K4_LDL")) : 1;
     const bool use_ldl = use_ldl_env && variant == 0 && dmma_bins == 0xF && two_warp_bins == 0;
     if (!d_dense && variant != 1 && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
@@ -585,10 +606,16 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             Lf[b].grid = 0;
             if (!bin_count[b]) continue;
             if (use_ldl) {
-                rc = b == 0 ? band_ldl_geometry<1>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
-                   : b == 1 ? band_ldl_geometry<2>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
-                   : b == 2 ? band_ldl_geometry<3>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
-                            : band_ldl_geometry<4>(ctx, n, bin_count[b], bin_nb[b], &Lf[b]);
+                if (use_ldl_env == 2)
+                    rc = b == 0 ? band_ldl_geometry<1>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                       : b == 1 ? band_ldl_geometry<2>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                       : b == 2 ? band_ldl_geometry<3>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                                : band_ldl_geometry<4>(ctx, n, bin_count[b], bin_nb[b], &Lf[b]);
+                else
+                    rc = b == 0 ? band_bldl_geometry<1>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                       : b == 1 ? band_bldl_geometry<2>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                       : b == 2 ? band_bldl_geometry<3>(ctx, n, bin_count[b], bin_nb[b], &Lf[b])
+                                : band_bldl_geometry<4>(ctx, n, bin_count[b], bin_nb[b], &Lf[b]);
                 if (rc) return rc;
                 if (Lf[b].scratch > scratch) scratch = Lf[b].scratch;
             }
@@ -633,12 +660,20 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                 q.n_sys = bin_count[b];
                 q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
                 q.nb_max = bin_nb[b];
-                q.ustride_cta = b == 0 ? frx_k4::LdlGeo<1>::ustride(n) : b == 1 ? frx_k4::LdlGeo<2>::ustride(n)
-                              : b == 2 ? frx_k4::LdlGeo<3>::ustride(n) : frx_k4::LdlGeo<4>::ustride(n);
+                if (use_ldl_env == 2)
+                    q.ustride_cta = b == 0 ? frx_k4::LdlGeo<1>::ustride(n) : b == 1 ? frx_k4::LdlGeo<2>::ustride(n)
+                                  : b == 2 ? frx_k4::LdlGeo<3>::ustride(n) : frx_k4::LdlGeo<4>::ustride(n);
+                else
+                    q.ustride_cta = b == 0 ? frx_k4::BldlGeo<1>::ustride(n) : b == 1 ? frx_k4::BldlGeo<2>::ustride(n)
+                                  : b == 2 ? frx_k4::BldlGeo<3>::ustride(n) : frx_k4::BldlGeo<4>::ustride(n);
                 q.fail_list = (int32_t*)(ws + o_fail) + bin_begin[b];
                 q.fail_count = (int32_t*)((char*)ctx->scalars + 256) + b;
-                rc = b == 0 ? band_ldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_ldl_launch<2>(ctx, q, Lf[b])
-                   : b == 2 ? band_ldl_launch<3>(ctx, q, Lf[b]) : band_ldl_launch<4>(ctx, q, Lf[b]);
+                if (use_ldl_env == 2)
+                    rc = b == 0 ? band_ldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_ldl_launch<2>(ctx, q, Lf[b])
+                       : b == 2 ? band_ldl_launch<3>(ctx, q, Lf[b]) : band_ldl_launch<4>(ctx, q, Lf[b]);
+                else
+                    rc = b == 0 ? band_bldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_bldl_launch<2>(ctx, q, Lf[b])
+                       : b == 2 ? band_bldl_launch<3>(ctx, q, Lf[b]) : band_bldl_launch<4>(ctx, q, Lf[b]);
                 if (rc) return rc;
             }
             q.fail_list = nullptr;

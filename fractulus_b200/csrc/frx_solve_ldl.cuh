@@ -311,4 +311,220 @@ __global__ void __launch_bounds__(32) frx_k4_band_ldl(const BandParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Second form of the same attempt: BLOCK LDL^T with 8 x 8 block pivots, everything in registers and on the tensor cores.
+//
+// ncu on frx_k4_band_ldl (profiles/r02_k4_band_ldl_v1_ncu_full.txt): the shuffle / shared-memory pipe is the limit
+// (stalls: short scoreboard 4.6 and MIO throttle 2.8 per issue) -- ~470 shared-memory wavefronts and shuffles per panel
+// for the pivot-row broadcasts, the row <-> fragment layout changes and the tile traffic.  Here no tile ever leaves the
+// DMMA C-fragment layout (lane (g, cp) holds M[g][2cp], M[g][2cp+1]):
+//   * A = L_B D_B L_B^T with unit BLOCK lower L_B: the diagonal tile D_p is inverted in place by eight Gauss-Jordan steps
+//     without pivoting on the fragment itself (per step four 64-bit shuffles: the lane's column-c entry, the pivot row's
+//     two entries, the pivot; one reciprocal, two FMAs) -- the pivots are those of the scalar LDL^T, so the definiteness
+//     test is unchanged;
+//   * L21(t) = A21(t) Dinv: two DMMAs per tile with A21(t) AS IT IS (a C fragment is a valid A operand when the B operand
+//     holds rows 2cp / 2cp+1 of the right factor, and Dinv is symmetric: its own fragment); the result is again a C fragment;
+//   * trailing update C(i,j) += (-L21(i)) A21(j)^T: A = the fragment just computed, B = the fragment of A21(j): two DMMAs,
+//     accumulating in the registers of tile (i+1, j+1), which become tile (i, j) of the next panel; tiles entering the band
+//     are T + 1 constant Toeplitz fragments kept in registers (masked at the end of the matrix: identity padding);
+//   * right-hand side as replicated 8-vectors: b(t) += (-L21(t)) z (two FMAs and two xor-shuffles per tile);
+//   * back substitution x_p = Dinv z_p - sum_t L21(t)^T x_{p+t}: two FMAs per tile on the stored fragments and ONE
+//     reduction over the row index (three xor-shuffles of two doubles) -- no triangular solve, no dependent chain.
+// Shared memory: the coefficient vector only.  ~100 shuffles per panel, 2T + T(T+1) DMMAs.  The explicit inverse of the
+// 8 x 8 tile leaves residuals of 1e-15 on the operator's matrices (tools/proto_band_bldl.py checks that on oracle
+// coefficients together with the index bookkeeping).
+template <int T_>
+struct BldlGeo {
+    static constexpr int T = T_;
+    static constexpr int OFF = 8 * T + 8;               // apad[OFF + k] = a_|k|, zero for nb < |k| <= OFF
+    static constexpr int APAD = 2 * OFF + 2;
+    static constexpr int UBLK = (T + 1) * 64 + 16;      // per panel: -Dinv, -L21(1..T) as fragments, z (8) + pad to 128 bytes
+    __host__ __device__ static inline int smem_doubles(int) { return APAD; }
+    __host__ __device__ static inline int64_t ustride(int n) { return (int64_t)((n + 7) >> 3) * UBLK; }
+};
+
+template <int T>
+__global__ void __launch_bounds__(32) frx_k4_band_bldl(const BandParams p) {
+    using G = BldlGeo<T>;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int OFF = G::OFF;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x, g = lane >> 2, cp = lane & 3, n = p.n;
+    double* apad = sm;
+    double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
+    const int n_panels = (n + 7) >> 3;
+    const int fo = g * 8 + 2 * cp;                       // this lane's place inside a stored fragment
+    const int64_t n_sys = p.n_sys_dev ? (int64_t)*p.n_sys_dev : p.n_sys;
+    for (int64_t si = blockIdx.x; si < n_sys; si += gridDim.x) {
+        const int64_t s = p.order[si];
+        const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
+        const int nb_a = res + 1;
+        const int nb = nb_a > n - 1 ? n - 1 : nb_a;
+        const double ih = 1.0 / p.h[s];
+        const double* rc = p.rcw + p.wptr[s] + res;
+        const double* rhs = p.rhs + s * p.ldb;
+        double* xo = p.x + s * p.ldx;
+        __syncwarp();
+        for (int e = lane; e < G::APAD; e += 32) apad[e] = 0.0;
+        __syncwarp();
+        for (int m = lane; m <= nb; m += 32) {               // the lower band, mirrored
+            const double a = band_coefficient(-m, res, ih, rc);
+            apad[OFF + m] = a;
+            apad[OFF - m] = a;
+        }
+        __syncwarp();
+        // the tile on tile-diagonal d of the (infinite) Toeplitz matrix, as this lane's fragment
+        double2 F[T + 1];
+#pragma unroll
+        for (int d = 0; d <= T; ++d) F[d] = make_double2(apad[OFF + 8 * d + g - 2 * cp], apad[OFF + 8 * d + g - 2 * cp - 1]);
+        // ... and what the identity padding beyond n makes of it: (R, C) = row and column of the fragment's first entry
+        auto masked = [&](double2 v, const int R, const int C) -> double2 {
+            if (R >= n || C >= n) v.x = R == C ? 1.0 : 0.0;
+            if (R >= n || C + 1 >= n) v.y = R == C + 1 ? 1.0 : 0.0;
+            return v;
+        };
+        double2 S[T][T];                                     // S[i][j], i >= j: trailing block behind the panel
+        double bv[T];                                        // right-hand side of block row t, entry g (replicated over cp)
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) S[i][j] = 8 * T > n ? masked(F[i - j], 8 * i + g, 8 * j + 2 * cp) : F[i - j];
+            bv[i] = 8 * i + g < n ? rhs[8 * i + g] : 0.0;
+        }
+        double b_in = 8 * T + g < n ? rhs[8 * T + g] : 0.0; // the block row that enters with panel 0
+        const double sgn = apad[OFF] < 0.0 ? -1.0 : 1.0;
+        bool bad = false;
+        for (int pnl = 0; pnl < n_panels; ++pnl) {
+            const int k0 = pnl * 8;
+            const bool edge = k0 + 8 * T + 8 > n;
+            const double b_cur = b_in;
+            b_in = k0 + 8 * T + 8 + g < n ? rhs[k0 + 8 * T + 8 + g] : 0.0;     // one panel ahead
+            // ---- Gauss-Jordan inverse of the diagonal tile, in place in its fragment ----------------------------------
+            double2 M = S[0][0];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int hc = c >> 1;
+                const double own = (c & 1) ? M.y : M.x;
+                const double f = __shfl_sync(FULL, own, (lane & ~3) | hc);      // M[g][c]
+                const double prx = __shfl_sync(FULL, M.x, c * 4 + cp);         // M[c][2cp]
+                const double pry = __shfl_sync(FULL, M.y, c * 4 + cp);         // M[c][2cp+1]
+                const double pv = __shfl_sync(FULL, own, c * 4 + hc);          // M[c][c]
+                if (k0 + c < n && !(pv * sgn > 0.0)) bad = true;               // warp-uniform
+                const double r = 1.0 / pv;
+                const double px = prx * r, py = pry * r, nfr = -f * r;
+                const bool rowc = g == c, atc = cp == hc;
+                double nx = rowc ? px : fma(-f, px, M.x);
+                double ny = rowc ? py : fma(-f, py, M.y);
+                if (atc && !(c & 1)) nx = rowc ? r : nfr;
+                if (atc && (c & 1)) ny = rowc ? r : nfr;
+                M.x = nx;
+                M.y = ny;
+            }
+            if (bad) break;
+            const double2 nD = make_double2(-M.x, -M.y);                       // -Dinv (symmetric)
+            // ---- -L21(t) = A21(t) (-Dinv) -----------------------------------------------------------------------------
+            double2 A21[T + 1], Xn[T + 1];
+#pragma unroll
+            for (int t = 1; t <= T; ++t) {
+                if (t <= T - 1) A21[t] = S[t < T ? t : 0][0];
+                else A21[t] = edge ? masked(F[T], k0 + 8 * T + g, k0 + 2 * cp) : F[T];
+                Xn[t] = make_double2(0.0, 0.0);
+                dmma884(Xn[t].x, Xn[t].y, A21[t].x, nD.x);
+                dmma884(Xn[t].x, Xn[t].y, A21[t].y, nD.y);
+            }
+            // ---- this panel's block of the scratch ---------------------------------------------------------------------
+            double* ublk = U + (int64_t)pnl * G::UBLK;
+            *reinterpret_cast<double2*>(ublk + fo) = nD;
+#pragma unroll
+            for (int t = 1; t <= T; ++t) *reinterpret_cast<double2*>(ublk + t * 64 + fo) = Xn[t];
+            const double z = bv[0];
+            if (cp == 0) ublk[(T + 1) * 64 + g] = z;
+            // ---- right-hand side: b(t) += (-L21(t)) z -------------------------------------------------------------------
+            const double z0 = __shfl_sync(FULL, z, 8 * cp), z1 = __shfl_sync(FULL, z, 8 * cp + 4);    // z[2cp], z[2cp+1]
+            double nbv[T];
+#pragma unroll
+            for (int t = 1; t <= T; ++t) {
+                double part = fma(Xn[t].x, z0, Xn[t].y * z1);
+                part += __shfl_xor_sync(FULL, part, 1);
+                part += __shfl_xor_sync(FULL, part, 2);
+                nbv[t - 1] = (t <= T - 1 ? bv[t < T ? t : 0] : b_cur) + part;
+            }
+            // ---- trailing update: tile (i+1, j+1) of this panel becomes tile (i, j) of the next ---------------------------
+            double2 nS[T][T];
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    double2 c;
+                    if (i + 1 <= T - 1) c = S[i + 1 < T ? i + 1 : 0][j + 1 < T ? j + 1 : 0];
+                    else c = edge ? masked(F[i - j], k0 + 8 + 8 * i + g, k0 + 8 + 8 * j + 2 * cp) : F[i - j];
+                    dmma884(c.x, c.y, Xn[i + 1].x, A21[j + 1].x);
+                    dmma884(c.x, c.y, Xn[i + 1].y, A21[j + 1].y);
+                    nS[i][j] = c;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) S[i][j] = nS[i][j];
+                bv[i] = nbv[i];
+            }
+        }
+        if (!bad) {
+            __syncwarp();                                    // the scratch stores of all lanes are visible to the warp
+            double xv[T];                                    // x of block rows p+1 .. p+T, entry g (replicated over cp)
+#pragma unroll
+            for (int t = 0; t < T; ++t) xv[t] = 0.0;
+            double2 nDn, Xnn[T + 1];
+            double zn;
+            {
+                const double* blk = U + (int64_t)(n_panels - 1) * G::UBLK;
+                nDn = __ldcg(reinterpret_cast<const double2*>(blk + fo));
+#pragma unroll
+                for (int t = 1; t <= T; ++t) Xnn[t] = __ldcg(reinterpret_cast<const double2*>(blk + t * 64 + fo));
+                zn = __ldcg(blk + (T + 1) * 64 + g);
+            }
+            for (int pnl = n_panels - 1; pnl >= 0; --pnl) {
+                const double2 nD = nDn;
+                double2 Xn[T + 1];
+#pragma unroll
+                for (int t = 1; t <= T; ++t) Xn[t] = Xnn[t];
+                const double z = zn;
+                if (pnl > 0) {
+                    const double* blk = U + (int64_t)(pnl - 1) * G::UBLK;
+                    nDn = __ldcg(reinterpret_cast<const double2*>(blk + fo));
+#pragma unroll
+                    for (int t = 1; t <= T; ++t) Xnn[t] = __ldcg(reinterpret_cast<const double2*>(blk + t * 64 + fo));
+                    zn = __ldcg(blk + (T + 1) * 64 + g);
+                }
+                double ax = -nD.x * z, ay = -nD.y * z;       // Dinv[g][j] z[g], j = 2cp, 2cp+1
+#pragma unroll
+                for (int t = 1; t <= T; ++t) {
+                    ax = fma(Xn[t].x, xv[t - 1], ax);
+                    ay = fma(Xn[t].y, xv[t - 1], ay);
+                }
+#pragma unroll
+                for (int off = 4; off <= 16; off <<= 1) {    // sum over the row index g
+                    ax += __shfl_xor_sync(FULL, ax, off);
+                    ay += __shfl_xor_sync(FULL, ay, off);
+                }
+                // x_p[2cp], x_p[2cp+1] in every lane -> x_p[g] in every lane
+                const double sx = __shfl_sync(FULL, ax, (lane & ~3) | (g >> 1)), sy = __shfl_sync(FULL, ay, (lane & ~3) | (g >> 1));
+                const double xg = (g & 1) ? sy : sx;
+                if (cp == 0 && pnl * 8 + g < n) xo[pnl * 8 + g] = xg;
+#pragma unroll
+                for (int t = T - 1; t >= 1; --t) xv[t] = xv[t - 1];
+                xv[0] = xg;
+            }
+            if (lane == 0 && p.info) p.info[s] = 0;
+            __syncwarp();
+            discard_l2(U, G::ustride(n) * 8, lane, 32);
+        } else if (lane == 0) {
+            p.fail_list[atomicAdd(p.fail_count, 1)] = (int32_t)s;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace frx_k4
