@@ -696,23 +696,42 @@ def sub_cfg4(env, n, steps=5):
     ktimes = ctx.kernel_times()
     ctx.set_timing(False)
     solve_ms_per_step = ktimes['solve'][0] / steps              # ALL band-width bins of one step (one launch per bin)
-    # flops the band-limited elimination needs: per column k, nb multipliers + nb x (2nb + 1) updates (x2) + b
+    # Algorithmic flops.  A DEFINITE system needs the band LDL^T: per column nb(nb+1)/2 FMAs + nb multipliers, and 4 nb + 1
+    # flops for the two substitutions; an INDEFINITE one the partially pivoted band LU: nb multipliers + nb x (2nb + 1)
+    # updates (x2) + the substitutions over the filled-in band.  Which systems are which is the kernel's own count, per
+    # band-width bin (frx_solve_stats; the definiteness test is checked against eigenvalues in tests/test_gpu_solve.py).
     nb = np.minimum(res + 1, n - 1)
-    flop = float(np.sum(n * (2.0 * nb * (2 * nb + 1) + 3 * nb) + n * (4 * nb + 1)))
+    flop_lu = n * (2.0 * nb * (2 * nb + 1) + 3 * nb) + n * (4 * nb + 1)
+    flop_ldl = n * (nb * (nb + 1.0) + nb) + n * (4 * nb + 1)
+    n_stat, n_piv, piv_bins = ctx.solve_stats(per_bin=True)
+    bins = np.digitize(res + 1, [7.5, 15.5, 23.5])
+    flop = 0.0
+    for b in range(4):
+        m = bins == b
+        if not m.any():
+            continue
+        share = 1.0 if piv_bins[b] < 0 else piv_bins[b] / float(m.sum())
+        flop += share * float(flop_lu[m].sum()) + (1.0 - share) * float(flop_ldl[m].sum())
     dense_flop = n_sys * (2.0 / 3.0 * n ** 3 + 2.0 * n * n)
     achieved = flop / (solve_ms_per_step * 1e-3) / 1e12
     out = {'workload': 'cfg4: assemble + batch-solve %d systems per GPU, n=%d unknowns, 400 alpha in [0.05,0.95] x 250 length scales '
                        "(resolution 1..30), rule 'caputo' Riesz-Caputo operator, rhs sin(pi x); step = K5 stencil weights + K4 in-kernel "
-                       'assembly + blocked band LU (DMMA trailing update); PARITY UNPINNED (the reference has no solver)' % (n_sys, n),
+                       'assembly + block band LDL^T without pivoting for every system (DMMA), partially pivoted blocked band LU for the '
+                       'indefinite ones it rejects; PARITY UNPINNED (the reference has no solver)' % (n_sys, n),
            'metric': 'fractional_bvp_solves_per_sec', 'value': world * n_sys / (ms_per_step * 1e-3), 'unit': 'solves/s',
            'ms_per_step': ms_per_step, 'steps': steps, 'gpu_launches': launches,
-           'roofline': {'kernel': 'frx_k4_band_dmma (four band-width bins per step)', 'bound': 'fp64', 'achieved': achieved,
+           'indefinite_systems': {'count': n_piv, 'of': n_stat, 'per_band_width_bin': piv_bins,
+                                  'note': 'rejected by the pivot-free attempt (pivot of the wrong sign) and solved by the pivoted LU'},
+           'roofline': {'kernel': 'frx_k4_band_bldl (every system) + frx_k4_band_dmma (indefinite systems), four band-width bins each',
+                        'bound': 'fp64', 'achieved': achieved,
                         'peak': env['peak_dmma'], 'unit': 'TFLOP/s', 'frac': achieved / env['peak_dmma'], 'traffic': None,
                         'kernel_ms': solve_ms_per_step, 'kernel_ms_is': 'sum of the per-bin launches of ONE step',
-                        'algorithmic_flop_per_launch': flop, 'dense_lu_flop_for_context': dense_flop,
+                        'algorithmic_flop_per_launch': flop, 'flop_if_every_system_took_the_pivoted_lu': float(flop_lu.sum()),
+                        'dense_lu_flop_for_context': dense_flop,
                         'per_step_kernel_ms': {kk: v[0] / steps for kk, v in ktimes.items() if v[1]},
-                        'note': 'flop = what the band-limited elimination needs (not 2/3 n^3); peak = the DMMA probe (the trailing update '
-                                'runs on the FP64 tensor cores; DFMA probe %.2f TFLOP/s)' % env['peak_dfma']}}
+                        'note': 'flop = band LDL^T for the definite systems + pivoted band LU for the indefinite ones (not 2/3 n^3); the '
+                                'kernels execute more than that (explicit 8x8 block inverses, full tiles at the band edge); peak = the '
+                                'DMMA probe (DFMA probe %.2f TFLOP/s)' % env['peak_dfma']}}
     # residual of a sample through the kernel's own dense assembly
     idx = np.arange(0, n_sys, 997)
     A = batched.assemble_dense(RULE, alpha[idx], h, res[idx], n)

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "frx_internal.h"
+#include "frx_rules.cuh"
 #include "frx_solve_dmma.cuh"
 #include "frx_solve_ldl.cuh"
 
@@ -521,10 +522,22 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     int bin_nb[kStreamBins] = {0, 0, 0, 0};
     wptr[0] = 0;
     int max_store = 0, max_res = 0;
+    // (the common case inline: the full check -- and its error text -- only for a setting the quick test does not pass)
+    const double alpha_max = rule == FRX_RULE_RECTANGLE ? 1.0 : 2.0, res_min = rule == FRX_RULE_CAPUTO || rule == FRX_RULE_TRAPEZOIDAL ? 1.0 : 2.0;
+    const bool quick_rule = rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON;
     for (int64_t s = 0; s < n_sys; ++s) {
         int32_t first, count;
-        rc = frx_stencil_layout(rule, FRX_SIDE_RIESZ_CAPUTO, h_alpha[s], h_res[s], &first, &count);
-        if (rc) return rc;
+        const double al = h_alpha[s], rs = h_res[s];
+        if (quick_rule && al >= 0.0 && al < alpha_max && rs >= res_min && rs <= 1.0e9 && rs == (double)(long long)rs) {
+            long long f, c;
+            frx_left_layout(rule, (long long)rs, &f, &c);
+            const long long last = f + c - 1, lo = f < -last ? f : -last;       // as frx_stencil_layout, Riesz-Caputo side
+            first = (int32_t)lo;
+            count = (int32_t)(-2 * lo + 1);
+        } else {
+            rc = frx_stencil_layout(rule, FRX_SIDE_RIESZ_CAPUTO, al, rs, &first, &count);
+            if (rc) return rc;
+        }
         if (!(h_h[s] > 0.0)) { frx_set_error("grid step must be positive"); return FRX_ERR_DOMAIN; }
         if (rule == FRX_RULE_SIMPSON && ((int64_t)h_res[s] & 1)) {
             frx_set_error("'simpson' with odd resolution has a node right of the point; use an even resolution here");

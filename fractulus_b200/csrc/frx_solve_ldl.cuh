@@ -345,7 +345,7 @@ struct BldlGeo {
 };
 
 template <int T>
-__global__ void __launch_bounds__(32) frx_k4_band_bldl(const BandParams p) {
+__global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const BandParams p) {
     using G = BldlGeo<T>;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int OFF = G::OFF;
