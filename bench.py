@@ -696,14 +696,15 @@ def sub_cfg4(env, n, steps=5):
     ktimes = ctx.kernel_times()
     ctx.set_timing(False)
     solve_ms_per_step = ktimes['solve'][0] / steps              # ALL band-width bins of one step (one launch per bin)
-    # Algorithmic flops.  A DEFINITE system needs the band LDL^T: per column nb(nb+1)/2 FMAs + nb multipliers, and 4 nb + 1
-    # flops for the two substitutions; an INDEFINITE one the partially pivoted band LU: nb multipliers + nb x (2nb + 1)
-    # updates (x2) + the substitutions over the filled-in band.  Which systems are which is the kernel's own count, per
-    # band-width bin (frx_solve_stats; the definiteness test is checked against eigenvalues in tests/test_gpu_solve.py).
+    # Algorithmic flops.  A system that the pivot-free factorisation solves (definite, or indefinite and accepted on its
+    # residual) is charged the band LDL^T: per column nb(nb+1)/2 FMAs + nb multipliers, and 4 nb + 1 flops for the two
+    # substitutions (refinement steps are overhead, not algorithmic work); one that needs the partially pivoted band LU:
+    # nb multipliers + nb x (2nb + 1) updates (x2) + the substitutions over the filled-in band.  Which systems are which is
+    # the kernel's own count, per band-width bin (frx_solve_stats; checked against eigenvalues in tests/test_gpu_solve.py).
     nb = np.minimum(res + 1, n - 1)
     flop_lu = n * (2.0 * nb * (2 * nb + 1) + 3 * nb) + n * (4 * nb + 1)
     flop_ldl = n * (nb * (nb + 1.0) + nb) + n * (4 * nb + 1)
-    n_stat, n_piv, piv_bins = ctx.solve_stats(per_bin=True)
+    n_stat, n_piv, piv_bins, refined_bins = ctx.solve_stats(per_bin=True)
     bins = np.digitize(res + 1, [7.5, 15.5, 23.5])
     flop = 0.0
     for b in range(4):
@@ -720,8 +721,11 @@ def sub_cfg4(env, n, steps=5):
                        'indefinite ones it rejects; PARITY UNPINNED (the reference has no solver)' % (n_sys, n),
            'metric': 'fractional_bvp_solves_per_sec', 'value': world * n_sys / (ms_per_step * 1e-3), 'unit': 'solves/s',
            'ms_per_step': ms_per_step, 'steps': steps, 'gpu_launches': launches,
-           'indefinite_systems': {'count': n_piv, 'of': n_stat, 'per_band_width_bin': piv_bins,
-                                  'note': 'rejected by the pivot-free attempt (pivot of the wrong sign) and solved by the pivoted LU'},
+           'indefinite_systems': {'accepted_on_residual_after_refinement': int(sum(refined_bins)), 'solved_by_pivoted_lu': n_piv,
+                                  'of': n_stat, 'refined_per_band_width_bin': refined_bins, 'pivoted_per_band_width_bin': piv_bins,
+                                  'note': 'a pivot of the wrong sign in the pivot-free block LDL^T marks a system indefinite: it is kept '
+                                          'only if ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) after <= 2 refinement steps, else the '
+                                          'partially pivoted band LU solves it again'},
            'roofline': {'kernel': 'frx_k4_band_bldl (every system) + frx_k4_band_dmma (indefinite systems), four band-width bins each',
                         'bound': 'fp64', 'achieved': achieved,
                         'peak': env['peak_dmma'], 'unit': 'TFLOP/s', 'frac': achieved / env['peak_dmma'], 'traffic': None,

@@ -69,7 +69,7 @@ SIGNATURES = {
                                            c_void_p, c_void_p, ctypes.c_int64, c_void_p]),
     'frx_assemble_solve': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int32, c_double_p, c_double_p,
                                           c_double_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, c_void_p]),
-    'frx_solve_stats': (ctypes.c_int, [c_void_p, c_int64_p, c_int64_p, c_int64_p]),
+    'frx_solve_stats': (ctypes.c_int, [c_void_p, c_int64_p, c_int64_p, c_int64_p, c_int64_p]),
     'frx_assemble_dense': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int32, c_double_p, c_double_p,
                                           c_double_p, c_void_p]),
     'frx_measure_fp64_peak': (ctypes.c_int, [c_void_p, ctypes.c_int, c_double_p, c_double_p]),
@@ -140,12 +140,12 @@ class Context(object):
         return n.value
 
     def solve_stats(self, per_bin=False):
-        """(systems of the last assemble_solve on this context, how many of them were indefinite and took the pivoted LU
-        [, that count per band-width bin])"""
+        """(systems of the last assemble_solve on this context, how many of them went to the pivoted LU
+        [, that count per band-width bin, the indefinite systems accepted on their residual after refinement per bin])"""
         n, piv = ctypes.c_int64(), ctypes.c_int64()
-        bins = (ctypes.c_int64 * 4)()
-        check(lib().frx_solve_stats(self._h, ctypes.byref(n), ctypes.byref(piv), bins))
-        return (n.value, piv.value, list(bins)) if per_bin else (n.value, piv.value)
+        bins, refined = (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
+        check(lib().frx_solve_stats(self._h, ctypes.byref(n), ctypes.byref(piv), bins, refined))
+        return (n.value, piv.value, list(bins), list(refined)) if per_bin else (n.value, piv.value)
 
     KERNEL_CLASSES = ('weights_table', 'pad_fields', 'history_main', 'history_fixup', 'stencil', 'toeplitz',
                       'solve', 'other')

@@ -160,20 +160,25 @@ extern "C" int frx_ctx_launch_count(frx_ctx* ctx, int64_t* n) {
     return FRX_OK;
 }
 
-extern "C" int frx_solve_stats(frx_ctx* ctx, int64_t* n_systems, int64_t* n_pivoted, int64_t* pivoted_per_bin) {
+extern "C" int frx_solve_stats(frx_ctx* ctx, int64_t* n_systems, int64_t* n_pivoted, int64_t* pivoted_per_bin,
+                               int64_t* refined_per_bin) {
     FRX_REQUIRE(ctx != nullptr && n_systems && n_pivoted, FRX_ERR_INVALID_ARG, "NULL argument");
     FRX_ON_DEVICE(ctx);
     *n_systems = ctx->k4_n_sys < 0 ? 0 : ctx->k4_n_sys;
     *n_pivoted = *n_systems;
-    if (pivoted_per_bin)
-        for (int b = 0; b < 4; ++b) pivoted_per_bin[b] = -1;
+    for (int b = 0; b < 4; ++b) {
+        if (pivoted_per_bin) pivoted_per_bin[b] = -1;
+        if (refined_per_bin) refined_per_bin[b] = -1;
+    }
     if (ctx->k4_n_sys < 0 || !ctx->k4_ldl) return FRX_OK;
-    int32_t cnt[4] = {0, 0, 0, 0};
+    int32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     FRX_CUDA(cudaMemcpyAsync(cnt, (const char*)ctx->scalars + 256, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
     FRX_CUDA(cudaStreamSynchronize(ctx->stream));
     *n_pivoted = (int64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3];
-    if (pivoted_per_bin)
-        for (int b = 0; b < 4; ++b) pivoted_per_bin[b] = cnt[b];
+    for (int b = 0; b < 4; ++b) {
+        if (pivoted_per_bin) pivoted_per_bin[b] = cnt[b];
+        if (refined_per_bin) refined_per_bin[b] = cnt[4 + b];
+    }
     return FRX_OK;
 }
 

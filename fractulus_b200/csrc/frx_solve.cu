@@ -612,6 +612,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.n_sys_dev = nullptr;
         q.fail_list = nullptr;
         q.fail_count = nullptr;
+        q.refined_count = nullptr;
         BinLaunch L[kStreamBins], Lf[kStreamBins];
         size_t scratch = 0;
         for (int b = 0; b < kStreamBins; ++b) {
@@ -667,7 +668,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.uscratch = (double*)ctx->io;
         ctx->k4_ldl = use_ldl ? 1 : 0;
         if (use_ldl) {
-            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * kStreamBins, ctx->stream));
+            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * 2 * kStreamBins, ctx->stream));
             for (int b = kStreamBins - 1; b >= 0; --b) {
                 if (!bin_count[b]) continue;
                 q.n_sys = bin_count[b];
@@ -681,6 +682,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                                   : b == 2 ? frx_k4::BldlGeo<3>::ustride(n) : frx_k4::BldlGeo<4>::ustride(n);
                 q.fail_list = (int32_t*)(ws + o_fail) + bin_begin[b];
                 q.fail_count = (int32_t*)((char*)ctx->scalars + 256) + b;
+                q.refined_count = (int32_t*)((char*)ctx->scalars + 256) + kStreamBins + b;
                 if (use_ldl_env == 2)
                     rc = b == 0 ? band_ldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_ldl_launch<2>(ctx, q, Lf[b])
                        : b == 2 ? band_ldl_launch<3>(ctx, q, Lf[b]) : band_ldl_launch<4>(ctx, q, Lf[b]);
@@ -691,6 +693,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             }
             q.fail_list = nullptr;
             q.fail_count = nullptr;
+            q.refined_count = nullptr;
         }
         for (int b = kStreamBins - 1; b >= 0; --b) {    // widest bands first: the longest-running CTAs start first
             if (!bin_count[b]) continue;

@@ -87,6 +87,7 @@ struct BandParams {
     const int32_t* n_sys_dev;   // if not NULL: the number of systems in `order` is read from here (a fail list of frx_k4_band_ldl)
     int32_t* fail_list;      // frx_k4_band_ldl: systems that turned out indefinite, appended at fail_list[atomicAdd(fail_count, 1)]
     int32_t* fail_count;
+    int32_t* refined_count;  // frx_k4_band_bldl: indefinite systems accepted on their residual after iterative refinement (may be NULL)
 };
 
 // Back substitution in blocks of 8 rows, one warp.  xs[k] = transformed rhs on entry, the solution on exit;

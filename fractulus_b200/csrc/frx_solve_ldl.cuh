@@ -340,9 +340,117 @@ struct BldlGeo {
     static constexpr int OFF = 8 * T + 8;               // apad[OFF + k] = a_|k|, zero for nb < |k| <= OFF
     static constexpr int APAD = 2 * OFF + 2;
     static constexpr int UBLK = (T + 1) * 64 + 16;      // per panel: -Dinv, -L21(1..T) as fragments, z (8) + pad to 128 bytes
-    __host__ __device__ static inline int smem_doubles(int) { return APAD; }
+    static constexpr int XPAD = 32;                     // zeros in front of the solution vector (the band reaches back nb <= 32)
+    __host__ __device__ static inline int npad(int n) { return (n + 31) & ~31; }
+    __host__ __device__ static inline int xs_doubles(int n) { return XPAD + npad(n) + 8 * T + 32; }   // x, zero on both sides
+    __host__ __device__ static inline int rs_doubles(int n) { return npad(n) + 8 * T + 8; }           // residual, zero beyond n
+    __host__ __device__ static inline int smem_doubles(int n) { return APAD + xs_doubles(n) + rs_doubles(n); }
     __host__ __device__ static inline int64_t ustride(int n) { return (int64_t)((n + 7) >> 3) * UBLK; }
 };
+
+// NaN-propagating maximum (fmax would drop a NaN: a broken factorisation must not pass the acceptance test)
+__device__ __forceinline__ double nanmax(const double m, const double v) { return (v > m || v != v) ? v : m; }
+__device__ __forceinline__ double warp_nanmax(double m) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    return m;
+}
+
+// Forward substitution L_B z = r for a NEW right-hand side (iterative refinement) with the stored -L21 fragments;
+// r in shared memory (zero beyond n), z_p goes to the panel blocks of the scratch.
+template <int T>
+__device__ __forceinline__ void bldl_forward(const int lane, const int n_panels, double* U, const double* rs) {
+    using G = BldlGeo<T>;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int g = lane >> 2, cp = lane & 3, fo = g * 8 + 2 * cp;
+    double bv[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) bv[t] = rs[8 * t + g];
+    double2 Xnn[T + 1];
+#pragma unroll
+    for (int t = 1; t <= T; ++t) Xnn[t] = __ldcg(reinterpret_cast<const double2*>(U + t * 64 + fo));
+#pragma unroll 1
+    for (int pnl = 0; pnl < n_panels; ++pnl) {
+        double2 Xn[T + 1];
+#pragma unroll
+        for (int t = 1; t <= T; ++t) Xn[t] = Xnn[t];
+        if (pnl + 1 < n_panels) {
+            const double* blk = U + (int64_t)(pnl + 1) * G::UBLK;
+#pragma unroll
+            for (int t = 1; t <= T; ++t) Xnn[t] = __ldcg(reinterpret_cast<const double2*>(blk + t * 64 + fo));
+        }
+        const double z = bv[0];
+        if (cp == 0) U[(int64_t)pnl * G::UBLK + (T + 1) * 64 + g] = z;
+        const double z0 = __shfl_sync(FULL, z, 8 * cp), z1 = __shfl_sync(FULL, z, 8 * cp + 4);
+        double nbv[T];
+#pragma unroll
+        for (int t = 1; t <= T; ++t) {
+            double part = fma(Xn[t].x, z0, Xn[t].y * z1);
+            part += __shfl_xor_sync(FULL, part, 1);
+            part += __shfl_xor_sync(FULL, part, 2);
+            nbv[t - 1] = (t <= T - 1 ? bv[t < T ? t : 0] : rs[pnl * 8 + 8 * T + g]) + part;
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t) bv[t] = nbv[t];
+    }
+}
+
+// Back substitution x_p = Dinv z_p - sum_t L21(t)^T x_{p+t} on the panel blocks of the scratch; the solution goes to
+// shared memory (xs[XPAD + i]), added to what is there when `accumulate` (a refinement step).
+template <int T>
+__device__ __forceinline__ void bldl_backward(const int lane, const int n_panels, const double* U, double* xs, const bool accumulate) {
+    using G = BldlGeo<T>;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int g = lane >> 2, cp = lane & 3, fo = g * 8 + 2 * cp;
+    double xv[T];                                    // x of block rows p+1 .. p+T, entry g (replicated over cp)
+#pragma unroll
+    for (int t = 0; t < T; ++t) xv[t] = 0.0;
+    double2 nDn, Xnn[T + 1];
+    double zn;
+    {
+        const double* blk = U + (int64_t)(n_panels - 1) * G::UBLK;
+        nDn = __ldcg(reinterpret_cast<const double2*>(blk + fo));
+#pragma unroll
+        for (int t = 1; t <= T; ++t) Xnn[t] = __ldcg(reinterpret_cast<const double2*>(blk + t * 64 + fo));
+        zn = __ldcg(blk + (T + 1) * 64 + g);
+    }
+#pragma unroll 1
+    for (int pnl = n_panels - 1; pnl >= 0; --pnl) {
+        const double2 nD = nDn;
+        double2 Xn[T + 1];
+#pragma unroll
+        for (int t = 1; t <= T; ++t) Xn[t] = Xnn[t];
+        const double z = zn;
+        if (pnl > 0) {
+            const double* blk = U + (int64_t)(pnl - 1) * G::UBLK;
+            nDn = __ldcg(reinterpret_cast<const double2*>(blk + fo));
+#pragma unroll
+            for (int t = 1; t <= T; ++t) Xnn[t] = __ldcg(reinterpret_cast<const double2*>(blk + t * 64 + fo));
+            zn = __ldcg(blk + (T + 1) * 64 + g);
+        }
+        double ax = -nD.x * z, ay = -nD.y * z;       // Dinv[g][j] z[g], j = 2cp, 2cp+1
+#pragma unroll
+        for (int t = 1; t <= T; ++t) {
+            ax = fma(Xn[t].x, xv[t - 1], ax);
+            ay = fma(Xn[t].y, xv[t - 1], ay);
+        }
+#pragma unroll
+        for (int off = 4; off <= 16; off <<= 1) {    // sum over the row index g
+            ax += __shfl_xor_sync(FULL, ax, off);
+            ay += __shfl_xor_sync(FULL, ay, off);
+        }
+        // x_p[2cp], x_p[2cp+1] in every lane -> x_p[g] in every lane
+        const double sx = __shfl_sync(FULL, ax, (lane & ~3) | (g >> 1)), sy = __shfl_sync(FULL, ay, (lane & ~3) | (g >> 1));
+        const double xg = (g & 1) ? sy : sx;
+        if (cp == 0) {
+            double* dst = xs + G::XPAD + pnl * 8 + g;
+            *dst = accumulate ? *dst + xg : xg;
+        }
+#pragma unroll
+        for (int t = T - 1; t >= 1; --t) xv[t] = xv[t - 1];
+        xv[0] = xg;
+    }
+}
 
 template <int T>
 __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const BandParams p) {
@@ -352,6 +460,8 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x, g = lane >> 2, cp = lane & 3, n = p.n;
     double* apad = sm;
+    double* xs = apad + G::APAD;                         // xs[XPAD + i] = x_i, zero before 0 and beyond n
+    double* rs = xs + G::xs_doubles(n);                  // residual of a refinement step, zero beyond n
     double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
     const int n_panels = (n + 7) >> 3;
     const int fo = g * 8 + 2 * cp;                       // this lane's place inside a stored fragment
@@ -367,11 +477,14 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         double* xo = p.x + s * p.ldx;
         __syncwarp();
         for (int e = lane; e < G::APAD; e += 32) apad[e] = 0.0;
+        for (int e = lane; e < G::xs_doubles(n); e += 32) xs[e] = 0.0;
         __syncwarp();
+        double amax = 0.0;
         for (int m = lane; m <= nb; m += 32) {               // the lower band, mirrored
             const double a = band_coefficient(-m, res, ih, rc);
             apad[OFF + m] = a;
             apad[OFF - m] = a;
+            amax = fmax(amax, fabs(a));
         }
         __syncwarp();
         // the tile on tile-diagonal d of the (infinite) Toeplitz matrix, as this lane's fragment
@@ -394,7 +507,8 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         }
         double b_in = 8 * T + g < n ? rhs[8 * T + g] : 0.0; // the block row that enters with panel 0
         const double sgn = apad[OFF] < 0.0 ? -1.0 : 1.0;
-        bool bad = false;
+        bool indef = false;
+#pragma unroll 1
         for (int pnl = 0; pnl < n_panels; ++pnl) {
             const int k0 = pnl * 8;
             const bool edge = k0 + 8 * T + 8 > n;
@@ -410,7 +524,7 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
                 const double prx = __shfl_sync(FULL, M.x, c * 4 + cp);         // M[c][2cp]
                 const double pry = __shfl_sync(FULL, M.y, c * 4 + cp);         // M[c][2cp+1]
                 const double pv = __shfl_sync(FULL, own, c * 4 + hc);          // M[c][c]
-                if (k0 + c < n && !(pv * sgn > 0.0)) bad = true;               // warp-uniform
+                if (k0 + c < n && !(pv * sgn > 0.0)) indef = true;             // warp-uniform
                 const double r = 1.0 / pv;
                 const double px = prx * r, py = pry * r, nfr = -f * r;
                 const bool rowc = g == c, atc = cp == hc;
@@ -421,7 +535,6 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
                 M.x = nx;
                 M.y = ny;
             }
-            if (bad) break;
             const double2 nD = make_double2(-M.x, -M.y);                       // -Dinv (symmetric)
             // ---- -L21(t) = A21(t) (-Dinv) -----------------------------------------------------------------------------
             double2 A21[T + 1], Xn[T + 1];
@@ -471,58 +584,54 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
                 bv[i] = nbv[i];
             }
         }
-        if (!bad) {
-            __syncwarp();                                    // the scratch stores of all lanes are visible to the warp
-            double xv[T];                                    // x of block rows p+1 .. p+T, entry g (replicated over cp)
-#pragma unroll
-            for (int t = 0; t < T; ++t) xv[t] = 0.0;
-            double2 nDn, Xnn[T + 1];
-            double zn;
-            {
-                const double* blk = U + (int64_t)(n_panels - 1) * G::UBLK;
-                nDn = __ldcg(reinterpret_cast<const double2*>(blk + fo));
-#pragma unroll
-                for (int t = 1; t <= T; ++t) Xnn[t] = __ldcg(reinterpret_cast<const double2*>(blk + t * 64 + fo));
-                zn = __ldcg(blk + (T + 1) * 64 + g);
+        __syncwarp();                                        // the scratch stores of all lanes are visible to the warp
+        bldl_backward<T>(lane, n_panels, U, xs, false);
+        __syncwarp();
+        // A definite matrix (every pivot of the sign of the first) needs nothing else: elimination without interchanges is
+        // backward stable for it.  An indefinite one is ACCEPTED ONLY ON ITS RESIDUAL: up to two steps of iterative refinement
+        // with the same factors, each followed by the test  ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||)  (max norms; NaN fails).
+        bool ok = !indef;
+        if (indef) {
+            amax = warp_nanmax(amax);
+#pragma unroll 1
+            for (int it = 0; it < 3 && !ok; ++it) {
+                double rmax = 0.0, xmax = 0.0, bmax = 0.0;
+                for (int i = lane; i < G::rs_doubles(n); i += 32) {
+                    double acc = 0.0;
+                    if (i < n) {
+                        const double bi = rhs[i];
+                        acc = bi;
+                        const double* xi = xs + G::XPAD + i;
+                        for (int k = -nb; k <= nb; ++k) acc = fma(-apad[OFF + k], xi[k], acc);
+                        rmax = nanmax(rmax, fabs(acc));
+                        xmax = nanmax(xmax, fabs(xi[0]));
+                        bmax = nanmax(bmax, fabs(bi));
+                    }
+                    rs[i] = acc;
+                }
+                rmax = warp_nanmax(rmax);
+                xmax = warp_nanmax(xmax);
+                bmax = warp_nanmax(bmax);
+                ok = rmax <= 16.0 * 2.220446049250313e-16 * fma(amax, xmax, bmax);
+                if (ok || it == 2) break;
+                __syncwarp();
+                bldl_forward<T>(lane, n_panels, U, rs);
+                __syncwarp();
+                bldl_backward<T>(lane, n_panels, U, xs, true);
+                __syncwarp();
             }
-            for (int pnl = n_panels - 1; pnl >= 0; --pnl) {
-                const double2 nD = nDn;
-                double2 Xn[T + 1];
-#pragma unroll
-                for (int t = 1; t <= T; ++t) Xn[t] = Xnn[t];
-                const double z = zn;
-                if (pnl > 0) {
-                    const double* blk = U + (int64_t)(pnl - 1) * G::UBLK;
-                    nDn = __ldcg(reinterpret_cast<const double2*>(blk + fo));
-#pragma unroll
-                    for (int t = 1; t <= T; ++t) Xnn[t] = __ldcg(reinterpret_cast<const double2*>(blk + t * 64 + fo));
-                    zn = __ldcg(blk + (T + 1) * 64 + g);
-                }
-                double ax = -nD.x * z, ay = -nD.y * z;       // Dinv[g][j] z[g], j = 2cp, 2cp+1
-#pragma unroll
-                for (int t = 1; t <= T; ++t) {
-                    ax = fma(Xn[t].x, xv[t - 1], ax);
-                    ay = fma(Xn[t].y, xv[t - 1], ay);
-                }
-#pragma unroll
-                for (int off = 4; off <= 16; off <<= 1) {    // sum over the row index g
-                    ax += __shfl_xor_sync(FULL, ax, off);
-                    ay += __shfl_xor_sync(FULL, ay, off);
-                }
-                // x_p[2cp], x_p[2cp+1] in every lane -> x_p[g] in every lane
-                const double sx = __shfl_sync(FULL, ax, (lane & ~3) | (g >> 1)), sy = __shfl_sync(FULL, ay, (lane & ~3) | (g >> 1));
-                const double xg = (g & 1) ? sy : sx;
-                if (cp == 0 && pnl * 8 + g < n) xo[pnl * 8 + g] = xg;
-#pragma unroll
-                for (int t = T - 1; t >= 1; --t) xv[t] = xv[t - 1];
-                xv[0] = xg;
+        }
+        if (ok) {
+            for (int i = lane; i < n; i += 32) xo[i] = xs[G::XPAD + i];
+            if (lane == 0) {
+                if (p.info) p.info[s] = 0;
+                if (indef && p.refined_count) atomicAdd(p.refined_count, 1);
             }
-            if (lane == 0 && p.info) p.info[s] = 0;
-            __syncwarp();
-            discard_l2(U, G::ustride(n) * 8, lane, 32);
         } else if (lane == 0) {
             p.fail_list[atomicAdd(p.fail_count, 1)] = (int32_t)s;
         }
+        __syncwarp();
+        discard_l2(U, G::ustride(n) * 8, lane, 32);
         __syncwarp();
     }
 }

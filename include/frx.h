@@ -216,13 +216,16 @@ int frx_stencil_compose(frx_ctx* ctx, int64_t n_items, const int64_t* d_ptr_a, c
 int frx_assemble_solve(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
                        const double* h_res, const double* d_rhs, int64_t ldb, double* d_x, int64_t ldx,
                        int32_t* d_info);
-/* After frx_assemble_solve: how many systems the last call on this context held and how many of them were INDEFINITE,
- * i.e. rejected by the pivot-free block LDL^T attempt (a pivot of the wrong sign) and solved by the partially pivoted band
- * LU; pivoted_per_bin (may be NULL) receives that count for each band-width bin (res + 1 <= 7, 15, 23, 31), -1 when the
- * attempt did not run.  Synchronises the context's stream.  n_pivoted == n_systems when the attempt is switched off
- * (FRX_K4_LDL=0) or the batch took another kernel (bands wider than 31, n > 256).  No counterpart in the reference
- * (it has no solver). */
-int frx_solve_stats(frx_ctx* ctx, int64_t* n_systems, int64_t* n_pivoted, int64_t* pivoted_per_bin /*[4]*/);
+/* After frx_assemble_solve: what the last call on this context did with its systems.  Every system is first factorised
+ * WITHOUT pivoting (block LDL^T): a DEFINITE matrix (every pivot of the sign of the first) ends there -- elimination without
+ * interchanges is backward stable for it; an INDEFINITE one is accepted only on its residual, after at most two steps of
+ * iterative refinement with the same factors:  ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||)  in max norms -- refined_per_bin
+ * counts those; what fails that test is solved again by the partially pivoted band LU -- n_pivoted / pivoted_per_bin count
+ * those.  Bins: band width res + 1 <= 7, 15, 23, 31; the per-bin arrays may be NULL and hold -1 when the attempt did not
+ * run.  Synchronises the context's stream.  n_pivoted == n_systems when the attempt is switched off (FRX_K4_LDL=0) or the
+ * batch took another kernel (bands wider than 31, n > 256).  No counterpart in the reference (it has no solver). */
+int frx_solve_stats(frx_ctx* ctx, int64_t* n_systems, int64_t* n_pivoted, int64_t* pivoted_per_bin /*[4]*/,
+                    int64_t* refined_per_bin /*[4]*/);
 /* verification aid: the assembled matrices, row-major n x n per system, written to d_A (no solve) */
 int frx_assemble_dense(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
                        const double* h_res, double* d_A);

@@ -26,7 +26,7 @@ for rule in ('caputo', 'trapezoidal'):
         g = torch.Generator(device='cuda').manual_seed(n)
         rhs = torch.randn(n_sys, n, dtype=torch.float64, device='cuda', generator=g)
         x, info = batched.assemble_solve(rule, alpha, h, res, rhs, return_info=True)
-        total, pivoted = ctx.solve_stats()
+        total, pivoted, piv_bins, refined_bins = ctx.solve_stats(per_bin=True)
         A = batched.assemble_dense(rule, alpha, h, res, n)
         r = torch.bmm(A, x.unsqueeze(-1)).squeeze(-1) - rhs
         scale = (A.abs().amax(dim=(1, 2)) * x.abs().amax(dim=1)).unsqueeze(-1) + rhs.abs().amax(dim=1, keepdim=True)
@@ -36,11 +36,12 @@ for rule in ('caputo', 'trapezoidal'):
         want = torch.linalg.solve(A, rhs)
         cond = (ev.abs().amax(dim=1) / ev.abs().amin(dim=1))
         err = ((x - want).abs().amax(dim=1) / want.abs().amax(dim=1)) / cond
-        rec = {'rule': rule, 'n': n, 'n_sys': n_sys, 'stats_total': total, 'pivoted': pivoted,
+        rec = {'rule': rule, 'n': n, 'n_sys': n_sys, 'stats_total': total, 'pivoted': pivoted, 'refined': int(sum(refined_bins)),
                'indefinite_by_eig': int((~definite).sum()), 'max_resid': float(resid.max()), 'max_err_over_cond': float(err.max()),
                'info_nonzero': int((info != 0).sum()), 'finite': bool(torch.isfinite(x).all())}
         print(json.dumps(rec), flush=True)
         out.append(rec)
-ok = all(r['finite'] and r['max_resid'] < 1e-13 and r['stats_total'] == r['n_sys'] and r['max_err_over_cond'] < 1e-14 for r in out)
+ok = all(r['finite'] and r['max_resid'] < 1e-14 and r['stats_total'] == r['n_sys'] and r['max_err_over_cond'] < 1e-14
+         and r['pivoted'] + r['refined'] == r['indefinite_by_eig'] for r in out)
 print('OK' if ok else 'FAILED')
 sys.exit(0 if ok else 1)
