@@ -13,6 +13,10 @@
 // with rc_o the Riesz-Caputo stencil weights -- the terms and their order are those of the dict-merging
 // expansion, so the assembled matrix is bit-identical to the oracle's wherever the stencil weights are.
 //
+// Kernels: bands up to 31 wide and n <= 256 go, one warp per system, through the pivot-free block
+// LDL^T of frx_solve_ldl.cuh (definite systems end there, indefinite ones only if refinement certifies their residual) and
+// then, for what that rejects, through the partially pivoted blocked band LU of frx_solve_dmma.cuh; everything else through
+// the CTA-per-system kernel of this file:
 // The matrix never touches HBM: each CTA builds it in shared memory from the 2*res+1 stencil weights (produced
 // for the whole batch by kernel K5), factors it by LU with partial pivoting, and solves.  A is banded
 // (half-bandwidth nb = res+1; partial pivoting fills at most 2*nb above the diagonal), so it is stored in LAPACK

@@ -1,16 +1,19 @@
-// K4, definite systems: blocked band LDL^T without pivoting -- sm_100a.
+// K4, first path: band LDL^T WITHOUT pivoting -- sm_100a.  Two forms of the same idea live here:
+//   frx_k4_band_bldl<T>  (shipped, second half of the file): block LDL^T with 8 x 8 block pivots, tiles in registers;
+//   frx_k4_band_ldl<T>   (first form, FRX_K4_LDL=2): scalar pivots, tiles in shared memory; kept for comparison.
 //
 // The assembled operator (central o Riesz-Caputo o central) is a SYMMETRIC banded Toeplitz matrix;
 // about three quarters of the (alpha, resolution) pairs of the cfg-4 sweep give a DEFINITE one.  For a definite matrix
 // elimination without row interchanges is unconditionally backward stable (it is the Cholesky / LDL^T factorisation), and
 // definiteness shows in the factorisation itself (Sylvester: the matrix is definite iff every pivot has the sign of the
-// first).  So every system is first tried here; the first pivot of the wrong sign (or a zero / NaN one) ends the attempt and
-// the system is appended to the launch's fail list, which the pivoted kernels of frx_solve_dmma.cuh then work through
-// (device-side count, no host round trip).  Like LAPACK's dpbtrf(uplo='L') the routine reads ONE triangle: the lower band
-// a_m = A[i+m][i], m = 0..nb, mirrored where a diagonal tile needs its upper part.
+// first).  So every system is first tried here.  A pivot of the wrong sign marks the system indefinite: the first form
+// gives up at once, the shipped form keeps the solution only if its residual passes after at most two steps of iterative
+// refinement.  What is rejected is appended to the launch's fail list, which the pivoted kernels of frx_solve_dmma.cuh then
+// work through (device-side count, no host round trip).  Like LAPACK's dpbtrf(uplo='L') the routines read ONE triangle:
+// the lower band a_m = A[i+m][i], m = 0..nb, mirrored where a diagonal tile needs its upper part.
 //
-// Without interchanges nothing fills in beyond the band and no row ever moves, which removes what the pivoted kernel
-// spends its time on (ncu: 62 % of its instructions are the pivot search / row retirement chain):
+// frx_k4_band_ldl<T>: without interchanges nothing fills in beyond the band and no row ever moves, which removes what the
+// pivoted kernel spends its time on (ncu: 62 % of its instructions are the pivot search / row retirement chain):
 //   * state = the T x T trailing block behind the current panel of 8 columns, lower tiles only: T(T+1)/2 tiles of 8 x 8
 //     in shared memory (5 KB at nb <= 32 against 18 KB of pivoted window), every tile stored as its DMMA C fragment reads it;
 //   * panel: lanes 0..7 hold the rows of the diagonal tile (+ rhs), lane l < 8T the row 8 + l below it.  Per column: the
@@ -22,9 +25,10 @@
 //     lane feed all T(T+1)/2 tiles.  Tile (i,j) is written where the NEXT panel expects it (one tile up and left), tiles
 //     that enter the band are built from the coefficient vector in the C fragment layout -- no ring, no copies;
 //   * rows >= n: the system is padded with identity rows up to the next multiple of 8;
-//   * U rows (reciprocal pivot at [0]) go to the per-warp scratch in L2, back substitution as in the pivoted kernel.
+//   * per panel the rows of the diagonal tile (reciprocal pivot on the diagonal) and of U12^T go to the per-warp scratch in
+//     L2 as dense blocks; back substitution in blocks of 8 rows (transpose-reduce + 8 x 8 triangle).
 //
-// Index bookkeeping prototyped in NumPy first: tools/proto_band_ldl.py.
+// Index bookkeeping prototyped in NumPy first: tools/proto_band_ldl.py, tools/proto_band_bldl.py.
 #pragma once
 #include "frx_solve_dmma.cuh"
 
@@ -33,7 +37,6 @@ namespace frx_k4 {
 template <int T_>
 struct LdlGeo {
     static constexpr int T = T_;
-    static constexpr int TW = 8 * T, TPL = 1;           // what band_back_substitution reads: columns right of a block
     static constexpr int NT = T * (T + 1) / 2;          // lower tiles of the trailing block
     static constexpr int OFF = 8 * T + 8;               // apad[OFF + k] = a_|k|, zero for nb < |k| <= OFF
     static constexpr int APAD = 2 * OFF + 2;
@@ -331,9 +334,13 @@ __global__ void __launch_bounds__(32) frx_k4_band_ldl(const BandParams p) {
 //   * right-hand side as replicated 8-vectors: b(t) += (-L21(t)) z (two FMAs and two xor-shuffles per tile);
 //   * back substitution x_p = Dinv z_p - sum_t L21(t)^T x_{p+t}: two FMAs per tile on the stored fragments and ONE
 //     reduction over the row index (three xor-shuffles of two doubles) -- no triangular solve, no dependent chain.
-// Shared memory: the coefficient vector only.  ~100 shuffles per panel, 2T + T(T+1) DMMAs.  The explicit inverse of the
-// 8 x 8 tile leaves residuals of 1e-15 on the operator's matrices (tools/proto_band_bldl.py checks that on oracle
-// coefficients together with the index bookkeeping).
+//   * an INDEFINITE system (a pivot of the wrong sign) is kept only on its residual: up to two steps of iterative
+//     refinement with the same factors (residual with one lane per row from the coefficient vector, forward substitution
+//     with the stored -L21 fragments, the same back substitution accumulating into x), each followed by the test
+//     ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) in max norms; what fails goes to the fail list.
+// Shared memory: the coefficient vector, x and the residual.  ~100 shuffles per panel, 2T + T(T+1) DMMAs.  The explicit
+// inverse of the 8 x 8 tile leaves residuals of 1e-15 on the operator's definite matrices (tools/proto_band_bldl.py checks
+// that on oracle coefficients together with the index bookkeeping).
 template <int T_>
 struct BldlGeo {
     static constexpr int T = T_;
