@@ -766,9 +766,10 @@ def sub_cfg4(env, n, steps=5):
         e2e_s = t.item()
     out['e2e'] = {'value': world * n_sys / e2e_s, 'unit': 'solves/s', 'ms_per_step': e2e_s * 1e3,
                   'h2d_bytes_per_step': (8 * n_sys * n + 24 * n_sys) * world, 'd2h_bytes_per_step': 8 * n_sys * n * world,
-                  'api': 'sweep.assemble_solve_sweep (pinned NumPy rhs in, shared pinned host result out; chunks of 16384 systems, copies '
-                         'overlapped with the solves)' if world == 1 else
-                         'batched.assemble_solve_host on every rank (its own systems; pinned NumPy in and out, chunked, overlapped)'}
+                  'api': 'sweep.assemble_solve_sweep (pinned NumPy rhs in, shared page-locked host result out, both used IN PLACE by the '
+                         'kernels: every right-hand side is read once and every solution written once over PCIe while the batch solves)'
+                         if world == 1 else
+                         'batched.assemble_solve_host on every rank (its own systems; pinned NumPy in and out, used in place by the kernels)'}
     if rank == 0:
         from oracle import assemble
         k = 6

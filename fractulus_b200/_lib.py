@@ -69,6 +69,8 @@ SIGNATURES = {
                                            c_void_p, c_void_p, ctypes.c_int64, c_void_p]),
     'frx_assemble_solve': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int32, c_double_p, c_double_p,
                                           c_double_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64, c_void_p]),
+    'frx_assemble_solve_host': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int32, c_double_p, c_double_p,
+                                               c_double_p, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),
     'frx_solve_stats': (ctypes.c_int, [c_void_p, c_int64_p, c_int64_p, c_int64_p, c_int64_p]),
     'frx_assemble_dense': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int32, c_double_p, c_double_p,
                                           c_double_p, c_void_p]),

@@ -11,6 +11,8 @@ number is produced by the hand-written kernels in fractulus_b200/csrc.
 import collections
 import ctypes
 
+import os
+
 import numpy as np
 import torch
 
@@ -456,15 +458,33 @@ def toeplitz_apply_host(approximation, alpha, h, G, N=None, out=None, chunk=512,
     return out
 
 
-def assemble_solve_host(approximation, alpha, h, res, rhs, out=None, chunk=16384, device=None):
-    """K4 with host buffers: rhs NumPy [n_sys, n] in, x NumPy [n_sys, n] out, in chunks of `chunk` systems with the copies
-    overlapped with the solves."""
+def _is_page_locked(a):
+    """True for a C-contiguous float64 NumPy array in pinned / CUDA-registered host memory"""
+    return (type(a) is np.ndarray and a.dtype == np.float64 and a.flags.c_contiguous and a.size > 0
+            and torch.as_tensor(a).is_pinned())
+
+
+def assemble_solve_host(approximation, alpha, h, res, rhs, out=None, chunk=32768, device=None):
+    """K4 with host buffers: rhs NumPy [n_sys, n] in, x NumPy [n_sys, n] out.
+
+    Page-locked buffers (pinned_empty, a CUDA-registered shared segment) are used IN PLACE by one call of
+    frx_assemble_solve_host: every kernel reads a right-hand side once and writes a solution once over PCIe while it solves.
+    Pageable buffers (or FRX_HOST_ZERO_COPY=0) travel in chunks of `chunk` systems, copies overlapped with the solves."""
     dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
     n_sys, n = rhs.shape
     a, hh, rr = _solve_params(alpha, h, res, n_sys)
     if out is None:
         out = pinned_empty((n_sys, n))
-    if n_sys:
-        _pipelined(rhs, out, max(1, min(n_sys, chunk)), n, n,
-                   lambda d_in, d_out, b, e: assemble_solve(approximation, a[b:e], hh[b:e], rr[b:e], d_in, out=d_out), dev)
+    if not n_sys:
+        return out
+    if os.environ.get('FRX_HOST_ZERO_COPY', '1') != '0' and _is_page_locked(rhs) and _is_page_locked(out) \
+            and tuple(out.shape) == (n_sys, n):
+        ctx, idx = _ctx_for(dev)
+        _lib.check(_lib.lib().frx_assemble_solve_host(ctx.handle, _lib.RULES[approximation], n_sys, n,
+                                                      a.ctypes.data_as(_lib.c_double_p), hh.ctypes.data_as(_lib.c_double_p),
+                                                      rr.ctypes.data_as(_lib.c_double_p), rhs.ctypes.data, n, out.ctypes.data, n))
+        ctx.synchronize()
+        return out
+    _pipelined(rhs, out, max(1, min(n_sys, chunk)), n, n,
+               lambda d_in, d_out, b, e: assemble_solve(approximation, a[b:e], hh[b:e], rr[b:e], d_in, out=d_out), dev)
     return out

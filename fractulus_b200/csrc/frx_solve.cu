@@ -771,6 +771,28 @@ extern "C" int frx_assemble_solve(frx_ctx* ctx, int rule, int64_t n_sys, int32_t
     return solve_common(ctx, rule, n_sys, n, h_alpha, h_h, h_res, d_rhs, ldb, d_x, ldx, d_info, nullptr);
 }
 
+// Host-buffer form: right-hand sides and solutions in PAGE-LOCKED host memory (cudaHostAlloc / cudaHostRegister, e.g. a
+// pinned NumPy array or the shared segment of a multi-GPU sweep), used IN PLACE: every kernel reads a system's right-hand
+// side once (coalesced, into shared memory) and writes its solution once, so the two transfers ride on the solves instead
+// of framing them.  Pageable buffers are refused (the Python layer stages those through chunked copies).
+extern "C" int frx_assemble_solve_host(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
+                                       const double* h_res, const double* h_rhs, int64_t ldb, double* h_x, int64_t ldx) {
+    FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
+    if (n_sys == 0) return FRX_OK;
+    FRX_REQUIRE(h_rhs && h_x, FRX_ERR_INVALID_ARG, "NULL buffer");
+    FRX_ON_DEVICE(ctx);
+    cudaPointerAttributes at_b, at_x;
+    const bool ok_b = cudaPointerGetAttributes(&at_b, h_rhs) == cudaSuccess && at_b.type == cudaMemoryTypeHost && at_b.devicePointer;
+    const bool ok_x = cudaPointerGetAttributes(&at_x, h_x) == cudaSuccess && at_x.type == cudaMemoryTypeHost && at_x.devicePointer;
+    cudaGetLastError();
+    if (!ok_b || !ok_x) {
+        frx_set_error("frx_assemble_solve_host needs page-locked (pinned or registered) host buffers");
+        return FRX_ERR_INVALID_ARG;
+    }
+    return solve_common(ctx, rule, n_sys, n, h_alpha, h_h, h_res, (const double*)at_b.devicePointer, ldb,
+                        (double*)at_x.devicePointer, ldx, nullptr, nullptr);
+}
+
 extern "C" int frx_assemble_dense(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
                                   const double* h_res, double* d_A) {
     FRX_REQUIRE(d_A != nullptr, FRX_ERR_INVALID_ARG, "d_A is NULL");

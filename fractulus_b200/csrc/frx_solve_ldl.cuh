@@ -351,7 +351,7 @@ struct BldlGeo {
     __host__ __device__ static inline int npad(int n) { return (n + 31) & ~31; }
     __host__ __device__ static inline int xs_doubles(int n) { return XPAD + npad(n) + 8 * T + 32; }   // x, zero on both sides
     __host__ __device__ static inline int rs_doubles(int n) { return npad(n) + 8 * T + 8; }           // residual, zero beyond n
-    __host__ __device__ static inline int smem_doubles(int n) { return APAD + xs_doubles(n) + rs_doubles(n); }
+    __host__ __device__ static inline int smem_doubles(int n) { return APAD + xs_doubles(n) + 2 * rs_doubles(n); }
     __host__ __device__ static inline int64_t ustride(int n) { return (int64_t)((n + 7) >> 3) * UBLK; }
 };
 
@@ -469,6 +469,8 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
     double* apad = sm;
     double* xs = apad + G::APAD;                         // xs[XPAD + i] = x_i, zero before 0 and beyond n
     double* rs = xs + G::xs_doubles(n);                  // residual of a refinement step, zero beyond n
+    double* bs = rs + G::rs_doubles(n);                  // the right-hand side, zero beyond n: read ONCE from global memory
+                                                         // (which may be page-locked host memory: frx_assemble_solve_host)
     double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
     const int n_panels = (n + 7) >> 3;
     const int fo = g * 8 + 2 * cp;                       // this lane's place inside a stored fragment
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         __syncwarp();
         for (int e = lane; e < G::APAD; e += 32) apad[e] = 0.0;
         for (int e = lane; e < G::xs_doubles(n); e += 32) xs[e] = 0.0;
+        for (int e = lane; e < G::rs_doubles(n); e += 32) bs[e] = e < n ? rhs[e] : 0.0;
         __syncwarp();
         double amax = 0.0;
         for (int m = lane; m <= nb; m += 32) {               // the lower band, mirrored
@@ -510,9 +513,9 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         for (int i = 0; i < T; ++i) {
 #pragma unroll
             for (int j = 0; j <= i; ++j) S[i][j] = 8 * T > n ? masked(F[i - j], 8 * i + g, 8 * j + 2 * cp) : F[i - j];
-            bv[i] = 8 * i + g < n ? rhs[8 * i + g] : 0.0;
+            bv[i] = bs[8 * i + g];
         }
-        double b_in = 8 * T + g < n ? rhs[8 * T + g] : 0.0; // the block row that enters with panel 0
+        double b_in = bs[8 * T + g];                         // the block row that enters with panel 0
         const double sgn = apad[OFF] < 0.0 ? -1.0 : 1.0;
         bool indef = false;
 #pragma unroll 1
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
             const int k0 = pnl * 8;
             const bool edge = k0 + 8 * T + 8 > n;
             const double b_cur = b_in;
-            b_in = k0 + 8 * T + 8 + g < n ? rhs[k0 + 8 * T + 8 + g] : 0.0;     // one panel ahead
+            b_in = bs[k0 + 8 * T + 8 + g];                                     // one panel ahead
             // ---- Gauss-Jordan inverse of the diagonal tile, in place in its fragment ----------------------------------
             double2 M = S[0][0];
 #pragma unroll
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
                 for (int i = lane; i < G::rs_doubles(n); i += 32) {
                     double acc = 0.0;
                     if (i < n) {
-                        const double bi = rhs[i];
+                        const double bi = bs[i];
                         acc = bi;
                         const double* xi = xs + G::XPAD + i;
                         for (int k = -nb; k <= nb; ++k) acc = fma(-apad[OFF + k], xi[k], acc);

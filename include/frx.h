@@ -216,6 +216,11 @@ int frx_stencil_compose(frx_ctx* ctx, int64_t n_items, const int64_t* d_ptr_a, c
 int frx_assemble_solve(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
                        const double* h_res, const double* d_rhs, int64_t ldb, double* d_x, int64_t ldx,
                        int32_t* d_info);
+/* The same with right-hand sides and solutions in PAGE-LOCKED host memory (pinned or cudaHostRegister'ed), used in place:
+ * the kernels read each right-hand side once and write each solution once over PCIe while they solve; returns when the
+ * work is queued (frx_ctx_synchronize before reading h_x).  Pageable buffers: FRX_ERR_INVALID_ARG. */
+int frx_assemble_solve_host(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
+                            const double* h_res, const double* h_rhs, int64_t ldb, double* h_x, int64_t ldx);
 /* After frx_assemble_solve: what the last call on this context did with its systems.  Every system is first factorised
  * WITHOUT pivoting (block LDL^T): a DEFINITE matrix (every pivot of the sign of the first) ends there -- elimination without
  * interchanges is backward stable for it; an INDEFINITE one is accepted only on its residual, after at most two steps of

@@ -124,7 +124,8 @@ def test_solve_errors():
 
 
 def test_host_buffer_forms_equal_device_calls():
-    """batched.assemble_solve_host / toeplitz_apply_host (chunked, copies overlapped with the kernels) = the device calls."""
+    """batched.assemble_solve_host (pageable buffers: chunked, copies overlapped with the kernels; page-locked buffers: used
+    in place by the kernels) and toeplitz_apply_host = the device calls."""
     n, n_sys = 64, 5000
     rng = np.random.default_rng(2)
     alpha = rng.uniform(0.1, 0.9, n_sys)
