@@ -351,9 +351,16 @@ struct BldlGeo {
     __host__ __device__ static inline int npad(int n) { return (n + 31) & ~31; }
     __host__ __device__ static inline int xs_doubles(int n) { return XPAD + npad(n) + 8 * T + 32; }   // x, zero on both sides
     __host__ __device__ static inline int rs_doubles(int n) { return npad(n) + 8 * T + 8; }           // residual, zero beyond n
-    __host__ __device__ static inline int smem_doubles(int n) { return APAD + xs_doubles(n) + 2 * rs_doubles(n); }
+    __host__ __device__ static inline int smem_doubles(int n) { return APAD + xs_doubles(n) + 3 * rs_doubles(n); }
     __host__ __device__ static inline int64_t ustride(int n) { return (int64_t)((n + 7) >> 3) * UBLK; }
 };
+
+// 8-byte asynchronous copy global -> shared (LDGSTS): the NEXT system's right-hand side travels while this one is solved
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // NaN-propagating maximum (fmax would drop a NaN: a broken factorisation must not pass the acceptance test)
 __device__ __forceinline__ double nanmax(const double m, const double v) { return (v > m || v != v) ? v : m; }
@@ -469,12 +476,19 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
     double* apad = sm;
     double* xs = apad + G::APAD;                         // xs[XPAD + i] = x_i, zero before 0 and beyond n
     double* rs = xs + G::xs_doubles(n);                  // residual of a refinement step, zero beyond n
-    double* bs = rs + G::rs_doubles(n);                  // the right-hand side, zero beyond n: read ONCE from global memory
-                                                         // (which may be page-locked host memory: frx_assemble_solve_host)
+    // the right-hand side, zero beyond n: read ONCE from global memory (which may be page-locked host memory:
+    // frx_assemble_solve_host), one system ahead by asynchronous copies into the other of two buffers
+    double* bs = rs + G::rs_doubles(n);
+    double* bs_next = bs + G::rs_doubles(n);
     double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta;
     const int n_panels = (n + 7) >> 3;
     const int fo = g * 8 + 2 * cp;                       // this lane's place inside a stored fragment
     const int64_t n_sys = p.n_sys_dev ? (int64_t)*p.n_sys_dev : p.n_sys;
+    for (int e = n + lane; e < G::rs_doubles(n); e += 32) bs[e] = bs_next[e] = 0.0;
+    if ((int64_t)blockIdx.x < n_sys) {
+        const double* rhs0 = p.rhs + (int64_t)p.order[blockIdx.x] * p.ldb;
+        for (int e = lane; e < n; e += 32) cp_async8(bs + e, rhs0 + e);
+    }
     for (int64_t si = blockIdx.x; si < n_sys; si += gridDim.x) {
         const int64_t s = p.order[si];
         const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
@@ -482,12 +496,15 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         const int nb = nb_a > n - 1 ? n - 1 : nb_a;
         const double ih = 1.0 / p.h[s];
         const double* rc = p.rcw + p.wptr[s] + res;
-        const double* rhs = p.rhs + s * p.ldb;
         double* xo = p.x + s * p.ldx;
+        cp_async_wait_all();                                 // this system's right-hand side has landed in bs
         __syncwarp();
+        if (si + gridDim.x < n_sys) {
+            const double* rhs1 = p.rhs + (int64_t)p.order[si + gridDim.x] * p.ldb;
+            for (int e = lane; e < n; e += 32) cp_async8(bs_next + e, rhs1 + e);
+        }
         for (int e = lane; e < G::APAD; e += 32) apad[e] = 0.0;
         for (int e = lane; e < G::xs_doubles(n); e += 32) xs[e] = 0.0;
-        for (int e = lane; e < G::rs_doubles(n); e += 32) bs[e] = e < n ? rhs[e] : 0.0;
         __syncwarp();
         double amax = 0.0;
         for (int m = lane; m <= nb; m += 32) {               // the lower band, mirrored
@@ -643,7 +660,11 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         __syncwarp();
         discard_l2(U, G::ustride(n) * 8, lane, 32);
         __syncwarp();
+        double* t = bs;
+        bs = bs_next;
+        bs_next = t;
     }
+    cp_async_wait_all();
 }
 
 }  // namespace frx_k4

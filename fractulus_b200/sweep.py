@@ -317,7 +317,7 @@ def assemble_solve_sweep(approximation, alpha, h, res, rhs, group=None, compute=
     host_io = not torch.is_tensor(rhs)
     n_sys, n = int(rhs.shape[0]), int(rhs.shape[1])
     a, hh, rr = batched._solve_params(alpha, h, res, n_sys)
-    begin, end = partition_weighted(solve_cost(rr, n), world, rank)
+    begin, end = (0, n_sys) if world == 1 else partition_weighted(solve_cost(rr, n), world, rank)
     sl = slice(begin, end)
     if not host_io:
         x = batched.assemble_solve(approximation, a[sl], hh[sl], rr[sl], rhs[sl]) if compute is None else \
