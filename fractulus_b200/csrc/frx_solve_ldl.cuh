@@ -362,6 +362,16 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// 1 / p for the pivots: MUFU seed (2^-23) and two Newton steps, no special-case branch.  p = 0, denormal, Inf or NaN give
+// Inf / NaN -- such a pivot has already failed the sign test (p * sgn > 1e-300), and the residual test rejects what follows.
+__device__ __forceinline__ double pivot_reciprocal(const double p) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    r = fma(r, fma(-p, r, 1.0), r);
+    r = fma(r, fma(-p, r, 1.0), r);
+    return r;
+}
+
 // NaN-propagating maximum (fmax would drop a NaN: a broken factorisation must not pass the acceptance test)
 __device__ __forceinline__ double nanmax(const double m, const double v) { return (v > m || v != v) ? v : m; }
 __device__ __forceinline__ double warp_nanmax(double m) {
@@ -518,10 +528,12 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         double2 F[T + 1];
 #pragma unroll
         for (int d = 0; d <= T; ++d) F[d] = make_double2(apad[OFF + 8 * d + g - 2 * cp], apad[OFF + 8 * d + g - 2 * cp - 1]);
-        // ... and what the identity padding beyond n makes of it: (R, C) = row and column of the fragment's first entry
+        // ... and what the padding beyond n makes of it (diagonal entries of the sign of a_0, so that a padded pivot passes
+        // the sign test like any other): (R, C) = row and column of the fragment's first entry
+        const double sgn = apad[OFF] < 0.0 ? -1.0 : 1.0;
         auto masked = [&](double2 v, const int R, const int C) -> double2 {
-            if (R >= n || C >= n) v.x = R == C ? 1.0 : 0.0;
-            if (R >= n || C + 1 >= n) v.y = R == C + 1 ? 1.0 : 0.0;
+            if (R >= n || C >= n) v.x = R == C ? sgn : 0.0;
+            if (R >= n || C + 1 >= n) v.y = R == C + 1 ? sgn : 0.0;
             return v;
         };
         double2 S[T][T];                                     // S[i][j], i >= j: trailing block behind the panel
@@ -533,8 +545,7 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
             bv[i] = bs[8 * i + g];
         }
         double b_in = bs[8 * T + g];                         // the block row that enters with panel 0
-        const double sgn = apad[OFF] < 0.0 ? -1.0 : 1.0;
-        bool indef = false;
+        int n_bad = 0;                                       // pivots that are not of the sign of a_0 (warp-uniform)
 #pragma unroll 1
         for (int pnl = 0; pnl < n_panels; ++pnl) {
             const int k0 = pnl * 8;
@@ -551,8 +562,8 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
                 const double prx = __shfl_sync(FULL, M.x, c * 4 + cp);         // M[c][2cp]
                 const double pry = __shfl_sync(FULL, M.y, c * 4 + cp);         // M[c][2cp+1]
                 const double pv = __shfl_sync(FULL, own, c * 4 + hc);          // M[c][c]
-                if (k0 + c < n && !(pv * sgn > 0.0)) indef = true;             // warp-uniform
-                const double r = 1.0 / pv;
+                n_bad += !(pv * sgn > 1e-300);
+                const double r = pivot_reciprocal(pv);
                 const double px = prx * r, py = pry * r, nfr = -f * r;
                 const bool rowc = g == c, atc = cp == hc;
                 double nx = rowc ? px : fma(-f, px, M.x);
@@ -617,6 +628,7 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         // A definite matrix (every pivot of the sign of the first) needs nothing else: elimination without interchanges is
         // backward stable for it.  An indefinite one is ACCEPTED ONLY ON ITS RESIDUAL: up to two steps of iterative refinement
         // with the same factors, each followed by the test  ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||)  (max norms; NaN fails).
+        const bool indef = n_bad != 0;
         bool ok = !indef;
         if (indef) {
             amax = warp_nanmax(amax);

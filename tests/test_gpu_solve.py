@@ -146,3 +146,28 @@ def test_host_buffer_forms_equal_device_calls():
     Yd = batched.toeplitz_apply('caputo', 0.4, 1. / N, torch.as_tensor(G, device='cuda'), N=N).cpu().numpy()
     Yh = batched.toeplitz_apply_host('caputo', 0.4, 1. / N, G, N=N, chunk=8)
     assert np.allclose(Yh[:, 1:], Yd[:, 1:], rtol=1e-12, atol=1e-12 * np.abs(Yd[:, 1:]).max())
+
+
+def test_assemble_solve_host_entry_point_needs_page_locked_buffers():
+    """frx_assemble_solve_host uses its buffers in place: pageable memory is refused (the Python layer stages that through
+    chunked copies instead), page-locked memory gives the device call's bits."""
+    import ctypes
+    from fractulus_b200 import _lib
+    n, n_sys = 40, 64
+    alpha, hh, rr = np.full(n_sys, 0.4), np.full(n_sys, 1. / (n + 1)), 1. + np.arange(n_sys) % 9
+    rhs = np.random.default_rng(0).standard_normal((n_sys, n))
+    out = np.empty_like(rhs)
+    ctx = _lib.context(0)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+    rc = _lib.lib().frx_assemble_solve_host(ctx.handle, _lib.RULES['caputo'], n_sys, n, dp(alpha), dp(hh), dp(rr), rhs.ctypes.data, n,
+                                            out.ctypes.data, n)
+    assert rc != 0 and b'page-locked' in _lib.lib().frx_last_error_string()
+    rhs_pin, out_pin = batched.pinned_empty(rhs.shape), batched.pinned_empty(rhs.shape)
+    rhs_pin[:] = rhs
+    rc = _lib.lib().frx_assemble_solve_host(ctx.handle, _lib.RULES['caputo'], n_sys, n, dp(alpha), dp(hh), dp(rr), rhs_pin.ctypes.data, n,
+                                            out_pin.ctypes.data, n)
+    assert rc == 0
+    ctx.synchronize()
+    want = batched.assemble_solve('caputo', alpha, hh, rr, torch.as_tensor(rhs, device='cuda')).cpu().numpy()
+    assert np.array_equal(out_pin, want)
+
