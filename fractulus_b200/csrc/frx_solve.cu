@@ -617,6 +617,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.fail_list = nullptr;
         q.fail_count = nullptr;
         q.refined_count = nullptr;
+        q.queue = nullptr;
         BinLaunch L[kStreamBins], Lf[kStreamBins];
         size_t scratch = 0;
         for (int b = 0; b < kStreamBins; ++b) {
@@ -672,7 +673,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.uscratch = (double*)ctx->io;
         ctx->k4_ldl = use_ldl ? 1 : 0;
         if (use_ldl) {
-            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * 2 * kStreamBins, ctx->stream));
+            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * 3 * kStreamBins, ctx->stream));
             for (int b = kStreamBins - 1; b >= 0; --b) {
                 if (!bin_count[b]) continue;
                 q.n_sys = bin_count[b];
@@ -687,6 +688,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                 q.fail_list = (int32_t*)(ws + o_fail) + bin_begin[b];
                 q.fail_count = (int32_t*)((char*)ctx->scalars + 256) + b;
                 q.refined_count = (int32_t*)((char*)ctx->scalars + 256) + kStreamBins + b;
+                q.queue = (int32_t*)((char*)ctx->scalars + 256) + 2 * kStreamBins + b;
                 if (use_ldl_env == 2)
                     rc = b == 0 ? band_ldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_ldl_launch<2>(ctx, q, Lf[b])
                        : b == 2 ? band_ldl_launch<3>(ctx, q, Lf[b]) : band_ldl_launch<4>(ctx, q, Lf[b]);

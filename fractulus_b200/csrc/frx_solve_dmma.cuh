@@ -88,6 +88,7 @@ struct BandParams {
     int32_t* fail_list;      // frx_k4_band_ldl: systems that turned out indefinite, appended at fail_list[atomicAdd(fail_count, 1)]
     int32_t* fail_count;
     int32_t* refined_count;  // frx_k4_band_bldl: indefinite systems accepted on their residual after iterative refinement (may be NULL)
+    int32_t* queue;          // frx_k4_band_bldl: work counter of this launch (zero at launch), see the kernel
 };
 
 // Back substitution in blocks of 8 rows, one warp.  xs[k] = transformed rhs on entry, the solution on exit;

@@ -499,7 +499,18 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         const double* rhs0 = p.rhs + (int64_t)p.order[blockIdx.x] * p.ldb;
         for (int e = lane; e < n; e += 32) cp_async8(bs + e, rhs0 + e);
     }
-    for (int64_t si = blockIdx.x; si < n_sys; si += gridDim.x) {
+    // Work distribution: the first system of a warp is its block index, every further one comes from the launch's counter.
+    // Systems differ in cost (an indefinite one takes ~1.7x a definite one), and with ~10 systems per warp a static
+    // assignment leaves the slowest warp ~25 % behind the mean.
+    int64_t si_next = blockIdx.x;
+    for (;;) {
+        const int64_t si = si_next;
+        if (si >= n_sys) break;
+        {
+            int nx = 0;
+            if (lane == 0) nx = atomicAdd(p.queue, 1);
+            si_next = (int64_t)gridDim.x + __shfl_sync(FULL, nx, 0);
+        }
         const int64_t s = p.order[si];
         const int res = (int)((p.wptr[s + 1] - p.wptr[s] - 1) / 2);
         const int nb_a = res + 1;
@@ -509,8 +520,8 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         double* xo = p.x + s * p.ldx;
         cp_async_wait_all();                                 // this system's right-hand side has landed in bs
         __syncwarp();
-        if (si + gridDim.x < n_sys) {
-            const double* rhs1 = p.rhs + (int64_t)p.order[si + gridDim.x] * p.ldb;
+        if (si_next < n_sys) {
+            const double* rhs1 = p.rhs + (int64_t)p.order[si_next] * p.ldb;
             for (int e = lane; e < n; e += 32) cp_async8(bs_next + e, rhs1 + e);
         }
         for (int e = lane; e < G::APAD; e += 32) apad[e] = 0.0;
