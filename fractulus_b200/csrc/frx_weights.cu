@@ -194,6 +194,88 @@ __global__ void __launch_bounds__(128) frx_k5b_riesz_half(int rule, int64_t n, i
     }
 }
 
+// 'caputo' and 'trapezoidal' weights are second differences of ONE power sequence, a - 2b + c with a, b, c = (d+1)^e, d^e,
+// (d-1)^e (equation.py:54,95); the first node adds p^e' with a second exponent (equation.py:49,90).  frx_k5c_riesz_shared gives
+// every node of the left half one lane that evaluates ONE correctly rounded pow() -- what the stencil kernels spend their
+// time on -- and takes the other operands from its neighbours by shuffle: the same pow() results in the same expressions,
+// so the same bits as frx_k5b_riesz_half with a third of the evaluations.  No lane may take a second pow() (a divergent call
+// would cost the whole warp another evaluation), so
+//   * every stencil gets one extra VIRTUAL position: [first node: p^e'] [virtual: p^e] [p-1] [p-2] ... [0];
+//   * warps overlap: a warp covers positions 29w - 1 .. 29w + 30 and writes the nodes of lanes 1..29 (the first node reads
+//     the lane two to its right, everyone else its two neighbours).
+struct frx_pow_lanes {
+    const frx_par* P;
+    double base0, q0, base1, q1, base2, q2;     // three (base, power) pairs for slot FRX_E_MAIN, plus ...
+    double basef, qf;                            // ... one for slot FRX_E_FIRST
+    __device__ double operator()(double base, int slot) const {
+        if (slot == FRX_E_MAIN) {
+            if (base == base0) return q0;
+            if (base == base1) return q1;
+            if (base == base2) return q2;
+        } else if (slot == FRX_E_FIRST && base == basef) {
+            return qf;
+        }
+        return frx_pow_cr(base, P->expo[slot]);     // (never taken for valid layouts)
+    }
+};
+
+__global__ void __launch_bounds__(128) frx_k5c_riesz_shared(int rule, int64_t n, int64_t total_virtual,
+                                                            const double* __restrict__ resolution,
+                                                            const int64_t* __restrict__ row_ptr,
+                                                            const frx_k5_scalars* __restrict__ scal,
+                                                            int32_t* __restrict__ offsets, double* __restrict__ weights) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t pos_raw = 29 * gw + lane - 1;
+    const bool valid = pos_raw >= 0 && pos_raw < total_virtual;
+    const int64_t pos = pos_raw < 0 ? 0 : (pos_raw >= total_virtual ? total_virtual - 1 : pos_raw);
+    int64_t lo = 0, hi = n;                   // vptr(lo) <= pos < vptr(hi), vptr(s) = (row_ptr[s] + s) / 2 + s
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((((row_ptr[mid] + mid) >> 1) + mid) <= pos) lo = mid; else hi = mid;
+    }
+    const int64_t s = lo, kv = pos - (((row_ptr[s] + s) >> 1) + s), base = row_ptr[s], count = row_ptr[s + 1] - base;
+    const frx_k5_scalars& S = scal[s];
+    const frx_par P = S.P;
+    const long long p = (long long)resolution[s];
+    // kv = 0: the first node (distance p, exponent e'), kv = 1: virtual (distance p, exponent e), kv >= 2: distance p - kv + 1
+    const bool is_first = kv == 0, is_virtual = kv == 1;
+    const double d = (double)(kv <= 1 ? p : p - kv + 1);
+    const double own = frx_pow_cr(d, P.expo[is_first ? FRX_E_FIRST : FRX_E_MAIN]);
+    const double q_m1 = __shfl_up_sync(FULL, own, 1), q_p1 = __shfl_down_sync(FULL, own, 1), q_p2 = __shfl_down_sync(FULL, own, 2);
+    if (!valid || is_virtual || lane < 1 || lane > 29) return;
+    frx_pow_lanes pw;
+    pw.P = &P;
+    double raw;
+    if (is_first) {                           // (p-1)^e from two lanes to the right, p^e' is this lane's
+        pw.base0 = d - 1.0; pw.q0 = q_p2;
+        pw.base1 = pw.base2 = -1.0; pw.q1 = pw.q2 = 0.0;
+        pw.basef = d; pw.qf = own;
+        raw = frx_raw_first_pw(P, d, pw);
+    } else {
+        pw.base0 = d; pw.q0 = own;
+        pw.base1 = d + 1.0; pw.q1 = q_m1;
+        pw.base2 = d - 1.0; pw.q2 = q_p1;
+        pw.basef = -1.0; pw.qf = 0.0;
+        raw = frx_raw_toeplitz_pw(P, d, false, pw);
+    }
+    // as frx_k5b_riesz_half for these rules: the left stencil is offsets -p .. 0, a node's mirror image is in it only for o = 0
+    const int64_t k = is_first ? 0 : kv - 1;
+    const long long o = -(long long)d;
+    const double Lo = FRX_MUL(S.mult, raw);
+    {
+        double acc = Lo;
+        if (o == 0) acc = FRX_ADD(acc, FRX_MUL(S.sgn, FRX_MUL(Lo, -1.0)));
+        weights[base + k] = FRX_MUL(S.K, acc);
+        if (offsets) offsets[base + k] = (int32_t)o;
+    }
+    if (o != 0) {
+        weights[base + (count - 1 - k)] = FRX_MUL(S.K, FRX_MUL(S.sgn, FRX_MUL(Lo, -1.0)));
+        if (offsets) offsets[base + (count - 1 - k)] = (int32_t)(-o);
+    }
+}
+
 // One Settings triple passed BY VALUE (the drop-in's create_*_stencil call): no parameter upload, one launch.  Every CTA
 // re-evaluates the scalars (a few microseconds) and then one node per thread -- the operations of k5a + k5b, same bits.
 __global__ void __launch_bounds__(128) frx_k5_single(int rule, int side, double alpha, double lf, double resolution,
@@ -258,6 +340,16 @@ int frx_launch_stencil_weights(frx_ctx* ctx, int rule, int side, int64_t n_setti
     FRX_LAUNCH(ctx, FRX_K_STENCIL,
                frx_k5a_settings_scalars<<<(unsigned)((n_settings + 127) / 128), 128, 0, ctx->stream>>>(
                    rule, n_settings, d_alpha, d_lf, d_resolution, (frx_k5_scalars*)d_scratch));
+    if (side == FRX_SIDE_RIESZ_CAPUTO && (rule == FRX_RULE_CAPUTO || rule == FRX_RULE_TRAPEZOIDAL)) {
+        // one pow() per node, operands shared between neighbouring lanes (29 nodes per warp)
+        const int64_t total_virtual = (total + n_settings) / 2 + n_settings;
+        const int64_t warps = (total_virtual + 28) / 29;
+        FRX_LAUNCH(ctx, FRX_K_STENCIL,
+                   frx_k5c_riesz_shared<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+                       rule, n_settings, total_virtual, d_resolution, d_row_ptr, (const frx_k5_scalars*)d_scratch, d_offsets,
+                       d_weights));
+        return FRX_OK;
+    }
     if (side == FRX_SIDE_RIESZ_CAPUTO) {
         const int64_t total_half = (total + n_settings) / 2;
         FRX_LAUNCH(ctx, FRX_K_STENCIL,
