@@ -724,7 +724,7 @@ def sub_cfg4(env, n, steps=5):
            'indefinite_systems': {'accepted_on_residual_after_refinement': int(sum(refined_bins)), 'solved_by_pivoted_lu': n_piv,
                                   'of': n_stat, 'refined_per_band_width_bin': refined_bins, 'pivoted_per_band_width_bin': piv_bins,
                                   'note': 'a pivot of the wrong sign in the pivot-free block LDL^T marks a system indefinite: it is kept '
-                                          'only if ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) after <= 2 refinement steps, else the '
+                                          'only if ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) after <= 6 refinement steps, else the '
                                           'partially pivoted band LU solves it again'},
            'roofline': {'kernel': 'frx_k4_band_bldl (every system) + frx_k4_band_dmma (indefinite systems), four band-width bins each',
                         'bound': 'fp64', 'achieved': achieved,

@@ -7,7 +7,7 @@
 // elimination without row interchanges is unconditionally backward stable (it is the Cholesky / LDL^T factorisation), and
 // definiteness shows in the factorisation itself (Sylvester: the matrix is definite iff every pivot has the sign of the
 // first).  So every system is first tried here.  A pivot of the wrong sign marks the system indefinite: the first form
-// gives up at once, the shipped form keeps the solution only if its residual passes after at most two steps of iterative
+// gives up at once, the shipped form keeps the solution only if its residual passes after at most six steps of iterative
 // refinement.  What is rejected is appended to the launch's fail list, which the pivoted kernels of frx_solve_dmma.cuh then
 // work through (device-side count, no host round trip).  Like LAPACK's dpbtrf(uplo='L') the routines read ONE triangle:
 // the lower band a_m = A[i+m][i], m = 0..nb, mirrored where a diagonal tile needs its upper part.
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(32) frx_k4_band_ldl(const BandParams p) {
 //   * right-hand side as replicated 8-vectors: b(t) += (-L21(t)) z (two FMAs and two xor-shuffles per tile);
 //   * back substitution x_p = Dinv z_p - sum_t L21(t)^T x_{p+t}: two FMAs per tile on the stored fragments and ONE
 //     reduction over the row index (three xor-shuffles of two doubles) -- no triangular solve, no dependent chain.
-//   * an INDEFINITE system (a pivot of the wrong sign) is kept only on its residual: up to two steps of iterative
+//   * an INDEFINITE system (a pivot of the wrong sign) is kept only on its residual: up to six steps of iterative
 //     refinement with the same factors (residual with one lane per row from the coefficient vector, forward substitution
 //     with the stored -L21 fragments, the same back substitution accumulating into x), each followed by the test
 //     ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) in max norms; what fails goes to the fail list.
@@ -371,6 +371,11 @@ __device__ __forceinline__ double pivot_reciprocal(const double p) {
     r = fma(r, fma(-p, r, 1.0), r);
     return r;
 }
+
+// Iterative refinement of an indefinite system: at most this many steps (each ~1/3 of a factorisation; the pivoted LU that
+// takes over otherwise costs ~4 factorisations and runs at half the occupancy).  On the cfg-4 matrices every indefinite
+// system of n <= 128 passes after one step; at n = 256 two steps accept 67 %, six 91 % (tools/proto_band_bldl.py).
+constexpr int kBldlRefineSteps = 6;
 
 // NaN-propagating maximum (fmax would drop a NaN: a broken factorisation must not pass the acceptance test)
 __device__ __forceinline__ double nanmax(const double m, const double v) { return (v > m || v != v) ? v : m; }
@@ -637,14 +642,15 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         bldl_backward<T>(lane, n_panels, U, xs, false);
         __syncwarp();
         // A definite matrix (every pivot of the sign of the first) needs nothing else: elimination without interchanges is
-        // backward stable for it.  An indefinite one is ACCEPTED ONLY ON ITS RESIDUAL: up to two steps of iterative refinement
+        // backward stable for it.  An indefinite one is ACCEPTED ONLY ON ITS RESIDUAL: up to kBldlRefineSteps steps of iterative refinement
         // with the same factors, each followed by the test  ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||)  (max norms; NaN fails).
         const bool indef = n_bad != 0;
         bool ok = !indef;
         if (indef) {
             amax = warp_nanmax(amax);
+            double r_prev = 1e300;
 #pragma unroll 1
-            for (int it = 0; it < 3 && !ok; ++it) {
+            for (int it = 0; it <= kBldlRefineSteps && !ok; ++it) {
                 double rmax = 0.0, xmax = 0.0, bmax = 0.0;
                 for (int i = lane; i < G::rs_doubles(n); i += 32) {
                     double acc = 0.0;
@@ -663,7 +669,9 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
                 xmax = warp_nanmax(xmax);
                 bmax = warp_nanmax(bmax);
                 ok = rmax <= 16.0 * 2.220446049250313e-16 * fma(amax, xmax, bmax);
-                if (ok || it == 2) break;
+                // give up when the budget is spent or the residual no longer halves (NaN included): the pivoted LU takes over
+                if (ok || it == kBldlRefineSteps || !(rmax <= 0.5 * r_prev)) break;
+                r_prev = rmax;
                 __syncwarp();
                 bldl_forward<T>(lane, n_panels, U, rs);
                 __syncwarp();

@@ -223,7 +223,7 @@ int frx_assemble_solve_host(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, co
                             const double* h_res, const double* h_rhs, int64_t ldb, double* h_x, int64_t ldx);
 /* After frx_assemble_solve: what the last call on this context did with its systems.  Every system is first factorised
  * WITHOUT pivoting (block LDL^T): a DEFINITE matrix (every pivot of the sign of the first) ends there -- elimination without
- * interchanges is backward stable for it; an INDEFINITE one is accepted only on its residual, after at most two steps of
+ * interchanges is backward stable for it; an INDEFINITE one is accepted only on its residual, after at most six steps of
  * iterative refinement with the same factors:  ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||)  in max norms -- refined_per_bin
  * counts those; what fails that test is solved again by the partially pivoted band LU -- n_pivoted / pivoted_per_bin count
  * those.  Bins: band width res + 1 <= 7, 15, 23, 31; the per-bin arrays may be NULL and hold -1 when the attempt did not

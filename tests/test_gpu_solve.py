@@ -46,7 +46,7 @@ def test_solve_vs_numpy_on_oracle_matrix(n):
 def test_definite_systems_end_in_the_pivot_free_attempt_indefinite_ones_only_on_their_residual(n):
     """Every system is first factorised by the block LDL^T without pivoting (csrc/frx_solve_ldl.cuh).  A definite matrix ends
     there; a pivot of the wrong sign marks the system INDEFINITE: it is kept only if its residual passes
-    ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) after at most two refinement steps, otherwise the partially pivoted band LU
+    ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) after at most six refinement steps, otherwise the partially pivoted band LU
     solves it again.  refined + pivoted must be the number of indefinite matrices (eigenvalues of the kernel's own dense
     assembly), and every path must leave LAPACK-quality residuals and errors; n runs over sizes that are not multiples of
     the panel width."""
