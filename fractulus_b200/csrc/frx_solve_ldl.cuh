@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(32) frx_k4_band_ldl(const BandParams p) {
 //     holds rows 2cp / 2cp+1 of the right factor, and Dinv is symmetric: its own fragment); the result is again a C fragment;
 //   * trailing update C(i,j) += (-L21(i)) A21(j)^T: A = the fragment just computed, B = the fragment of A21(j): two DMMAs,
 //     accumulating in the registers of tile (i+1, j+1), which become tile (i, j) of the next panel; tiles entering the band
-//     are T + 1 constant Toeplitz fragments kept in registers (masked at the end of the matrix: identity padding);
+//     are T + 1 constant Toeplitz fragments kept in registers (masked at the end of the matrix: the system is padded with
+//     +-identity rows, of the sign of a_0, up to a multiple of 8);
 //   * right-hand side as replicated 8-vectors: b(t) += (-L21(t)) z (two FMAs and two xor-shuffles per tile);
 //   * back substitution x_p = Dinv z_p - sum_t L21(t)^T x_{p+t}: two FMAs per tile on the stored fragments and ONE
 //     reduction over the row index (three xor-shuffles of two doubles) -- no triangular solve, no dependent chain.
@@ -338,7 +339,8 @@ __global__ void __launch_bounds__(32) frx_k4_band_ldl(const BandParams p) {
 //     refinement with the same factors (residual with one lane per row from the coefficient vector, forward substitution
 //     with the stored -L21 fragments, the same back substitution accumulating into x), each followed by the test
 //     ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) in max norms; what fails goes to the fail list.
-// Shared memory: the coefficient vector, x and the residual.  ~100 shuffles per panel, 2T + T(T+1) DMMAs.  The explicit
+// Shared memory: the coefficient vector, x, the residual and two right-hand-side buffers (the next system's rhs arrives by
+// cp.async while this one is solved).  ~100 shuffles per panel, 2T + T(T+1) DMMAs.  The explicit
 // inverse of the 8 x 8 tile leaves residuals of 1e-15 on the operator's definite matrices (tools/proto_band_bldl.py checks
 // that on oracle coefficients together with the index bookkeeping).
 template <int T_>
@@ -374,7 +376,7 @@ __device__ __forceinline__ double pivot_reciprocal(const double p) {
 
 // Iterative refinement of an indefinite system: at most this many steps (each ~1/3 of a factorisation; the pivoted LU that
 // takes over otherwise costs ~4 factorisations and runs at half the occupancy).  On the cfg-4 matrices every indefinite
-// system of n <= 128 passes after one step; at n = 256 two steps accept 67 %, six 91 % (tools/proto_band_bldl.py).
+// system of n <= 128 passes after one step; at n = 256 two steps accept 67 %, six 89 % (tools/proto_band_bldl.py --refine).
 constexpr int kBldlRefineSteps = 6;
 
 // NaN-propagating maximum (fmax would drop a NaN: a broken factorisation must not pass the acceptance test)

@@ -151,5 +151,79 @@ def main():
     print('real operator: %d definite systems, worst residual %.2e at %s, worst err/cond %.2e at %s' % (cnt, worst[0], worst[1], worst_err[0], worst_err[1]))
 
 
+def refinement_statistics():
+    """How many refinement steps the INDEFINITE cfg-4 matrices need when they are factorised without pivoting (no sign test)
+    and accepted on  ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||):  the numbers behind kBldlRefineSteps in
+    csrc/frx_solve_ldl.cuh."""
+    import collections
+    from oracle import clib
+    global gj_inverse
+    checked = gj_inverse
+
+    def gj_no_sign_test(M, sgn, n_valid):
+        M = M.copy()
+        for c in range(8):
+            p = M[c, c]
+            if p == 0:
+                return None, False
+            r = 1.0 / p
+            f = M[:, c].copy()
+            prow = M[c, :] * r
+            new = M - np.outer(f, prow)
+            new[c, :] = prow
+            new[:, c] = -f * r
+            new[c, c] = r
+            M = new
+        return M, True
+
+    gj_inverse = gj_no_sign_test
+    eps = np.finfo(float).eps
+    try:
+        for n in (128, 256):
+            stats, tot = collections.Counter(), 0
+            h = 1.0 / (n + 1)
+            for alpha in np.linspace(0.05, 0.95, 37):
+                for res in range(1, 31):
+                    first, w = clib.riesz_caputo_arrays('caputo', (alpha, res * h, res))
+                    rcp = np.zeros(2 * res + 5)
+                    rcp[2:-2] = w
+                    k = np.arange(0, res + 2)
+                    a = (rcp[k + res + 2 - 1] - 2 * rcp[k + res + 2] + rcp[k + res + 2 + 1]) / h ** 2
+                    nb = min(res + 1, n - 1)
+                    a = a[:nb + 1]
+                    T = 1 if nb <= 7 else 2 if nb <= 15 else 3 if nb <= 23 else 4
+                    A = toeplitz(a, n)
+                    ev = np.linalg.eigvalsh(A)
+                    if ev.min() > 0 or ev.max() < 0:
+                        continue
+                    tot += 1
+                    b = np.sin(np.pi * np.arange(1, n + 1) * h)
+                    with np.errstate(all='ignore'):
+                        x, ok = solve_bldl(a, n, nb, T, b)
+                        if not ok or not np.isfinite(x).all():
+                            stats['never'] += 1
+                            continue
+                        amax, done = np.abs(a).max(), False
+                        for it in range(9):
+                            r = b - A @ x
+                            if np.abs(r).max() <= 16 * eps * (amax * np.abs(x).max() + np.abs(b).max()):
+                                stats[it] += 1
+                                done = True
+                                break
+                            d, ok = solve_bldl(a, n, nb, T, r)
+                            if not ok or not np.isfinite(d).all():
+                                break
+                            x = x + d
+                        if not done:
+                            stats['never'] += 1
+            print('n = %d: %d indefinite matrices, accepted after k refinement steps: %s'
+                  % (n, tot, sorted(stats.items(), key=lambda kv: str(kv[0]))))
+    finally:
+        gj_inverse = checked
+
+
 if __name__ == '__main__':
-    main()
+    if '--refine' in sys.argv:
+        refinement_statistics()
+    else:
+        main()
