@@ -364,14 +364,18 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// 1 / p for the pivots: MUFU seed (2^-23) and two Newton steps, no special-case branch.  p = 0, denormal, Inf or NaN give
+// 1 / p for the pivots: MUFU seed (upper 20 mantissa bits) and ONE third-order step (three DFMAs), no special-case branch.  p = 0, denormal, Inf or NaN give
 // Inf / NaN -- such a pivot has already failed the sign test (p * sgn > 1e-300), and the residual test rejects what follows.
 __device__ __forceinline__ double pivot_reciprocal(const double p) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
-    r = fma(r, fma(-p, r, 1.0), r);
-    r = fma(r, fma(-p, r, 1.0), r);
-    return r;
+    const double e = fma(-p, r, 1.0);            // |e| <= 2^-20: r (1 + e + e^2) is 1 / p to e^3 < 2^-60
+    return fma(r, fma(e, e, e), r);
+}
+
+// -v by flipping the sign bit of the high word (an integer instruction: the compiler's own negation is a DADD)
+__device__ __forceinline__ double flip_sign(const double v) {
+    return __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v));
 }
 
 // Iterative refinement of an indefinite system: at most this many steps (each ~1/3 of a factorisation; the pivoted LU that
@@ -563,35 +567,61 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
             bv[i] = bs[8 * i + g];
         }
         double b_in = bs[8 * T + g];                         // the block row that enters with panel 0
-        int n_bad = 0;                                       // pivots that are not of the sign of a_0 (warp-uniform)
+        // high word of the smallest pivot times sgn(a_0) so far (warp-uniform); a NaN pivot makes every later entry NaN and
+        // is caught on the last -Dinv below
+        int piv_min = 0x7ff00000;
+        bool nan_seen = false;
+        const int sgn_bit = apad[OFF] < 0.0 ? (int)0x80000000 : 0;
 #pragma unroll 1
         for (int pnl = 0; pnl < n_panels; ++pnl) {
             const int k0 = pnl * 8;
             const bool edge = k0 + 8 * T + 8 > n;
             const double b_cur = b_in;
             b_in = bs[k0 + 8 * T + 8 + g];                                     // one panel ahead
-            // ---- Gauss-Jordan inverse of the diagonal tile, in place in its fragment ----------------------------------
+            // ---- minus the inverse of the diagonal tile, in place in its fragment ------------------------------------------
+            // Eight SWEEPS, sweep(c): p = M[c][c];  M[i][j] -= M[i][c] M[c][j] / p;  M[i][c] = M[c][i] = M[i][c] / p;
+            // M[c][c] = -1 / p.  The tile stays symmetric through all eight; after them it is -Dinv.
             double2 M = S[0][0];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int hc = c >> 1;
                 const double own = (c & 1) ? M.y : M.x;
-                const double f = __shfl_sync(FULL, own, (lane & ~3) | hc);      // M[g][c]
-                const double prx = __shfl_sync(FULL, M.x, c * 4 + cp);         // M[c][2cp]
-                const double pry = __shfl_sync(FULL, M.y, c * 4 + cp);         // M[c][2cp+1]
                 const double pv = __shfl_sync(FULL, own, c * 4 + hc);          // M[c][c]
-                n_bad += !(pv * sgn > 1e-300);
-                const double r = pivot_reciprocal(pv);
-                const double px = prx * r, py = pry * r, nfr = -f * r;
+                // smallest pivot seen, as the high word of p * sgn(a_0) (integer order = order of the doubles there;
+                // a pivot of the other sign has the sign bit set and is negative as an integer)
+                piv_min = min(piv_min, __double2hiint(pv) ^ sgn_bit);
                 const bool rowc = g == c, atc = cp == hc;
-                double nx = rowc ? px : fma(-f, px, M.x);
-                double ny = rowc ? py : fma(-f, py, M.y);
-                if (atc && !(c & 1)) nx = rowc ? r : nfr;
-                if (atc && (c & 1)) ny = rowc ? r : nfr;
-                M.x = nx;
-                M.y = ny;
+                double dx = M.x, dy = M.y;
+                if (T == 1) {
+                    // narrow bands are bound by instruction issue: the rank-1 update as ONE DMMA whose operands are already
+                    // in this lane (A = the fragment component that holds column c, k = 2cp + (c & 1);  B = -M[n][c] / p in
+                    // the four lanes (n, c / 2) that own column c, zero elsewhere) -- one shuffle per sweep instead of four.
+                    // Row and column c, which the DMMA leaves at ~0, are the lane's own old entries times 1 / p.
+                    const double r = pivot_reciprocal(pv);
+                    const double sx = M.x * r, sy = M.y * r;
+                    const double so = (c & 1) ? sy : sx;                       // M[g][c] / p
+                    dmma884(dx, dy, own, atc ? flip_sign(so) : 0.0);
+                    if (rowc) { dx = sx; dy = sy; }
+                    if (atc && !(c & 1)) dx = rowc ? flip_sign(r) : so;
+                    if (atc && (c & 1)) dy = rowc ? flip_sign(r) : so;
+                } else {
+                    // wider bands are bound by the latency of this chain, and a DMMA in it is slower than shuffles + DFMAs
+                    // (measured: 1.45 -> 1.85 ms per 1e5 systems at nb <= 15)
+                    const double f = __shfl_sync(FULL, own, (lane & ~3) | hc);  // M[g][c]
+                    const double prx = __shfl_sync(FULL, M.x, c * 4 + cp);     // M[c][2cp]
+                    const double pry = __shfl_sync(FULL, M.y, c * 4 + cp);     // M[c][2cp+1]
+                    const double r = pivot_reciprocal(pv);
+                    const double px = prx * r, py = pry * r, fr = f * r;
+                    dx = rowc ? px : fma(-f, px, dx);
+                    dy = rowc ? py : fma(-f, py, dy);
+                    if (atc && !(c & 1)) dx = rowc ? flip_sign(r) : fr;
+                    if (atc && (c & 1)) dy = rowc ? flip_sign(r) : fr;
+                }
+                M.x = dx;
+                M.y = dy;
             }
-            const double2 nD = make_double2(-M.x, -M.y);                       // -Dinv (symmetric)
+            const double2 nD = M;                                              // -Dinv (symmetric)
+            nan_seen |= nD.x != nD.x;
             // ---- -L21(t) = A21(t) (-Dinv) -----------------------------------------------------------------------------
             double2 A21[T + 1], Xn[T + 1];
 #pragma unroll
@@ -646,7 +676,8 @@ __global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const
         // A definite matrix (every pivot of the sign of the first) needs nothing else: elimination without interchanges is
         // backward stable for it.  An indefinite one is ACCEPTED ONLY ON ITS RESIDUAL: up to kBldlRefineSteps steps of iterative refinement
         // with the same factors, each followed by the test  ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||)  (max norms; NaN fails).
-        const bool indef = n_bad != 0;
+        // every pivot p * sgn(a_0) > 1e-300 (0x01a56e1f = high word of 1e-300), none of them NaN
+        const bool indef = piv_min <= 0x01a56e1f || __any_sync(FULL, nan_seen);
         bool ok = !indef;
         if (indef) {
             amax = warp_nanmax(amax);
