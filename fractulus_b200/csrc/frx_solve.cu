@@ -30,6 +30,7 @@
 #include "frx_rules.cuh"
 #include "frx_solve_dmma.cuh"
 #include "frx_solve_ldl.cuh"
+#include "frx_solve_scalar.cuh"
 
 namespace {
 
@@ -478,6 +479,28 @@ static int band_bldl_geometry(frx_ctx* ctx, int n, int64_t count, int nb_bin, Bi
     return FRX_OK;
 }
 
+// one thread per system (nb <= 7): a few single-warp CTAs per SM, each with one scratch slab that stays in L2
+static int band_scalar_geometry(frx_ctx* ctx, int n, int64_t count, BinLaunch* out) {
+    using G = frx_k4::ScalarGeo;
+    out->dyn = 0;
+    // Single-warp CTAs per SM (FRX_K4_SCALAR_WARPS).  Each keeps one slab of n * 2 KB.  Few warps keep the slabs in L2 but
+    // leave every dependent chain exposed; measured per 1e5 systems with 1 / 2 / 4 / 8 / 12 warps per SM
+    // (gpurun_out/k4_scalar_sweep.txt): n = 64: 466 / 246 / 158 / 144 / 145 us, n = 128: 875 / 472 / 364 / 311 / 304 us,
+    // n = 256: 1791 / 1122 / 757 / 633 / 613 us -- from 8 warps on the kernel runs at the HBM rate of its slab traffic
+    // (n = 128: 1.6 GB at 5.2 TB/s).
+    static const int per_sm_env = getenv("FRX_K4_SCALAR_WARPS") ? atoi(getenv("FRX_K4_SCALAR_WARPS")) : 0;
+    const int per_sm = per_sm_env > 0 ? per_sm_env : 8;
+    out->grid = (int64_t)ctx->sm_count * per_sm;
+    if (out->grid > (count + 31) / 32) out->grid = (count + 31) / 32;
+    out->scratch = sizeof(double) * (size_t)out->grid * (size_t)G::ustride(n);
+    return FRX_OK;
+}
+
+static int band_scalar_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
+    FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_scalar<<<(unsigned)L.grid, 32, 0, ctx->stream>>>(q));
+    return FRX_OK;
+}
+
 template <int T>
 static int band_bldl_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const BinLaunch& L) {
     FRX_LAUNCH(ctx, FRX_K_SOLVE, frx_k4::frx_k4_band_bldl<T><<<(unsigned)L.grid, 32, L.dyn, ctx->stream>>>(q));
@@ -576,6 +599,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     extern size_t frx_k5_scratch_bytes(int64_t);
     const size_t o_k5 = carve(frx_k5_scratch_bytes(n_sys));
     const size_t o_fail = carve(sizeof(int32_t) * (size_t)n_sys);       // fail lists of the pivot-free attempt, bin by bin
+    const size_t o_retry = carve(sizeof(int32_t) * (size_t)(bin_count[0] + 1));   // what frx_k4_band_scalar hands to the block LDL^T
     rc = frx_ws_reserve(ctx, off);
     if (rc) return rc;
     char* ws = (char*)ctx->ws;
@@ -602,6 +626,10 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     // (frx_k4_band_ldl, scalar pivots, tiles in shared memory); 0 = pivoted kernels for everything
     static const int use_ldl_env = getenv("FRX_K4_LDL") ? atoi(getenv("FRX_K4_LDL")) : 1;
     const bool use_ldl = use_ldl_env && variant == 0 && dmma_bins == 0xF && two_warp_bins == 0;
+    // FRX_K4_SCALAR: 1 (default) = the narrowest bin (nb <= 7) is first tried with one THREAD per system
+    // (frx_k4_band_scalar: definite systems end there), the block LDL^T works through what that rejects; 0 = off
+    static const int use_scalar_env = getenv("FRX_K4_SCALAR") ? atoi(getenv("FRX_K4_SCALAR")) : 1;
+    const bool use_scalar = use_ldl && use_ldl_env == 1 && use_scalar_env && bin_count[0] > 0;
     if (!d_dense && variant != 1 && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
         frx_k4::BandParams q;
         q.n = n;
@@ -618,8 +646,14 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.fail_count = nullptr;
         q.refined_count = nullptr;
         q.queue = nullptr;
-        BinLaunch L[kStreamBins], Lf[kStreamBins];
+        BinLaunch L[kStreamBins], Lf[kStreamBins], Ls;
         size_t scratch = 0;
+        Ls.grid = 0;
+        if (use_scalar) {
+            rc = band_scalar_geometry(ctx, n, bin_count[0], &Ls);
+            if (rc) return rc;
+            scratch = Ls.scratch;
+        }
         for (int b = 0; b < kStreamBins; ++b) {
             L[b].grid = 0;
             Lf[b].grid = 0;
@@ -673,7 +707,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         q.uscratch = (double*)ctx->io;
         ctx->k4_ldl = use_ldl ? 1 : 0;
         if (use_ldl) {
-            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * 3 * kStreamBins, ctx->stream));
+            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * (3 * kStreamBins + 1), ctx->stream));
             for (int b = kStreamBins - 1; b >= 0; --b) {
                 if (!bin_count[b]) continue;
                 q.n_sys = bin_count[b];
@@ -689,6 +723,17 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                 q.fail_count = (int32_t*)((char*)ctx->scalars + 256) + b;
                 q.refined_count = (int32_t*)((char*)ctx->scalars + 256) + kStreamBins + b;
                 q.queue = (int32_t*)((char*)ctx->scalars + 256) + 2 * kStreamBins + b;
+                if (b == 0 && use_scalar) {
+                    // one thread per system first; the block LDL^T then takes the retry list (counted on the device)
+                    frx_k4::BandParams qs = q;
+                    qs.ustride_cta = frx_k4::ScalarGeo::ustride(n);
+                    qs.fail_list = (int32_t*)(ws + o_retry);
+                    qs.fail_count = (int32_t*)((char*)ctx->scalars + 256) + 3 * kStreamBins;
+                    rc = band_scalar_launch(ctx, qs, Ls);
+                    if (rc) return rc;
+                    q.order = qs.fail_list;
+                    q.n_sys_dev = qs.fail_count;
+                }
                 if (use_ldl_env == 2)
                     rc = b == 0 ? band_ldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_ldl_launch<2>(ctx, q, Lf[b])
                        : b == 2 ? band_ldl_launch<3>(ctx, q, Lf[b]) : band_ldl_launch<4>(ctx, q, Lf[b]);
@@ -700,6 +745,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             q.fail_list = nullptr;
             q.fail_count = nullptr;
             q.refined_count = nullptr;
+            q.n_sys_dev = nullptr;
         }
         for (int b = kStreamBins - 1; b >= 0; --b) {    // widest bands first: the longest-running CTAs start first
             if (!bin_count[b]) continue;

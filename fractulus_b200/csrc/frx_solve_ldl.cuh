@@ -487,8 +487,27 @@ __device__ __forceinline__ void bldl_backward(const int lane, const int n_panels
     }
 }
 
+// Resident warps per SM the register allocation is capped for (one warp per CTA), per T = ceil(nb / 8).  Measured per
+// 1e5 systems of n = 128 (tools/time_k4.py): T = 1 at 20 / 24 / 32 warps 1.025 / 0.989 / 0.968 ms, T = 2 at 16 / 20 / 24 warps
+// 1.406 / 1.337 / 1.375 ms, T = 3 at 16 / 20 / 24 warps 1.600 / 1.619 / 1.755 ms, T = 4 at 12 / 16 / 20 warps 2.041 / 1.922 / 2.300 ms.
+#ifndef FRX_BLDL_OCC_T1
+#define FRX_BLDL_OCC_T1 32
+#endif
+#ifndef FRX_BLDL_OCC_T2
+#define FRX_BLDL_OCC_T2 20
+#endif
+#ifndef FRX_BLDL_OCC_T3
+#define FRX_BLDL_OCC_T3 16
+#endif
+#ifndef FRX_BLDL_OCC_T4
+#define FRX_BLDL_OCC_T4 16
+#endif
+constexpr int bldl_warps_per_sm(const int T) {
+    return T == 1 ? FRX_BLDL_OCC_T1 : T == 2 ? FRX_BLDL_OCC_T2 : T == 3 ? FRX_BLDL_OCC_T3 : FRX_BLDL_OCC_T4;
+}
+
 template <int T>
-__global__ void __launch_bounds__(32, (T >= 2 ? 16 : 20)) frx_k4_band_bldl(const BandParams p) {
+__global__ void __launch_bounds__(32, bldl_warps_per_sm(T)) frx_k4_band_bldl(const BandParams p) {
     using G = BldlGeo<T>;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int OFF = G::OFF;
