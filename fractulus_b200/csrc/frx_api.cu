@@ -73,6 +73,11 @@ extern "C" int frx_ctx_destroy(frx_ctx* ctx) {
     if (ctx->hstage) cudaFreeHost(ctx->hstage);
     if (ctx->hstage_ev) cudaEventDestroy(ctx->hstage_ev);
     if (ctx->switch_ev) cudaEventDestroy(ctx->switch_ev);
+    if (ctx->bin_fork) cudaEventDestroy(ctx->bin_fork);
+    for (int b = 0; b < 4; ++b) {
+        if (ctx->bin_join[b]) cudaEventDestroy(ctx->bin_join[b]);
+        if (ctx->bin_stream[b]) cudaStreamDestroy(ctx->bin_stream[b]);
+    }
     for (int i = 0; i < FRX_EV_POOL; ++i) {
         if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
         if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
@@ -179,6 +184,16 @@ extern "C" int frx_solve_stats(frx_ctx* ctx, int64_t* n_systems, int64_t* n_pivo
         if (pivoted_per_bin) pivoted_per_bin[b] = cnt[b];
         if (refined_per_bin) refined_per_bin[b] = cnt[4 + b];
     }
+    return FRX_OK;
+}
+
+int frx_bin_streams(frx_ctx* ctx) {
+    if (ctx->bin_fork) return FRX_OK;
+    for (int b = 0; b < 4; ++b) {
+        FRX_CUDA(cudaStreamCreateWithFlags(&ctx->bin_stream[b], cudaStreamNonBlocking));
+        FRX_CUDA(cudaEventCreateWithFlags(&ctx->bin_join[b], cudaEventDisableTiming));
+    }
+    FRX_CUDA(cudaEventCreateWithFlags(&ctx->bin_fork, cudaEventDisableTiming));
     return FRX_OK;
 }
 

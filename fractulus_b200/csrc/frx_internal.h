@@ -29,6 +29,9 @@ struct frx_ctx {
     int hstage_pending;
     // cross-stream ordering: everything this context has queued is ordered before work on a newly set stream
     cudaEvent_t switch_ev;
+    // K4: one stream per band-width bin, forked from / joined to `stream` inside frx_assemble_solve (frx_bin_streams)
+    cudaStream_t bin_stream[4];
+    cudaEvent_t bin_fork, bin_join[4];
     // optional per-kernel CUDA-event timing (frx_ctx_set_timing): bench.py's roofline numbers
     int timing;
     int ev_n;
@@ -38,6 +41,8 @@ struct frx_ctx {
     int64_t k_calls[FRX_K_COUNT];
 };
 
+// creates the bin streams and their events on first use
+int frx_bin_streams(frx_ctx* ctx);
 // a kernel launch bracketed by events when timing is on; counts the launch either way
 int frx_timing_begin(frx_ctx* ctx, int kid);
 int frx_timing_end(frx_ctx* ctx);

@@ -521,7 +521,7 @@ static int band_dmma_launch(frx_ctx* ctx, const frx_k4::BandParams& q, const Bin
 
 static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
                         const double* h_res, const double* d_rhs, int64_t ldb, double* d_x, int64_t ldx, int32_t* d_info,
-                        double* d_dense) {
+                        double* d_dense, bool host_io = false) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
     FRX_REQUIRE(n_sys >= 0 && n_sys < ((int64_t)1 << 31) && n >= 1 && n <= 4096, FRX_ERR_INVALID_ARG, "bad n_sys / n");
     if (n_sys == 0) return FRX_OK;
@@ -629,7 +629,10 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     // FRX_K4_SCALAR: 1 (default) = the narrowest bin (nb <= 7) is first tried with one THREAD per system
     // (frx_k4_band_scalar: definite systems end there), the block LDL^T works through what that rejects; 0 = off
     static const int use_scalar_env = getenv("FRX_K4_SCALAR") ? atoi(getenv("FRX_K4_SCALAR")) : 1;
-    const bool use_scalar = use_ldl && use_ldl_env == 1 && use_scalar_env && bin_count[0] > 0;
+    // (not when the kernels read and write page-locked HOST buffers in place, unless FRX_K4_SCALAR=2: a group of 32 systems
+    // reads all its right-hand sides before it writes any solution, and with ~1 group per warp the two directions of the
+    // PCIe link are used one after the other: measured 4.38 against 4.15 ms end to end per 1e5 systems of n = 128)
+    const bool use_scalar = use_ldl && use_ldl_env == 1 && use_scalar_env && bin_count[0] > 0 && (!host_io || use_scalar_env == 2);
     if (!d_dense && variant != 1 && max_res + 1 <= kStreamMaxNb && n <= kStreamMaxN) {
         frx_k4::BandParams q;
         q.n = n;
@@ -702,56 +705,74 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             }
             if (L[b].scratch > scratch) scratch = L[b].scratch;
         }
-        rc = frx_io_reserve(ctx, scratch);     // U rows of the resident systems (L2-resident: each warp reuses its slab)
+        // FRX_K4_CONCURRENT: 1 (default) = the chains of the four band-width bins (thread-per-system kernel -> block LDL^T ->
+        // pivoted LU on the fail list) run on four streams of the context, forked from and joined to its own stream: the
+        // bins share nothing but read-only inputs, and the tail of one launch (a few resident CTAs finishing their last
+        // system, or a pivoted kernel with a handful of systems) is filled with the CTAs of the next; 0 = one stream
+        static const int conc_env = getenv("FRX_K4_CONCURRENT") ? atoi(getenv("FRX_K4_CONCURRENT")) : 1;
+        const bool concurrent = use_ldl && conc_env != 0;
+        size_t bin_scratch[kStreamBins] = {0, 0, 0, 0}, bin_off[kStreamBins] = {0, 0, 0, 0}, io_total = scratch;
+        if (concurrent) {                      // every bin its own region of the scratch
+            io_total = 0;
+            for (int b = 0; b < kStreamBins; ++b) {
+                if (!bin_count[b]) continue;
+                bin_scratch[b] = Lf[b].scratch > L[b].scratch ? Lf[b].scratch : L[b].scratch;
+                if (b == 0 && use_scalar && Ls.scratch > bin_scratch[b]) bin_scratch[b] = Ls.scratch;
+                bin_off[b] = io_total;
+                io_total += frx_align_up(bin_scratch[b], 256);
+            }
+        }
+        rc = frx_io_reserve(ctx, io_total);    // factor scratch of the resident systems (each warp reuses its slab)
         if (rc) return rc;
         q.uscratch = (double*)ctx->io;
         ctx->k4_ldl = use_ldl ? 1 : 0;
-        if (use_ldl) {
-            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * (3 * kStreamBins + 1), ctx->stream));
-            for (int b = kStreamBins - 1; b >= 0; --b) {
-                if (!bin_count[b]) continue;
-                q.n_sys = bin_count[b];
-                q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
-                q.nb_max = bin_nb[b];
-                if (use_ldl_env == 2)
-                    q.ustride_cta = b == 0 ? frx_k4::LdlGeo<1>::ustride(n) : b == 1 ? frx_k4::LdlGeo<2>::ustride(n)
-                                  : b == 2 ? frx_k4::LdlGeo<3>::ustride(n) : frx_k4::LdlGeo<4>::ustride(n);
-                else
-                    q.ustride_cta = b == 0 ? frx_k4::BldlGeo<1>::ustride(n) : b == 1 ? frx_k4::BldlGeo<2>::ustride(n)
-                                  : b == 2 ? frx_k4::BldlGeo<3>::ustride(n) : frx_k4::BldlGeo<4>::ustride(n);
-                q.fail_list = (int32_t*)(ws + o_fail) + bin_begin[b];
-                q.fail_count = (int32_t*)((char*)ctx->scalars + 256) + b;
-                q.refined_count = (int32_t*)((char*)ctx->scalars + 256) + kStreamBins + b;
-                q.queue = (int32_t*)((char*)ctx->scalars + 256) + 2 * kStreamBins + b;
-                if (b == 0 && use_scalar) {
-                    // one thread per system first; the block LDL^T then takes the retry list (counted on the device)
-                    frx_k4::BandParams qs = q;
-                    qs.ustride_cta = frx_k4::ScalarGeo::ustride(n);
-                    qs.fail_list = (int32_t*)(ws + o_retry);
-                    qs.fail_count = (int32_t*)((char*)ctx->scalars + 256) + 3 * kStreamBins;
-                    rc = band_scalar_launch(ctx, qs, Ls);
-                    if (rc) return rc;
-                    q.order = qs.fail_list;
-                    q.n_sys_dev = qs.fail_count;
-                }
-                if (use_ldl_env == 2)
-                    rc = b == 0 ? band_ldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_ldl_launch<2>(ctx, q, Lf[b])
-                       : b == 2 ? band_ldl_launch<3>(ctx, q, Lf[b]) : band_ldl_launch<4>(ctx, q, Lf[b]);
-                else
-                    rc = b == 0 ? band_bldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_bldl_launch<2>(ctx, q, Lf[b])
-                       : b == 2 ? band_bldl_launch<3>(ctx, q, Lf[b]) : band_bldl_launch<4>(ctx, q, Lf[b]);
-                if (rc) return rc;
+        // the pivot-free attempt of bin b (thread per system for the narrowest bin, then the block LDL^T)
+        auto launch_attempt = [&](const int b) -> int {
+            int rc2 = FRX_OK;
+            q.n_sys = bin_count[b];
+            q.n_sys_dev = nullptr;
+            q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
+            q.nb_max = bin_nb[b];
+            if (use_ldl_env == 2)
+                q.ustride_cta = b == 0 ? frx_k4::LdlGeo<1>::ustride(n) : b == 1 ? frx_k4::LdlGeo<2>::ustride(n)
+                              : b == 2 ? frx_k4::LdlGeo<3>::ustride(n) : frx_k4::LdlGeo<4>::ustride(n);
+            else
+                q.ustride_cta = b == 0 ? frx_k4::BldlGeo<1>::ustride(n) : b == 1 ? frx_k4::BldlGeo<2>::ustride(n)
+                              : b == 2 ? frx_k4::BldlGeo<3>::ustride(n) : frx_k4::BldlGeo<4>::ustride(n);
+            q.fail_list = (int32_t*)(ws + o_fail) + bin_begin[b];
+            q.fail_count = (int32_t*)((char*)ctx->scalars + 256) + b;
+            q.refined_count = (int32_t*)((char*)ctx->scalars + 256) + kStreamBins + b;
+            q.queue = (int32_t*)((char*)ctx->scalars + 256) + 2 * kStreamBins + b;
+            if (b == 0 && use_scalar) {
+                // one thread per system first; the block LDL^T then takes the retry list (counted on the device)
+                frx_k4::BandParams qs = q;
+                qs.ustride_cta = frx_k4::ScalarGeo::ustride(n);
+                qs.fail_list = (int32_t*)(ws + o_retry);
+                qs.fail_count = (int32_t*)((char*)ctx->scalars + 256) + 3 * kStreamBins;
+                rc2 = band_scalar_launch(ctx, qs, Ls);
+                if (rc2) return rc2;
+                q.order = qs.fail_list;
+                q.n_sys_dev = qs.fail_count;
             }
+            if (use_ldl_env == 2)
+                rc2 = b == 0 ? band_ldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_ldl_launch<2>(ctx, q, Lf[b])
+                    : b == 2 ? band_ldl_launch<3>(ctx, q, Lf[b]) : band_ldl_launch<4>(ctx, q, Lf[b]);
+            else
+                rc2 = b == 0 ? band_bldl_launch<1>(ctx, q, Lf[b]) : b == 1 ? band_bldl_launch<2>(ctx, q, Lf[b])
+                    : b == 2 ? band_bldl_launch<3>(ctx, q, Lf[b]) : band_bldl_launch<4>(ctx, q, Lf[b]);
             q.fail_list = nullptr;
             q.fail_count = nullptr;
             q.refined_count = nullptr;
             q.n_sys_dev = nullptr;
-        }
-        for (int b = kStreamBins - 1; b >= 0; --b) {    // widest bands first: the longest-running CTAs start first
-            if (!bin_count[b]) continue;
+            return rc2;
+        };
+        // the pivoted kernels of bin b: every system of the bin, or (behind the attempt) its fail list, counted on the device
+        auto launch_pivoted = [&](const int b) -> int {
+            int rc2 = FRX_OK;
             q.n_sys = bin_count[b];
+            q.n_sys_dev = nullptr;
             q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
-            if (use_ldl) {                                // what the pivot-free attempt rejected, counted on the device
+            if (use_ldl) {
                 q.order = (const int32_t*)(ws + o_fail) + bin_begin[b];
                 q.n_sys_dev = (const int32_t*)((char*)ctx->scalars + 256) + b;
             }
@@ -766,18 +787,60 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                 FRX_LAUNCH(ctx, FRX_K_SOLVE,
                            frx_k4_band_stream<<<(unsigned)L[b].grid, kStreamWarps * 32, L[b].dyn, ctx->stream>>>(sp));
             } else if (L[b].kind >= 7) {
-                rc = L[b].kind == 7 ? band_packed_launch<1, 3, 8>(ctx, q, L[b]) : band_packed_launch<2, 5, 16>(ctx, q, L[b]);
-                if (rc) return rc;
+                rc2 = L[b].kind == 7 ? band_packed_launch<1, 3, 8>(ctx, q, L[b]) : band_packed_launch<2, 5, 16>(ctx, q, L[b]);
             } else if (L[b].kind >= 5) {
-                rc = L[b].kind == 5 ? band_dmma2_launch<3, 7>(ctx, q, L[b]) : band_dmma2_launch<4, 9>(ctx, q, L[b]);
-                if (rc) return rc;
+                rc2 = L[b].kind == 5 ? band_dmma2_launch<3, 7>(ctx, q, L[b]) : band_dmma2_launch<4, 9>(ctx, q, L[b]);
             } else {
-                rc = L[b].kind == 1 ? band_dmma_launch<1, 3>(ctx, q, L[b])
-                   : L[b].kind == 2 ? band_dmma_launch<2, 5>(ctx, q, L[b])
-                   : L[b].kind == 3 ? band_dmma_launch<3, 7>(ctx, q, L[b])
-                                    : band_dmma_launch<4, 9>(ctx, q, L[b]);
+                rc2 = L[b].kind == 1 ? band_dmma_launch<1, 3>(ctx, q, L[b])
+                    : L[b].kind == 2 ? band_dmma_launch<2, 5>(ctx, q, L[b])
+                    : L[b].kind == 3 ? band_dmma_launch<3, 7>(ctx, q, L[b])
+                                     : band_dmma_launch<4, 9>(ctx, q, L[b]);
+            }
+            q.n_sys_dev = nullptr;
+            return rc2;
+        };
+        if (use_ldl)
+            FRX_CUDA(cudaMemsetAsync((char*)ctx->scalars + 256, 0, sizeof(int32_t) * (3 * kStreamBins + 1), ctx->stream));
+        if (concurrent) {
+            rc = frx_bin_streams(ctx);
+            if (rc) return rc;
+            // with per-kernel timing on, the fork-to-join region is ONE timed interval of the context's stream
+            rc = frx_timing_begin(ctx, FRX_K_SOLVE);
+            if (rc) return rc;
+            struct Restore {       // the context's stream and timing flag come back on every exit path
+                frx_ctx* c; cudaStream_t s; int t;
+                ~Restore() { c->stream = s; c->timing = t; }
+            } restore{ctx, ctx->stream, ctx->timing};
+            cudaStream_t main_stream = ctx->stream;
+            FRX_CUDA(cudaEventRecord(ctx->bin_fork, main_stream));
+            ctx->timing = 0;
+            for (int b = kStreamBins - 1; b >= 0; --b) {    // widest bands first: the longest-running CTAs start first
+                if (!bin_count[b]) continue;
+                FRX_CUDA(cudaStreamWaitEvent(ctx->bin_stream[b], ctx->bin_fork, 0));
+                ctx->stream = ctx->bin_stream[b];
+                q.uscratch = (double*)((char*)ctx->io + bin_off[b]);
+                rc = launch_attempt(b);
+                if (rc) return rc;
+                rc = launch_pivoted(b);
+                if (rc) return rc;
+                FRX_CUDA(cudaEventRecord(ctx->bin_join[b], ctx->bin_stream[b]));
+                FRX_CUDA(cudaStreamWaitEvent(main_stream, ctx->bin_join[b], 0));
+            }
+            ctx->stream = main_stream;
+            ctx->timing = restore.t;
+            return frx_timing_end(ctx);
+        }
+        if (use_ldl) {
+            for (int b = kStreamBins - 1; b >= 0; --b) {
+                if (!bin_count[b]) continue;
+                rc = launch_attempt(b);
                 if (rc) return rc;
             }
+        }
+        for (int b = kStreamBins - 1; b >= 0; --b) {    // widest bands first: the longest-running CTAs start first
+            if (!bin_count[b]) continue;
+            rc = launch_pivoted(b);
+            if (rc) return rc;
         }
         return FRX_OK;
     }
@@ -838,7 +901,7 @@ extern "C" int frx_assemble_solve_host(frx_ctx* ctx, int rule, int64_t n_sys, in
         return FRX_ERR_INVALID_ARG;
     }
     return solve_common(ctx, rule, n_sys, n, h_alpha, h_h, h_res, (const double*)at_b.devicePointer, ldb,
-                        (double*)at_x.devicePointer, ldx, nullptr, nullptr);
+                        (double*)at_x.devicePointer, ldx, nullptr, nullptr, /*host_io=*/true);
 }
 
 extern "C" int frx_assemble_dense(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,

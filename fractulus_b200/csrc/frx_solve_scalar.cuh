@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(32) frx_k4_band_scalar(const BandParams p) {
     using G = ScalarGeo;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int W = G::W;
-    __shared__ double tile[G::TILE];
+    __shared__ double tiles[2 * G::TILE];            // right-hand-side entries 32t .. 32t + 31 of the 32 systems in tiles[(t & 1) * TILE]
+    double* const tile = tiles;                        // (the backward pass stages the solutions in the first one)
     const int lane = threadIdx.x, n = p.n, npad = G::npad(n);
     double* U = p.uscratch + (int64_t)blockIdx.x * p.ustride_cta + lane;
 #pragma unroll 1
@@ -63,24 +64,34 @@ __global__ void __launch_bounds__(32) frx_k4_band_scalar(const BandParams p) {
             for (int j = 0; j <= i; ++j) Wd[G::tri(i, j)] = i < n ? a[i - j] : (i == j ? sgn : 0.0);
         int piv_min = 0x7ff00000;
         double r_last = 0.0;
+        // 32 entries of the 32 right-hand sides -> one tile: 32 asynchronous 8-byte copies per lane, all in flight at once
+        // (row r = system r, 256 contiguous bytes; zero beyond n and for idle lanes)
+        auto issue_tile = [&](const int t) {
+            double* dst = tiles + (t & 1) * G::TILE + lane * 33;
+            const int c = 32 * t + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const int64_t rb = __shfl_sync(FULL, row_b, r);
+                if (r < n_live && c < n) cp_async8(dst + r, p.rhs + rb + c);
+                else dst[r] = 0.0;
+            }
+        };
+        __syncwarp();
+        issue_tile(0);
+        cp_async_wait_all();
+        __syncwarp();
+        issue_tile(1);                                                    // travels while the first 24 columns are eliminated
 #pragma unroll
-        for (int i = 0; i < W; ++i) bw[i] = (live && i < n) ? p.rhs[row_b + i] : 0.0;
+        for (int i = 0; i < W; ++i) bw[i] = tiles[i * 33 + lane];
         // ---- forward ------------------------------------------------------------------------------------------------
 #pragma unroll 1
         for (int k0 = 0; k0 < npad; k0 += 8) {
-            if ((k0 & 31) == 0) {           // entries k0 + 8 .. k0 + 39 of the 32 right-hand sides: what columns k0 .. k0 + 31 let in
-                __syncwarp();
-                // 32 asynchronous 8-byte copies per lane, all in flight at once (row r of the tile = system r, 256 bytes)
-                const int c = k0 + 8 + lane;
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const int64_t rb = __shfl_sync(FULL, row_b, r);
-                    if (r < n_live && c < n) cp_async8(tile + lane * 33 + r, p.rhs + rb + c);
-                    else tile[lane * 33 + r] = 0.0;
-                }
+            if ((k0 & 31) == 24) {          // columns from here on let in entries of the next tile; the one before it is dead
                 cp_async_wait_all();
                 __syncwarp();
+                issue_tile((k0 >> 5) + 2);
             }
+            const double* tin = tiles + (((k0 + 8) >> 5) & 1) * G::TILE + lane;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
                 const int k = k0 + kk;
@@ -111,12 +122,14 @@ __global__ void __launch_bounds__(32) frx_k4_band_scalar(const BandParams p) {
 #pragma unroll
                 for (int j = 1; j < W; ++j) Wd[G::tri(kk, (kk + j) & 7)] = in ? a[W - j] : 0.0;
                 Wd[G::tri(kk, kk)] = in ? a[0] : sgn;
-                bw[kk] = tile[(k & 31) * 33 + lane];                     // right-hand side entry k + 8 (zero beyond n)
+                bw[kk] = tin[((k + 8) & 31) * 33];                       // right-hand side entry k + 8 (zero beyond n)
             }
         }
         // a pivot p with p * sgn(a_0) <= 1e-300 (0x01a56e1f = high word of 1e-300) marks the system as not definite; a NaN
         // (or infinite) pivot passes that integer test but poisons every later column: the last reciprocal shows it
         const bool ok = piv_min > 0x01a56e1f && r_last == r_last;
+        cp_async_wait_all();                                              // (a tile beyond the last column may still be in flight)
+        __syncwarp();
         // ---- backward ------------------------------------------------------------------------------------------------
         double xw[W];                                                     // x_{k+1 .. k+7} at the residues mod 8
 #pragma unroll

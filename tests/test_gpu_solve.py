@@ -123,6 +123,17 @@ def test_solve_errors():
         batched.assemble_solve('simpson', [0.5], 0.1, 3, rhs)     # odd Simpson stencil is not symmetric-closed
 
 
+def _same_bits_beyond_the_narrowest_bin(host, dev, res):
+    """Page-locked host buffers used IN PLACE give the device call's bits, except for the systems of the narrowest band
+    bin (nb = res + 1 <= 7): on device buffers those are first tried by the thread-per-system kernel
+    (frx_k4_band_scalar), which the in-place host form leaves out (FRX_K4_SCALAR=2 turns it on there too); both
+    eliminations are pivot-free LDL^T of the same matrix in a different order, so the solutions agree to rounding."""
+    wide = np.asarray(res) + 1 > 7
+    assert np.array_equal(host[wide], dev[wide])
+    scale = np.abs(dev[~wide]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(host[~wide] - dev[~wide]) <= 1e-10 * scale)
+
+
 def test_host_buffer_forms_equal_device_calls():
     """batched.assemble_solve_host (pageable buffers: chunked, copies overlapped with the kernels; page-locked buffers: used
     in place by the kernels) and toeplitz_apply_host = the device calls."""
@@ -140,7 +151,8 @@ def test_host_buffer_forms_equal_device_calls():
     got2 = batched.assemble_solve_host('caputo', alpha, h, res, rhs_pin, out=out, chunk=700)
     assert np.shares_memory(got2, out)
     # (per-chunk batches bin the systems differently, the arithmetic per system is the same)
-    assert np.array_equal(got, want) and np.array_equal(got2, want)
+    assert np.array_equal(got, want)
+    _same_bits_beyond_the_narrowest_bin(got2, want, res)
     N, B = 1500, 37
     G = rng.standard_normal((B, N + 2))
     Yd = batched.toeplitz_apply('caputo', 0.4, 1. / N, torch.as_tensor(G, device='cuda'), N=N).cpu().numpy()
@@ -169,5 +181,5 @@ def test_assemble_solve_host_entry_point_needs_page_locked_buffers():
     assert rc == 0
     ctx.synchronize()
     want = batched.assemble_solve('caputo', alpha, hh, rr, torch.as_tensor(rhs, device='cuda')).cpu().numpy()
-    assert np.array_equal(out_pin, want)
+    _same_bits_beyond_the_narrowest_bin(out_pin, want, rr)
 
