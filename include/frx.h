@@ -218,11 +218,14 @@ int frx_assemble_solve(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const d
                        int32_t* d_info);
 /* The same with right-hand sides and solutions in PAGE-LOCKED host memory (pinned or cudaHostRegister'ed), used in place:
  * the kernels read each right-hand side once and write each solution once over PCIe while they solve; returns when the
- * work is queued (frx_ctx_synchronize before reading h_x).  Pageable buffers: FRX_ERR_INVALID_ARG. */
+ * work is queued (frx_ctx_synchronize before reading h_x).  Pageable buffers: FRX_ERR_INVALID_ARG.
+ * Same kernels and same bits as frx_assemble_solve, except that systems of band width res + 1 <= 7 skip the
+ * thread-per-system kernel (another elimination order of the same pivot-free LDL^T: equal to rounding). */
 int frx_assemble_solve_host(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const double* h_alpha, const double* h_h,
                             const double* h_res, const double* h_rhs, int64_t ldb, double* h_x, int64_t ldx);
 /* After frx_assemble_solve: what the last call on this context did with its systems.  Every system is first factorised
- * WITHOUT pivoting (block LDL^T): a DEFINITE matrix (every pivot of the sign of the first) ends there -- elimination without
+ * WITHOUT pivoting (LDL^T: one thread per system at band width <= 7, a block LDL^T per warp above and for what the former
+ * finds indefinite): a DEFINITE matrix (every pivot of the sign of the first) ends there -- elimination without
  * interchanges is backward stable for it; an INDEFINITE one is accepted only on its residual, after at most six steps of
  * iterative refinement with the same factors:  ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||)  in max norms -- refined_per_bin
  * counts those; what fails that test is solved again by the partially pivoted band LU -- n_pivoted / pivoted_per_bin count
