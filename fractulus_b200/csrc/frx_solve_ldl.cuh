@@ -378,6 +378,11 @@ __device__ __forceinline__ double flip_sign(const double v) {
     return __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v));
 }
 
+#ifndef FRX_BLDL_PREDICT
+#define FRX_BLDL_PREDICT 0
+#endif
+constexpr bool kBldlPredict = FRX_BLDL_PREDICT != 0;      // see the sweeps of frx_k4_band_bldl
+
 // Iterative refinement of an indefinite system: at most this many steps (each ~1/3 of a factorisation; the pivoted LU that
 // takes over otherwise costs ~4 factorisations and runs at half the occupancy).  On the cfg-4 matrices every indefinite
 // system of n <= 128 passes after one step; at n = 256 two steps accept 67 %, six 89 % (tools/proto_band_bldl.py --refine).
@@ -600,15 +605,36 @@ __global__ void __launch_bounds__(32, bldl_warps_per_sm(T)) frx_k4_band_bldl(con
             // ---- minus the inverse of the diagonal tile, in place in its fragment ------------------------------------------
             // Eight SWEEPS, sweep(c): p = M[c][c];  M[i][j] -= M[i][c] M[c][j] / p;  M[i][c] = M[c][i] = M[i][c] / p;
             // M[c][c] = -1 / p.  The tile stays symmetric through all eight; after them it is -Dinv.
+            // -DFRX_BLDL_PREDICT=1 (measured, off): the NEXT pivot formed ahead of the update from the two entries it depends
+            // on, p_{c+1} = M[c+1][c+1] - M[c+1][c]^2 / p_c (both fetched with the other shuffles of sweep c), so that its
+            // reciprocal is under way while the rank-1 update of sweep c is applied -- the dependent chain pivot -> reciprocal
+            // -> update -> shuffle -> pivot shrinks by 40 %, and the kernels get 7-12 % SLOWER (1.37 -> 1.47, 1.61 -> 1.81,
+            // 1.92 -> 2.11 ms per 1e5 systems at nb <= 15 / 23 / 31): one more shuffle, multiply and FMA per sweep cost more
+            // than the chain did.  The wide bins are bound by what they issue to the FP64 pipe, not by this latency.
             double2 M = S[0][0];
+            double r_next = 0.0;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int hc = c >> 1;
                 const double own = (c & 1) ? M.y : M.x;
-                const double pv = __shfl_sync(FULL, own, c * 4 + hc);          // M[c][c]
-                // smallest pivot seen, as the high word of p * sgn(a_0) (integer order = order of the doubles there;
-                // a pivot of the other sign has the sign bit set and is negative as an integer)
-                piv_min = min(piv_min, __double2hiint(pv) ^ sgn_bit);
+                double r;
+                if (c == 0 || !kBldlPredict) {
+                    const double pv = __shfl_sync(FULL, own, c * 4 + hc);      // M[c][c]
+                    // smallest pivot seen, as the high word of p * sgn(a_0) (integer order = order of the doubles there;
+                    // a pivot of the other sign has the sign bit set and is negative as an integer)
+                    piv_min = min(piv_min, __double2hiint(pv) ^ sgn_bit);
+                    r = pivot_reciprocal(pv);
+                } else {
+                    r = r_next;
+                }
+                if (kBldlPredict && c < 7) {
+                    const int c1 = c + 1;
+                    const double dn = __shfl_sync(FULL, (c1 & 1) ? M.y : M.x, c1 * 4 + (c1 >> 1));   // M[c+1][c+1]
+                    const double bn = __shfl_sync(FULL, own, c1 * 4 + hc);                           // M[c+1][c]
+                    const double pn = fma(-(bn * bn), r, dn);
+                    piv_min = min(piv_min, __double2hiint(pn) ^ sgn_bit);
+                    r_next = pivot_reciprocal(pn);
+                }
                 const bool rowc = g == c, atc = cp == hc;
                 double dx = M.x, dy = M.y;
                 if (T == 1) {
@@ -616,7 +642,6 @@ __global__ void __launch_bounds__(32, bldl_warps_per_sm(T)) frx_k4_band_bldl(con
                     // in this lane (A = the fragment component that holds column c, k = 2cp + (c & 1);  B = -M[n][c] / p in
                     // the four lanes (n, c / 2) that own column c, zero elsewhere) -- one shuffle per sweep instead of four.
                     // Row and column c, which the DMMA leaves at ~0, are the lane's own old entries times 1 / p.
-                    const double r = pivot_reciprocal(pv);
                     const double sx = M.x * r, sy = M.y * r;
                     const double so = (c & 1) ? sy : sx;                       // M[g][c] / p
                     dmma884(dx, dy, own, atc ? flip_sign(so) : 0.0);
@@ -629,7 +654,6 @@ __global__ void __launch_bounds__(32, bldl_warps_per_sm(T)) frx_k4_band_bldl(con
                     const double f = __shfl_sync(FULL, own, (lane & ~3) | hc);  // M[g][c]
                     const double prx = __shfl_sync(FULL, M.x, c * 4 + cp);     // M[c][2cp]
                     const double pry = __shfl_sync(FULL, M.y, c * 4 + cp);     // M[c][2cp+1]
-                    const double r = pivot_reciprocal(pv);
                     const double px = prx * r, py = pry * r, fr = f * r;
                     dx = rowc ? px : fma(-f, px, dx);
                     dy = rowc ? py : fma(-f, py, dy);
