@@ -49,13 +49,11 @@ extern "C" int frx_ctx_create(int device, frx_ctx** out) {
     cudaError_t e = guard.err;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc(&c->scalars, 512);   // [0, 256): by-value scalars; [256, 512): K4's fail counters
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->hstage_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->switch_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaGetLastError();
         frx_set_error("context creation on device %d failed: %s", device, cudaGetErrorString(e));
         if (c->scalars) cudaFree(c->scalars);
-        if (c->hstage_ev) cudaEventDestroy(c->hstage_ev);
         if (c->switch_ev) cudaEventDestroy(c->switch_ev);
         free(c);
         return FRX_ERR_CUDA;
@@ -70,10 +68,15 @@ extern "C" int frx_ctx_destroy(frx_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->scalars) cudaFree(ctx->scalars);
-    if (ctx->hstage) cudaFreeHost(ctx->hstage);
-    if (ctx->hstage_ev) cudaEventDestroy(ctx->hstage_ev);
     if (ctx->switch_ev) cudaEventDestroy(ctx->switch_ev);
     if (ctx->bin_fork) cudaEventDestroy(ctx->bin_fork);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->k4_hst[k]) cudaFreeHost(ctx->k4_hst[k]);
+        if (ctx->k4_img[k]) cudaFree(ctx->k4_img[k]);
+        if (ctx->k4_copied[k]) cudaEventDestroy(ctx->k4_copied[k]);
+        if (ctx->k4_done[k]) cudaEventDestroy(ctx->k4_done[k]);
+    }
+    if (ctx->k4_copy_stream) cudaStreamDestroy(ctx->k4_copy_stream);
     for (int b = 0; b < 4; ++b) {
         if (ctx->bin_join[b]) cudaEventDestroy(ctx->bin_join[b]);
         if (ctx->bin_stream[b]) cudaStreamDestroy(ctx->bin_stream[b]);
@@ -122,36 +125,6 @@ extern "C" int frx_host_unregister(void* h_ptr) {
     return FRX_OK;
 }
 
-int frx_hstage_reserve(frx_ctx* ctx, size_t bytes) {
-    FRX_ON_DEVICE(ctx);
-    if (ctx->hstage_pending) {
-        FRX_CUDA(cudaEventSynchronize(ctx->hstage_ev));
-        ctx->hstage_pending = 0;
-    }
-    if (bytes <= ctx->hstage_bytes) return FRX_OK;
-    if (ctx->hstage) {
-        FRX_CUDA(cudaFreeHost(ctx->hstage));
-        ctx->hstage = nullptr;
-        ctx->hstage_bytes = 0;
-    }
-    const size_t want = frx_align_up(bytes + bytes / 8, (size_t)1 << 16);
-    cudaError_t e = cudaMallocHost(&ctx->hstage, want);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        ctx->hstage = nullptr;
-        frx_set_error("pinned staging allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
-        return FRX_ERR_ALLOC;
-    }
-    ctx->hstage_bytes = want;
-    return FRX_OK;
-}
-
-int frx_hstage_release(frx_ctx* ctx) {
-    FRX_CUDA(cudaEventRecord(ctx->hstage_ev, ctx->stream));
-    ctx->hstage_pending = 1;
-    return FRX_OK;
-}
-
 extern "C" int frx_ctx_synchronize(frx_ctx* ctx) {
     FRX_REQUIRE(ctx != nullptr, FRX_ERR_INVALID_ARG, "ctx is NULL");
     FRX_ON_DEVICE(ctx);
@@ -184,6 +157,80 @@ extern "C" int frx_solve_stats(frx_ctx* ctx, int64_t* n_systems, int64_t* n_pivo
         if (pivoted_per_bin) pivoted_per_bin[b] = cnt[b];
         if (refined_per_bin) refined_per_bin[b] = cnt[4 + b];
     }
+    return FRX_OK;
+}
+
+// ---- K4's parameter image: two pinned host blocks, two device blocks, one copy stream -------------------------------
+// Call i fills host block i & 1, uploads it on the copy stream into device block i & 1 and makes the context's stream wait
+// for that copy only.  The copy itself waits for the kernels of call i - 2 (the last readers of that device block), not for
+// those of call i - 1: it runs under them.  (One block on each side put 4.4 MB of upload, ~0.1 ms, between the kernels of
+// consecutive 1e5-system calls.)
+int frx_k4_stage_begin(frx_ctx* ctx, size_t bytes, int* slot, void** host_image) {
+    const int k = (int)(ctx->k4_calls & 1u);
+    *slot = k;
+    if (ctx->k4_copied_pending[k]) {             // the copy that last read this host block
+        FRX_CUDA(cudaEventSynchronize(ctx->k4_copied[k]));
+        ctx->k4_copied_pending[k] = 0;
+    }
+    if (bytes > ctx->k4_hst_bytes[k]) {
+        if (ctx->k4_hst[k]) {
+            FRX_CUDA(cudaFreeHost(ctx->k4_hst[k]));
+            ctx->k4_hst[k] = nullptr;
+            ctx->k4_hst_bytes[k] = 0;
+        }
+        const size_t want = frx_align_up(bytes + bytes / 8, (size_t)1 << 16);
+        cudaError_t e = cudaMallocHost(&ctx->k4_hst[k], want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ctx->k4_hst[k] = nullptr;
+            frx_set_error("pinned staging allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return FRX_ERR_ALLOC;
+        }
+        ctx->k4_hst_bytes[k] = want;
+    }
+    *host_image = ctx->k4_hst[k];
+    return FRX_OK;
+}
+
+int frx_k4_stage_upload(frx_ctx* ctx, int k, size_t bytes, void** device_image) {
+    if (!ctx->k4_copy_stream) {
+        FRX_CUDA(cudaStreamCreateWithFlags(&ctx->k4_copy_stream, cudaStreamNonBlocking));
+        for (int j = 0; j < 2; ++j) {
+            FRX_CUDA(cudaEventCreateWithFlags(&ctx->k4_copied[j], cudaEventDisableTiming));
+            FRX_CUDA(cudaEventCreateWithFlags(&ctx->k4_done[j], cudaEventDisableTiming));
+        }
+    }
+    if (bytes > ctx->k4_img_bytes[k]) {
+        if (ctx->k4_img[k]) {                    // its last readers must be through before it goes
+            if (ctx->k4_done_recorded[k]) FRX_CUDA(cudaEventSynchronize(ctx->k4_done[k]));
+            FRX_CUDA(cudaFree(ctx->k4_img[k]));
+            ctx->k4_img[k] = nullptr;
+            ctx->k4_img_bytes[k] = 0;
+        }
+        const size_t want = frx_align_up(bytes + bytes / 8, (size_t)1 << 16);
+        cudaError_t e = cudaMalloc(&ctx->k4_img[k], want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ctx->k4_img[k] = nullptr;
+            frx_set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return FRX_ERR_ALLOC;
+        }
+        ctx->k4_img_bytes[k] = want;
+    }
+    if (ctx->k4_done_recorded[k]) FRX_CUDA(cudaStreamWaitEvent(ctx->k4_copy_stream, ctx->k4_done[k], 0));
+    FRX_CUDA(cudaMemcpyAsync(ctx->k4_img[k], ctx->k4_hst[k], bytes, cudaMemcpyHostToDevice, ctx->k4_copy_stream));
+    FRX_CUDA(cudaEventRecord(ctx->k4_copied[k], ctx->k4_copy_stream));
+    ctx->k4_copied_pending[k] = 1;
+    FRX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->k4_copied[k], 0));
+    *device_image = ctx->k4_img[k];
+    return FRX_OK;
+}
+
+// after the last kernel of the call that reads device block `k` has been queued on the context's stream
+int frx_k4_stage_done(frx_ctx* ctx, int k) {
+    FRX_CUDA(cudaEventRecord(ctx->k4_done[k], ctx->stream));
+    ctx->k4_done_recorded[k] = 1;
+    ctx->k4_calls += 1;
     return FRX_OK;
 }
 

@@ -21,14 +21,19 @@ struct frx_ctx {
     void* scalars;         // 256 bytes of device memory for by-value scalar arguments, then K4's four fail counters
     int64_t k4_n_sys;      // systems of the last frx_assemble_solve (-1: none yet), k4_ldl: it went through the pivot-free attempt
     int k4_ldl;
-    // grow-only pinned host staging block for batches of host-side parameters (frx_hstage_reserve / _release):
-    // filled by the host, uploaded with one async copy, reused only after the event behind that copy has fired
-    void* hstage;
-    size_t hstage_bytes;
-    cudaEvent_t hstage_ev;
-    int hstage_pending;
     // cross-stream ordering: everything this context has queued is ordered before work on a newly set stream
     cudaEvent_t switch_ev;
+    // K4: the per-call image of the host-side parameters (settings, row pointers, bin order), double-buffered on both
+    // sides and uploaded on a copy stream, so that the upload of call i+1 runs under the kernels of call i
+    // (frx_k4_stage_begin / _upload / _done)
+    void* k4_hst[2];
+    size_t k4_hst_bytes[2];
+    void* k4_img[2];
+    size_t k4_img_bytes[2];
+    cudaEvent_t k4_copied[2], k4_done[2];
+    int k4_copied_pending[2], k4_done_recorded[2];
+    cudaStream_t k4_copy_stream;
+    unsigned k4_calls;
     // K4: one stream per band-width bin, forked from / joined to `stream` inside frx_assemble_solve (frx_bin_streams)
     cudaStream_t bin_stream[4];
     cudaEvent_t bin_fork, bin_join[4];
@@ -41,6 +46,10 @@ struct frx_ctx {
     int64_t k_calls[FRX_K_COUNT];
 };
 
+// the double-buffered parameter image of K4 (see frx_ctx)
+int frx_k4_stage_begin(frx_ctx* ctx, size_t bytes, int* slot, void** host_image);
+int frx_k4_stage_upload(frx_ctx* ctx, int slot, size_t bytes, void** device_image);
+int frx_k4_stage_done(frx_ctx* ctx, int slot);
 // creates the bin streams and their events on first use
 int frx_bin_streams(frx_ctx* ctx);
 // a kernel launch bracketed by events when timing is on; counts the launch either way
@@ -82,8 +91,6 @@ int frx_ws_reserve(frx_ctx* ctx, size_t bytes);
 int frx_io_reserve(frx_ctx* ctx, size_t bytes);
 // pinned staging: reserve waits for the previous upload out of the block (if any) and grows it; release records the
 // event after the caller has queued its copy on ctx->stream
-int frx_hstage_reserve(frx_ctx* ctx, size_t bytes);
-int frx_hstage_release(frx_ctx* ctx);
 // host-side domain check of one Settings triple against the reference's behaviour
 int frx_check_settings(int rule, double alpha, double resolution);
 int frx_check_rule_alpha(int rule, double alpha);

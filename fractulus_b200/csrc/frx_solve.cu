@@ -23,6 +23,7 @@
 // band layout (3*nb+1 rows per column) whenever that is smaller than dense, and the elimination skips the
 // structurally-zero part of the trailing matrix: n = 256, res = 32 fits in 205 KB of shared memory.
 // Algorithmic bytes per system: 8*(2*res+1) weights + 8n rhs in, 8n solution out.
+#include <chrono>
 #include <math.h>
 #include <stdlib.h>
 
@@ -528,6 +529,11 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     FRX_REQUIRE(h_alpha && h_h && h_res, FRX_ERR_INVALID_ARG, "NULL parameter array");
     FRX_REQUIRE(d_dense || (d_rhs && d_x && ldb >= n && ldx >= n), FRX_ERR_INVALID_ARG, "NULL buffer or bad leading dimension");
     FRX_ON_DEVICE(ctx);
+    // FRX_K4_HOST_PROFILE=1: host microseconds of this call by phase, on stderr
+    static const bool host_profile = getenv("FRX_K4_HOST_PROFILE") && atoi(getenv("FRX_K4_HOST_PROFILE"));
+    auto t_now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = host_profile ? t_now() : 0.0;
+    double t_stage = 0.0, t_pass = 0.0, t_k5 = 0.0, t_geo = 0.0;
     if (!d_dense) {
         ctx->k4_n_sys = n_sys;
         ctx->k4_ldl = 0;
@@ -538,9 +544,12 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     const size_t o_wptr = frx_align_up(sizeof(double) * 4 * (size_t)n_sys, 256);
     const size_t o_order = o_wptr + frx_align_up(sizeof(int64_t) * (size_t)(n_sys + 1), 256);
     const size_t stage_bytes = o_order + frx_align_up(sizeof(int32_t) * (size_t)n_sys, 256);
-    int rc = frx_hstage_reserve(ctx, stage_bytes);
+    int slot = 0;
+    void* host_image = nullptr;
+    int rc = frx_k4_stage_begin(ctx, stage_bytes, &slot, &host_image);
     if (rc) return rc;
-    char* hs = (char*)ctx->hstage;
+    if (host_profile) t_stage = t_now();
+    char* hs = (char*)host_image;
     double* s_par = (double*)(hs + o_par);
     int64_t* wptr = (int64_t*)(hs + o_wptr);
     int32_t* h_order = (int32_t*)(hs + o_order);
@@ -549,7 +558,9 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     int bin_nb[kStreamBins] = {0, 0, 0, 0};
     wptr[0] = 0;
     int max_store = 0, max_res = 0;
-    // (the common case inline: the full check -- and its error text -- only for a setting the quick test does not pass)
+    // (the common case inline: the full check -- and its error text -- only for a setting the quick test does not pass;
+    // 0.6-0.7 ms per 1e5 systems on one core of the GPU box.  Measured and dropped: the pass in chunks on 4-8 threads, 1.5 ms;
+    // non-temporal stores for the image, 0.82 ms)
     const double alpha_max = rule == FRX_RULE_RECTANGLE ? 1.0 : 2.0, res_min = rule == FRX_RULE_CAPUTO || rule == FRX_RULE_TRAPEZOIDAL ? 1.0 : 2.0;
     const bool quick_rule = rule >= FRX_RULE_CAPUTO && rule <= FRX_RULE_SIMPSON;
     for (int64_t s = 0; s < n_sys; ++s) {
@@ -589,11 +600,12 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         int64_t fill[kStreamBins] = {bin_begin[0], bin_begin[1], bin_begin[2], bin_begin[3]};
         for (int64_t s = 0; s < n_sys; ++s) h_order[fill[bin_of((int)((wptr[s + 1] - wptr[s] - 1) / 2) + 1)]++] = (int32_t)s;
     }
+    if (host_profile) t_pass = t_now();
     const int64_t total_w = wptr[n_sys];
     const int a_len = (2 * (max_res + 1) + 1 + 1) & ~1;
     const size_t smem = sizeof(double) * ((size_t)((max_store + 1) & ~1) + n + a_len) + sizeof(int) * (size_t)(n + 4);
-    // workspace: [staging image][rc weights][K5 scalars]
-    size_t off = stage_bytes;
+    // workspace: [rc weights][K5 scalars][fail lists]
+    size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += frx_align_up(bytes, 256); return o; };
     const size_t o_w = carve(sizeof(double) * (size_t)total_w);
     extern size_t frx_k5_scratch_bytes(int64_t);
@@ -603,16 +615,23 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     rc = frx_ws_reserve(ctx, off);
     if (rc) return rc;
     char* ws = (char*)ctx->ws;
-    double* d_par = (double*)(ws + o_par);
-    FRX_CUDA(cudaMemcpyAsync(ws, hs, stage_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = frx_hstage_release(ctx);     // event after the copy: the staging block is reused only once it has been read
+    // the image travels on the context's copy stream into the device block of this call's parity; this stream waits for it
+    void* device_image = nullptr;
+    rc = frx_k4_stage_upload(ctx, slot, stage_bytes, &device_image);
     if (rc) return rc;
+    struct StageDone {      // whatever path the call takes from here: the block's readers end with what this call queues
+        frx_ctx* c; int k;
+        ~StageDone() { frx_k4_stage_done(c, k); }
+    } stage_done{ctx, slot};
+    char* img = (char*)device_image;
+    double* d_par = (double*)(img + o_par);
     // K5 for the whole batch (row pointer already on the device)
     extern int frx_launch_stencil_weights(frx_ctx*, int, int, int64_t, const double*, const double*, const double*,
                                           const int64_t*, int64_t, void*, int32_t*, double*);
     rc = frx_launch_stencil_weights(ctx, rule, FRX_SIDE_RIESZ_CAPUTO, n_sys, d_par, d_par + n_sys, d_par + 2 * n_sys,
-                                    (const int64_t*)(ws + o_wptr), total_w, ws + o_k5, nullptr, (double*)(ws + o_w));
+                                    (const int64_t*)(img + o_wptr), total_w, ws + o_k5, nullptr, (double*)(ws + o_w));
     if (rc) return rc;
+    if (host_profile) t_k5 = t_now();
     // FRX_K4_VARIANT: 1 = CTA-per-system kernel for everything, 2 = column-at-a-time warp kernel for every bin;
     // FRX_K4_DMMA_BINS: bit b set = bin b runs the blocked tensor-core kernel (default: see kDefaultDmmaBins)
     static const int variant = getenv("FRX_K4_VARIANT") ? atoi(getenv("FRX_K4_VARIANT")) : 0;
@@ -637,7 +656,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
         frx_k4::BandParams q;
         q.n = n;
         q.rcw = (const double*)(ws + o_w);
-        q.wptr = (const int64_t*)(ws + o_wptr);
+        q.wptr = (const int64_t*)(img + o_wptr);
         q.h = d_par + 3 * n_sys;
         q.rhs = d_rhs;
         q.ldb = ldb;
@@ -722,6 +741,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
                 io_total += frx_align_up(bin_scratch[b], 256);
             }
         }
+        if (host_profile) t_geo = t_now();
         rc = frx_io_reserve(ctx, io_total);    // factor scratch of the resident systems (each warp reuses its slab)
         if (rc) return rc;
         q.uscratch = (double*)ctx->io;
@@ -731,7 +751,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             int rc2 = FRX_OK;
             q.n_sys = bin_count[b];
             q.n_sys_dev = nullptr;
-            q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
+            q.order = (const int32_t*)(img + o_order) + bin_begin[b];
             q.nb_max = bin_nb[b];
             if (use_ldl_env == 2)
                 q.ustride_cta = b == 0 ? frx_k4::LdlGeo<1>::ustride(n) : b == 1 ? frx_k4::LdlGeo<2>::ustride(n)
@@ -771,7 +791,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             int rc2 = FRX_OK;
             q.n_sys = bin_count[b];
             q.n_sys_dev = nullptr;
-            q.order = (const int32_t*)(ws + o_order) + bin_begin[b];
+            q.order = (const int32_t*)(img + o_order) + bin_begin[b];
             if (use_ldl) {
                 q.order = (const int32_t*)(ws + o_fail) + bin_begin[b];
                 q.n_sys_dev = (const int32_t*)((char*)ctx->scalars + 256) + b;
@@ -828,6 +848,10 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
             }
             ctx->stream = main_stream;
             ctx->timing = restore.t;
+            if (host_profile)
+                fprintf(stderr, "frx_assemble_solve host us: wait for the host block %.0f, pass over %lld settings %.0f, upload + K5 launch %.0f, "
+                                "launch geometry %.0f, bin chains %.0f\n", t_stage - t_begin, (long long)n_sys, t_pass - t_stage,
+                        t_k5 - t_pass, t_geo - t_k5, t_now() - t_geo);
             return frx_timing_end(ctx);
         }
         if (use_ldl) {
@@ -855,7 +879,7 @@ static int solve_common(frx_ctx* ctx, int rule, int64_t n_sys, int32_t n, const 
     p.n_sys = n_sys;
     p.n = n;
     p.rcw = (const double*)(ws + o_w);
-    p.wptr = (const int64_t*)(ws + o_wptr);
+    p.wptr = (const int64_t*)(img + o_wptr);
     p.h = d_par + 3 * n_sys;
     p.rhs = d_rhs;
     p.ldb = ldb;

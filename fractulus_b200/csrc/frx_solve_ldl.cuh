@@ -378,6 +378,11 @@ __device__ __forceinline__ double flip_sign(const double v) {
     return __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v));
 }
 
+// panels per trip of the factorisation loop (the tile renaming at its back edge costs ~40 moves per trip at T = 4)
+#ifndef FRX_BLDL_PANEL_UNROLL
+#define FRX_BLDL_PANEL_UNROLL 1
+#endif
+constexpr int kBldlPanelUnroll = FRX_BLDL_PANEL_UNROLL;
 #ifndef FRX_BLDL_PREDICT
 #define FRX_BLDL_PREDICT 0
 #endif
@@ -596,7 +601,7 @@ __global__ void __launch_bounds__(32, bldl_warps_per_sm(T)) frx_k4_band_bldl(con
         int piv_min = 0x7ff00000;
         bool nan_seen = false;
         const int sgn_bit = apad[OFF] < 0.0 ? (int)0x80000000 : 0;
-#pragma unroll 1
+#pragma unroll kBldlPanelUnroll
         for (int pnl = 0; pnl < n_panels; ++pnl) {
             const int k0 = pnl * 8;
             const bool edge = k0 + 8 * T + 8 > n;
