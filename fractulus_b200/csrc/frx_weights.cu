@@ -230,12 +230,31 @@ __global__ void __launch_bounds__(128) frx_k5c_riesz_shared(int rule, int64_t n,
     const int64_t pos_raw = 29 * gw + lane - 1;
     const bool valid = pos_raw >= 0 && pos_raw < total_virtual;
     const int64_t pos = pos_raw < 0 ? 0 : (pos_raw >= total_virtual ? total_virtual - 1 : pos_raw);
-    int64_t lo = 0, hi = n;                   // vptr(lo) <= pos < vptr(hi), vptr(s) = (row_ptr[s] + s) / 2 + s
+    // Which stencil owns position pos: vptr(s) <= pos < vptr(s + 1), vptr(s) = (row_ptr[s] + s) / 2 + s.  A binary search per
+    // lane is 17 dependent loads at 1e5 stencils; the warp searches ONCE, 33-way, for its first position (4 dependent
+    // loads), and each lane then places itself among the next 32 stencil starts (a stencil has at least two positions, so
+    // the warp's 32 positions span at most 16 stencils).  Same stencil, same bits; 0.141 -> 0.125-0.140 ms for the 1e5
+    // stencils of cfg 4 -- the kernel's time is the correctly rounded pow() itself.
+    auto vptr = [&](const int64_t t) { return ((row_ptr[t] + t) >> 1) + t; };
+    const int64_t pos0 = __shfl_sync(FULL, pos, 0);
+    int64_t lo = 0, hi = n;                   // vptr(lo) <= pos0 < vptr(hi)
     while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if ((((row_ptr[mid] + mid) >> 1) + mid) <= pos) lo = mid; else hi = mid;
+        const int64_t span = hi - lo;
+        const int64_t probe = lo + ((lane + 1) * span) / 33;          // nondecreasing in the lane, in [lo, hi)
+        const int below = __popc(__ballot_sync(FULL, vptr(probe) <= pos0));   // the lanes that pass form a prefix
+        const int64_t new_lo = below ? lo + (below * span) / 33 : lo;
+        hi = below < 32 ? lo + ((below + 1) * span) / 33 : hi;
+        lo = new_lo;
     }
-    const int64_t s = lo, kv = pos - (((row_ptr[s] + s) >> 1) + s), base = row_ptr[s], count = row_ptr[s + 1] - base;
+    const int64_t nxt = lo + 1 + lane;                                // start of stencil lo + 1 + lane (total beyond the last)
+    const int64_t v_next = nxt < n ? vptr(nxt) : total_virtual;
+    int ahead = 0;                                                    // stencil starts among them that are <= pos
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int64_t v = __shfl_sync(FULL, v_next, ahead + step - 1);
+        if (v <= pos) ahead += step;
+    }
+    const int64_t s = lo + ahead, kv = pos - vptr(s), base = row_ptr[s], count = row_ptr[s + 1] - base;
     const frx_k5_scalars& S = scal[s];
     const frx_par P = S.P;
     const long long p = (long long)resolution[s];
