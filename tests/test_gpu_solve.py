@@ -211,3 +211,41 @@ def test_large_batch_equals_small_batches_and_reports_the_first_invalid_setting(
     hh[20000] = 0.
     with pytest.raises(ValueError):
         batched.assemble_solve('caputo', alpha, hh, res, rhs)
+
+
+def test_kernel_selection_switches_agree():
+    """The diagnostic switches select other kernel paths for the same systems (the library reads them once per process, so
+    each runs in its own interpreter): one stream instead of concurrent bin chains and another queueing order give the
+    default's bits; without the thread-per-system kernel, or with the pivoted LU for everything, the solutions agree within
+    the solve's accuracy contract (1e-12 + 20 eps cond(A), here through a relative bound on well-conditioned systems)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from fractulus_b200 import batched\n"
+        "rng = np.random.default_rng(7)\n"
+        "n, n_sys = 40, 3000\n"
+        "alpha = rng.uniform(0.1, 0.9, n_sys); res = rng.integers(1, 31, n_sys).astype(np.float64)\n"
+        "rhs = torch.as_tensor(rng.standard_normal((n_sys, n)), device='cuda')\n"
+        "x = batched.assemble_solve('caputo', alpha, 1. / (n + 1), res, rhs)\n"
+        "np.save(sys.argv[1], x.cpu().numpy())\n" % repo)
+    outs = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, env in (('default', {}), ('one_stream', {'FRX_K4_CONCURRENT': '0'}), ('order', {'FRX_K4_BIN_ORDER': '3210'}),
+                          ('no_scalar', {'FRX_K4_SCALAR': '0'}), ('pivoted', {'FRX_K4_LDL': '0'})):
+            path = os.path.join(tmp, name + '.npy')
+            e = dict(os.environ)
+            e.update(env)
+            r = subprocess.run([sys.executable, '-c', script, path], env=e, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, (name, r.stderr[-2000:])
+            outs[name] = np.load(path)
+    ref = outs['default']
+    assert np.isfinite(ref).all()
+    assert np.array_equal(outs['one_stream'], ref) and np.array_equal(outs['order'], ref)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    for name in ('no_scalar', 'pivoted'):
+        assert np.all(np.abs(outs[name] - ref) <= 1e-9 * scale), name
