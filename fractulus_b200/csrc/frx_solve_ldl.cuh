@@ -322,10 +322,11 @@ __global__ void __launch_bounds__(32) frx_k4_band_ldl(const BandParams p) {
 // (stalls: short scoreboard 4.6 and MIO throttle 2.8 per issue) -- ~470 shared-memory wavefronts and shuffles per panel
 // for the pivot-row broadcasts, the row <-> fragment layout changes and the tile traffic.  Here no tile ever leaves the
 // DMMA C-fragment layout (lane (g, cp) holds M[g][2cp], M[g][2cp+1]):
-//   * A = L_B D_B L_B^T with unit BLOCK lower L_B: the diagonal tile D_p is inverted in place by eight Gauss-Jordan steps
-//     without pivoting on the fragment itself (per step four 64-bit shuffles: the lane's column-c entry, the pivot row's
-//     two entries, the pivot; one reciprocal, two FMAs) -- the pivots are those of the scalar LDL^T, so the definiteness
-//     test is unchanged;
+//   * A = L_B D_B L_B^T with unit BLOCK lower L_B: the diagonal tile D_p becomes MINUS its inverse in place, by eight
+//     symmetric sweeps without pivoting on the fragment itself (per sweep, T >= 2: four 64-bit shuffles -- the lane's
+//     column-c entry, the pivot row's two entries, the pivot --, one reciprocal, three multiplies, two FMAs; T = 1: one
+//     shuffle and ONE DMMA on in-lane operands) -- the pivots are those of the scalar LDL^T, so the definiteness test is
+//     unchanged;
 //   * L21(t) = A21(t) Dinv: two DMMAs per tile with A21(t) AS IT IS (a C fragment is a valid A operand when the B operand
 //     holds rows 2cp / 2cp+1 of the right factor, and Dinv is symmetric: its own fragment); the result is again a C fragment;
 //   * trailing update C(i,j) += (-L21(i)) A21(j)^T: A = the fragment just computed, B = the fragment of A21(j): two DMMAs,
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(32) frx_k4_band_ldl(const BandParams p) {
 //     with the stored -L21 fragments, the same back substitution accumulating into x), each followed by the test
 //     ||b - A x|| <= 16 eps (max|a| ||x|| + ||b||) in max norms; what fails goes to the fail list.
 // Shared memory: the coefficient vector, x, the residual and two right-hand-side buffers (the next system's rhs arrives by
-// cp.async while this one is solved).  ~100 shuffles per panel, 2T + T(T+1) DMMAs.  The explicit
+// cp.async while this one is solved).  ~100 shuffles per panel (52 at T = 1), 2T + T(T+1) DMMAs (+ 8 at T = 1).  The explicit
 // inverse of the 8 x 8 tile leaves residuals of 1e-15 on the operator's definite matrices (tools/proto_band_bldl.py checks
 // that on oracle coefficients together with the index bookkeeping).
 template <int T_>
